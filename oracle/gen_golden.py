@@ -1,0 +1,183 @@
+"""Pin the oracle against the real reference and write the golden fixtures under tests/golden/.
+
+Runs ONLY in the build container (needs /root/reference).  TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.gen_golden
+
+For every case: build ``model.MESM`` exactly as runner.py:255-298 does (Appendix B of SURVEY.md; ``runner`` itself is
+not importable here: it pulls ftfy/h5py/nltk), load ``oracle.weights.make_state_dict`` with strict=True (which also
+proves ``state_spec`` matches the reference key set and shapes), run the reference forward with
+``sample_outclass_neg`` patched to the injected neg_index, run the oracle, assert agreement, and save the REFERENCE
+outputs.  The decode chain is the reference's own ``span_cxw_to_xx`` / ``PostProcessorDETR`` / ``temporal_nms`` driven
+as eval.py:64-99,111-116,476-485 drives them.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("MESM_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+from oracle.config import CONFIGS  # noqa: E402
+from oracle import mesm_oracle, decode_oracle  # noqa: E402
+from oracle.weights import make_state_dict, make_inputs, make_neg_index, state_spec  # noqa: E402
+
+CASES = [
+    # name, config, num_clips, kwargs for make_inputs
+    ("tiny_uniform", "tiny", [1] * 6, dict(ragged_video=False, ragged_text=False)),
+    ("tiny_ragged", "tiny", [2, 1, 3, 1, 2, 4, 1, 2], dict()),
+    ("tiny_qvh_groups", "tiny_qvh", [2, 1, 3, 2], dict()),
+    ("tiny_twomlp", "tiny_twomlp", [3, 2, 4], dict()),
+    ("qvh_b6", "qvhighlights", [1] * 6, dict(ragged_video=False)),
+    ("qvh_groups", "qvhighlights", [2, 1, 2], dict()),
+    ("charades_csf_ragged", "charades_csf", [2, 3, 1, 2], dict()),
+    ("charades_vgg_l64", "charades_vgg", [2, 2, 1], dict(lv=64)),
+    ("tacos_l96", "tacos", [4, 3], dict(lv=96)),
+]
+NMS_THD = 0.7
+
+
+def build_reference(cfg):
+    from model.model import MESM
+    from model.transformer import T2VEncoder, T2VEncoder_TwoMLP, Transformer
+    from model.position_encoding import PositionEmbeddingSine, TrainablePositionalEncoding
+    kw = dict(d_model=cfg.hidden_dim, dropout=0.1, nhead=cfg.nheads, dim_feedforward=cfg.dim_feedforward,
+              normalize_before=False, activation="prelu")
+    enh = (T2VEncoder if cfg.share_mlp else T2VEncoder_TwoMLP)(num_encoder_layers=cfg.num_recfw_layers, **kw)
+    t2v = T2VEncoder(num_encoder_layers=cfg.t2v_layers, **kw)
+    tr = Transformer(num_encoder_layers=cfg.enc_layers, num_decoder_layers=cfg.dec_layers,
+                     return_intermediate_dec=True, **kw)
+    vpos = PositionEmbeddingSine(cfg.hidden_dim, normalize=True)
+    tpos = TrainablePositionalEncoding(cfg.max_words_l + 1 if cfg.rec_ss else cfg.max_words_l, cfg.hidden_dim, 0.5)
+    m = MESM(text_encoder=None, enhance_encoder=enh, t2v_encoder=t2v, transformer=tr, vid_position_embed=vpos,
+             txt_position_embed=tpos, txt_dim=cfg.t_feat_dim, vid_dim=cfg.v_feat_dim, num_queries=cfg.num_queries,
+             input_dropout=0.5, aux_loss=cfg.aux_loss, max_video_l=cfg.max_video_l, max_words_l=cfg.max_words_l,
+             normalize_txt=True, use_txt_pos=False, span_loss_type="l1", n_input_proj=cfg.n_input_proj,
+             rec_fw=cfg.rec_fw, vocab_size=cfg.vocab_size, rec_ss=cfg.rec_ss, num_recss_layers=cfg.num_recss_layers)
+    return m.eval()
+
+
+def reference_decode(logits, spans, duration, cfg, nms_thd):
+    """eval.py:64-99, 111-116, 476-485 with the reference's own utils."""
+    import torch.nn.functional as F
+    from utils import span_cxw_to_xx, PostProcessorDETR, temporal_nms
+    prob = F.softmax(logits, -1)
+    scores = prob[..., 0]
+    res = []
+    for idx, (sp, sc) in enumerate(zip(spans, scores)):
+        sp = span_cxw_to_xx(sp) * duration[idx]
+        rows = torch.cat([sp, sc[:, None]], dim=1).cpu().tolist()
+        order = sorted(range(len(rows)), key=lambda i: rows[i][2], reverse=True)
+        rows = sorted(rows, key=lambda x: x[2], reverse=True)
+        rows = [[float(f"{e:.4f}") for e in row] for row in rows]
+        res.append(dict(pred_relevant_windows=rows, order=order))
+    pp = PostProcessorDETR(clip_length=cfg.clip_len, min_ts_val=0, max_ts_val=cfg.max_ts_val, min_w_l=2, max_w_l=150,
+                           move_window_method="left",
+                           process_func_names=("clip_ts", "round_multiple") if cfg.clip_len != -1 else ("clip_ts",))
+    res = pp(res)
+    out = []
+    for r in res:
+        w = r["pred_relevant_windows"]
+        kept = temporal_nms(w[:10], nms_thd=nms_thd, max_after_nms=10)
+        out.append(dict(windows=w, order=r["order"], nms_windows=kept))
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    sys.path.insert(0, REF)
+    summary = {}
+    for name, cfg_name, num_clips, kw in CASES:
+        cfg = CONFIGS[cfg_name]
+        torch.manual_seed(0)
+        ref = build_reference(cfg)
+        sd = make_state_dict(cfg, seed=1)
+        ref_sd = ref.state_dict()
+        assert set(ref_sd) == set(sd), (sorted(set(ref_sd) ^ set(sd)))
+        for k, shp in state_spec(cfg):
+            assert tuple(ref_sd[k].shape) == tuple(shp), (k, ref_sd[k].shape, shp)
+        ref.load_state_dict(sd, strict=True)
+        inp = make_inputs(cfg, num_clips, seed=2, **kw)
+        neg = make_neg_index(num_clips, seed=3)
+        import model.model as mm
+        mm.sample_outclass_neg = lambda nc, _neg=neg: _neg
+        with torch.inference_mode():
+            ro = ref(video_feat=inp["video_feat"], video_mask=inp["video_mask"], words_id=inp["words_feat"].clone(),
+                     words_mask=None, words_weight=None, num_clips=inp["num_clips"],
+                     dataset_name=cfg.dataset_name, is_training=False)
+        oo = mesm_oracle.mesm_forward(sd, cfg, inp["video_feat"], inp["video_mask"], inp["words_feat"], inp["num_clips"],
+                                      neg_index=neg)
+        vm = inp["video_mask"]
+        errs = {}
+        for k in ("pred_logits", "pred_spans", "recon_feat", "projed_recon_feat", "projed_video_feat",
+                  "projed_words_feat", "enhanced_video_feat", "expanded_words_feat"):
+            errs[k] = float((ro[k] - oo[k]).abs().max())
+        for k in ("saliency_scores", "neg_saliency_scores"):
+            errs[k] = float(((ro[k] - oo[k]) * vm).abs().max())
+        errs["aux_logits"] = float((ro["aux_outputs"][0]["pred_logits"] - oo["aux_outputs"][0]["pred_logits"]).abs().max())
+        errs["aux_spans"] = float((ro["aux_outputs"][0]["pred_spans"] - oo["aux_outputs"][0]["pred_spans"]).abs().max())
+        assert bool((ro["expanded_words_mask"] == oo["expanded_words_mask"]).all())
+        worst = max(errs.values())
+        print(f"{name:24s} B={sum(num_clips):3d} max|ref-oracle|={worst:.2e}  " +
+              " ".join(f"{k}={v:.1e}" for k, v in errs.items() if v > 5e-6))
+        assert worst < 2e-5, errs
+        # alignment scores: reference formula (model/criterion.py:241-266) evaluated with torch on reference outputs
+        g = torch.Generator().manual_seed(11)
+        clip_mask = (torch.rand(vm.shape, generator=g) < 0.4) & vm
+        clip_mask[:, 0] = True
+        import torch.nn.functional as F
+        cm = clip_mask.unsqueeze(-1)
+        cf = (ro["projed_video_feat"] * cm).sum(1) / cm.sum(1)
+        wm = ro["expanded_words_mask"].unsqueeze(-1)
+        wf = (ro["expanded_words_feat"] * wm).sum(1) / wm.sum(1)
+        S_ref = F.normalize(cf, dim=-1, p=2) @ F.normalize(wf, dim=-1, p=2).permute(1, 0) / cfg.recss_tau
+        S_or = mesm_oracle.align_scores(oo["projed_video_feat"], clip_mask, oo["expanded_words_feat"],
+                                        oo["expanded_words_mask"], cfg.recss_tau)
+        assert float((S_ref - S_or).abs().max()) < 2e-5
+        # decode chain
+        rd = reference_decode(ro["pred_logits"], ro["pred_spans"], inp["duration"], cfg, NMS_THD)
+        win = np.array([r["windows"] for r in rd], dtype=np.float64)
+        order = np.array([r["order"] for r in rd], dtype=np.int32)
+        nms_n = np.array([len(r["nms_windows"]) for r in rd], dtype=np.int32)
+        nms_w = np.zeros((len(rd), 10, 3), dtype=np.float64)
+        for i, r in enumerate(rd):
+            nms_w[i, :nms_n[i]] = np.array(r["nms_windows"], dtype=np.float64)
+        lg, sp = ro["pred_logits"].numpy(), ro["pred_spans"].numpy()
+        for i in range(len(rd)):
+            od = decode_oracle.decode_pair(lg[i], sp[i], float(inp["duration"][i]), cfg.clip_len, cfg.max_ts_val,
+                                           NMS_THD, 10, 10)
+            assert od["order"] == rd[i]["order"], (name, i)
+            assert od["windows"] == rd[i]["windows"], (name, i, od["windows"], rd[i]["windows"])
+            assert od["nms_windows"] == rd[i]["nms_windows"], (name, i)
+        np.savez_compressed(
+            os.path.join(GOLD, f"{name}.npz"),
+            pred_logits=lg, pred_spans=sp, saliency_scores=ro["saliency_scores"].numpy(),
+            neg_saliency_scores=ro["neg_saliency_scores"].numpy(), recon_feat=ro["recon_feat"].numpy(),
+            projed_recon_feat=ro["projed_recon_feat"].numpy(),
+            aux_logits=ro["aux_outputs"][0]["pred_logits"].numpy(), aux_spans=ro["aux_outputs"][0]["pred_spans"].numpy(),
+            projed_video_row0=ro["projed_video_feat"][:, 0].numpy(), enhanced_video_row0=ro["enhanced_video_feat"][:, 0].numpy(),
+            projed_words_feat=ro["projed_words_feat"].numpy(),
+            align_clip_mask=clip_mask.numpy(), align_scores=S_ref.numpy(),
+            windows=win, order=order, nms_windows=nms_w, nms_count=nms_n, neg_index=neg.numpy())
+        summary[name] = dict(config=cfg_name, num_clips=num_clips, kwargs=kw, weight_seed=1, input_seed=2, neg_seed=3,
+                             nms_thd=NMS_THD, max_abs_ref_minus_oracle=worst)
+    # doctest vectors of utils/span_utils.py (the reference's only golden numbers), evaluated by the reference itself
+    from utils import span_utils as su
+    s1, s2 = torch.Tensor([[0, 0.2], [0.5, 1.0]]), torch.Tensor([[0, 0.3], [0., 1.0]])
+    iou, union = su.temporal_iou(s1, s2)
+    np.savez(os.path.join(GOLD, "span_utils_doctest.npz"), s1=s1.numpy(), s2=s2.numpy(), iou=iou.numpy(),
+             union=union.numpy(), giou=su.generalized_temporal_iou(s1, s2).numpy(),
+             cxw=su.span_xx_to_cxw(torch.Tensor([[0, 1], [0.2, 0.4]])).numpy(),
+             xx=su.span_cxw_to_xx(torch.Tensor([[0.5, 1.0], [0.3, 0.2]])).numpy())
+    with open(os.path.join(GOLD, "cases.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
