@@ -1,0 +1,187 @@
+/*
+ * mesm_b200 — C ABI of the B200-native (sm_100a) MESM per-pair inference path.
+ *
+ * The reference (lntzm/MESM) is pure Python/PyTorch and has no FFI surface; the drop-in boundary is therefore the set
+ * of Python call sites listed beside each entry point below (file:line in the reference repo).  `mesm_b200/` binds
+ * these symbols with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  Every `dev` pointer is device memory owned by the CALLER
+ *     (PyTorch); the library allocates device memory only inside mesm_create / mesm_load_weight (packed weights).
+ *   - All calls are stream-ordered on the `stream` argument (a cudaStream_t passed as void*), never synchronise the
+ *     device and never fall back to the CPU.  Non-zero return = error; text via mesm_last_error().
+ *   - float tensors are fp32 row-major contiguous; masks are uint8 (1 = valid), as torch.bool storage.
+ *   - One ctx per device; a ctx is not thread-safe.
+ */
+#ifndef MESM_B200_H
+#define MESM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MESM_ABI_VERSION 1
+
+typedef struct mesm_ctx mesm_ctx;
+
+/* Hyper-parameters that shape the module tree — the argparse/JSON keys of utils/config.py:26-163 that
+ * runner.py:255-298 (build_model) consumes. */
+typedef struct mesm_cfg {
+    int32_t v_feat_dim;        /* incl. the +2 tef columns (utils/config.py:242-243) */
+    int32_t t_feat_dim;
+    int32_t hidden_dim;        /* must be 256 */
+    int32_t nheads;            /* must be 8   */
+    int32_t dim_feedforward;   /* must be 1024 */
+    int32_t num_queries;       /* <= 32 (10 in every shipped config) */
+    int32_t num_recfw_layers;  /* enhance encoder (FW-MESM) */
+    int32_t t2v_layers;        /* aligner */
+    int32_t enc_layers;
+    int32_t dec_layers;
+    int32_t num_recss_layers;  /* SS-MESM reconstructor */
+    int32_t n_input_proj;      /* must be 2 */
+    int32_t rec_fw;            /* bool */
+    int32_t rec_ss;            /* bool */
+    int32_t share_mlp;         /* 0 -> T2VEncoder_TwoMLP key set for the enhance encoder (runner.py:190-210) */
+    int32_t qvh_grouping;      /* 1 -> dataset_name == "qvhighlights" branch of model/model.py:190-195, else :185-189 */
+    int32_t max_words_l;
+    int32_t max_video_l;
+} mesm_cfg;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+/* replaces runner.build_model (runner.py:255-298) + model.to(device) */
+mesm_ctx*   mesm_create(const mesm_cfg* cfg, int device);
+void        mesm_destroy(mesm_ctx* ctx);
+const char* mesm_last_error(const mesm_ctx* ctx);      /* ctx may be NULL: error of the last failed mesm_create */
+int         mesm_abi_version(void);
+
+/* replaces model.load_state_dict (eval.py:513-522).  `key` is the reference state_dict key; `data` is fp32, device
+ * (is_device=1) or host memory; shape/ndim as in the state_dict.  Unknown keys and training-only keys are accepted and
+ * ignored (returns 0).  Call mesm_finalize_weights once after the last tensor: it checks completeness and packs. */
+int mesm_load_weight(mesm_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim,
+                     int is_device, void* stream);
+int mesm_finalize_weights(mesm_ctx* ctx, void* stream);
+
+/* ---- forward: replaces MESM.forward in eval mode (model/model.py:154-359), called at eval.py:63 ---------------- */
+typedef struct mesm_inputs {
+    int32_t B;                     /* pairs = sum(num_clips) */
+    int32_t Lv;                    /* padded clip count */
+    int32_t Lt;                    /* padded word count */
+    int32_t G;                     /* video groups */
+    const float*   video_feat;     /* dev  [B,Lv,v_feat_dim] */
+    const uint8_t* video_mask;     /* dev  [B,Lv] 1 = valid */
+    const float*   words_feat;     /* dev  [B,Lt,t_feat_dim] — `words_id` of the text_encoder=None path (model.py:160-161) */
+    const int64_t* num_clips;      /* HOST [G]  (the reference calls .tolist() on it, model.py:191) */
+    const int64_t* neg_index;      /* dev  [B] or NULL: NULL skips the negative branch (model.py:260-302) */
+} mesm_inputs;
+
+/* Every pointer may be NULL (that output is then not materialised).  Shapes follow model/model.py:334-351. */
+typedef struct mesm_outputs {
+    float*   pred_logits;          /* [B,nq,2] */
+    float*   pred_spans;           /* [B,nq,2] (center,width) */
+    float*   saliency_scores;      /* [B,Lv] */
+    float*   neg_saliency_scores;  /* [B,Lv] (needs neg_index) */
+    float*   aux_logits;           /* [dec_layers-1,B,nq,2] */
+    float*   aux_spans;            /* [dec_layers-1,B,nq,2] */
+    float*   projed_video_feat;    /* [B,Lv,256] */
+    float*   enhanced_video_feat;  /* [B,Lv,256] */
+    float*   recon_feat;           /* [B,256] */
+    float*   projed_recon_feat;    /* [B,256] */
+    float*   expanded_words_feat;  /* [B,Lt+1,256]; projed_words_feat == [:,1:] */
+    uint8_t* expanded_words_mask;  /* [B,Lt+1] */
+    float*   memory;               /* [B,Lv,256]  encoder memory_local (tap) */
+    float*   memory_global;        /* [B,256] (tap) */
+    float*   hs;                   /* [dec_layers,B,nq,256] (tap) */
+} mesm_outputs;
+
+/* Bytes of caller-owned scratch mesm_forward needs for this shape (upper bound; independent of the masks). */
+size_t mesm_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t Lv, int32_t Lt, int32_t G);
+int    mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_outputs* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Pairs per internal chunk (whole video groups are never split; default 256).  Affects workspace size only. */
+int    mesm_set_chunk_pairs(mesm_ctx* ctx, int32_t pairs);
+/* Number of kernel launches the last mesm_forward issued (bench.py's gpu_launches). */
+int64_t mesm_last_launch_count(const mesm_ctx* ctx);
+
+/* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
+/* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),
+ * PostProcessorDETR as configured at eval.py:111-115 (utils/post_processing.py:22-47) and, when nms_thd != -1,
+ * post_processing_mr_nms (eval.py:476-485 -> utils/temporal_nms.py:25-74). */
+typedef struct mesm_decode_params {
+    double  clip_len;          /* -1 disables round_multiple; used in fp32 like torch does with the Python scalar */
+    double  min_ts_val;
+    double  max_ts_val;
+    double  nms_thd;           /* -1 disables NMS; compared in fp64 like utils/temporal_nms.py:52 */
+    int32_t max_before_nms;
+    int32_t max_after_nms;
+    int32_t sort_results;
+} mesm_decode_params;
+
+int mesm_decode_nms(const float* pred_logits,   /* dev [B,nq,2] */
+                    const float* pred_spans,    /* dev [B,nq,2] */
+                    const float* duration,      /* dev [B] */
+                    int32_t B, int32_t nq, const mesm_decode_params* p,
+                    double*  windows,           /* dev [B,nq,3]  ranked [st,ed,score] after post-processing */
+                    int32_t* order,             /* dev [B,nq]    query index at each rank */
+                    int32_t* keep,              /* dev [B,max_after_nms] query indices kept by NMS, -1 padded (NULL ok) */
+                    int32_t* keep_count,        /* dev [B] (NULL ok) */
+                    void* stream);
+
+/* replaces utils.temporal_nms (utils/temporal_nms.py:25-74) on ragged candidate lists:
+ * windows dev [total,3] fp64 rows [st,ed,score]; list i = rows [offsets[i], offsets[i+1]); n_i <= 1024.
+ * keep[i, :keep_count[i]] = positions (within list i) of the survivors in output order. */
+int mesm_temporal_nms(const double* windows, const int64_t* offsets, int32_t n_lists, double nms_thd,
+                      int32_t max_after_nms, int32_t* keep, int32_t* keep_count, void* stream);
+
+/* replaces utils/span_utils.py: temporal_iou (45-72), generalized_temporal_iou (92-121) on fp32 [N,2] x [M,2] -> [N,M];
+ * any output may be NULL. */
+int mesm_temporal_iou(const float* spans1, int32_t N, const float* spans2, int32_t M, float* iou, float* uni,
+                      float* giou, void* stream);
+/* span_cxw_to_xx (26-42) when to_xx != 0 else span_xx_to_cxw (5-23), n rows of 2. */
+int mesm_span_convert(const float* in, float* out, int64_t n, int to_xx, void* stream);
+
+/* ---- segment-sentence alignment scores: replaces model/criterion.py:241-266 (up to cos_sim / tau) --------------- */
+int mesm_align_scores(const float* projed_video_feat,    /* dev [B,Lv,256] */
+                      const uint8_t* clip_mask,          /* dev [B,Lv] */
+                      const float* expanded_words_feat,  /* dev [B,Lw,256] */
+                      const uint8_t* expanded_words_mask,/* dev [B,Lw] */
+                      int32_t B, int32_t Lv, int32_t Lw, float tau,
+                      float* scores,                     /* dev [B,B] */
+                      void* workspace, size_t workspace_bytes, /* >= mesm_align_workspace_bytes(B) */
+                      void* stream);
+size_t mesm_align_workspace_bytes(int32_t B);
+
+/* ---- sub-module entry points (drop-in T2VEncoder / Transformer / MultiheadAttention classes) ------------------- */
+/* projection-free MHA core of model/attention.py:185-394: q [L,B,E] k [S,B,E] v [S,B,Ev] (seq-first like the
+ * reference), out_proj weight [Ev,Ev] + bias; key_padding_mask [B,S] 1 = PAD or NULL. out [L,B,Ev];
+ * attn_weights [B,L,S] head-averaged or NULL. */
+int mesm_mha_noproj(const float* q, const float* k, const float* v, int32_t L, int32_t S, int32_t B, int32_t E,
+                    int32_t Ev, int32_t nheads, const float* out_w, const float* out_b,
+                    const uint8_t* key_padding_mask, float* out, float* attn_weights,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t mesm_mha_workspace_bytes(int32_t L, int32_t S, int32_t B, int32_t E, int32_t Ev);
+
+/* T2VEncoder(.forward) (model/transformer.py:83-105) with the weights loaded under `prefix`
+ * ("enhance_encoder", "t2v_encoder"): src_txt [B,Lt,256], src_vid [B,Lv,256], *_pad [B,L] 1 = PAD,
+ * pos_txt / pos_vid [B,L,256] or NULL.  out [B,Lv,256]. */
+int mesm_t2v_encoder(mesm_ctx* ctx, const char* prefix, const float* src_txt, const float* src_vid,
+                     const uint8_t* txt_pad, const uint8_t* vid_pad, const float* pos_txt, const float* pos_vid,
+                     int32_t B, int32_t Lt, int32_t Lv, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+size_t mesm_t2v_workspace_bytes(int32_t B, int32_t Lt, int32_t Lv);
+
+/* Transformer(.forward) (model/transformer.py:174-205): src [B,L,256], pad [B,L] 1 = PAD, query_embed [nq,2],
+ * pos_embed [B,L,256], global token / pos [256] (the reference repeats them over the batch, model.py:237-238).
+ * hs [nl,B,nq,256], references [nl,B,nq,2], memory_local [B,L,256], memory_global [B,256]. */
+int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const float* query_embed,
+                     const float* pos_embed, const float* global_token, const float* global_token_pos,
+                     int32_t B, int32_t L, float* hs, float* references, float* memory_local, float* memory_global,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t mesm_transformer_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t L);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESM_B200_H */

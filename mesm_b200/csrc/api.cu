@@ -1,0 +1,705 @@
+// C ABI of mesm_b200 (include/mesm_b200.h): context, weight ingestion/packing and the forward orchestration.
+//
+// The forward is a stream-ordered sequence of fused-linear, attention and row-wise kernels over caller-owned
+// workspace.  Pairs are processed in chunks of whole video groups so that a chunk's activations stay L2-resident
+// between the producing and the consuming kernel; the text side (tiny) is computed once for the whole batch because
+// the reference's negative branch and attn_mask quirk reach across pairs.
+#include "ctx.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace mesm;
+
+namespace {
+
+
+// ---- packing kernels ---------------------------------------------------------------------------------------------
+__global__ void transpose_pack_kernel(const float* __restrict__ W, int row0, int nrows, int K, const float* __restrict__ gamma,
+                                      float* __restrict__ Wt, int ldw, int Kp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)Kp * ldw) return;
+    const int k = (int)(idx / ldw), n = (int)(idx % ldw);
+    float v = 0.f;
+    if (k < K && n < nrows) v = W[(long long)(row0 + n) * K + k] * (gamma ? gamma[k] : 1.f);
+    Wt[idx] = v;
+}
+__global__ void colsum_kernel(const float* __restrict__ Wt, int Kp, int ldw, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int k = 0; k < Kp; ++k) s += Wt[(long long)k * ldw + n];
+    out[n] = s;
+}
+__global__ void fold_bias_kernel(const float* __restrict__ W, int row0, int N, int K, const float* __restrict__ beta,
+                                 const float* __restrict__ b, float* __restrict__ out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(W[(long long)(row0 + n) * K + k], beta[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[n] = s + (b ? b[row0 + n] : 0.f);
+}
+__global__ void vec_add_kernel(const float* a, const float* b, float* o, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] + b[i];
+}
+
+}  // namespace
+namespace mesm {
+cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, float* Wt, int ldw, int Kp, cudaStream_t s) {
+    const long long tot = (long long)Kp * ldw;
+    transpose_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(W, row0, nrows, K, nullptr, Wt, ldw, Kp);
+    g_stats.launches++;
+    return cudaGetLastError();
+}
+}  // namespace mesm
+namespace {
+
+struct Packer {
+    mesm_ctx* ctx;
+    cudaStream_t s;
+    std::string missing;
+    bool ok = true;
+    cudaError_t cerr = cudaSuccess;
+
+    float* alloc(size_t nfloats) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(nfloats, 4) * sizeof(float));
+        if (e != cudaSuccess) { ok = false; cerr = e; return nullptr; }
+        ctx->owned.push_back(p);
+        return (float*)p;
+    }
+    const Tensor* get(const std::string& key, std::initializer_list<int64_t> shape) {
+        auto it = ctx->w.find(key);
+        if (it == ctx->w.end()) { ok = false; if (missing.size() < 400) missing += key + " "; return nullptr; }
+        if (std::vector<int64_t>(shape) != it->second.shape) {
+            ok = false;
+            if (missing.size() < 400) missing += key + "(shape) ";
+            return nullptr;
+        }
+        return &it->second;
+    }
+    const float* vec(const std::string& key, int64_t n) { const Tensor* t = get(key, {n}); return t ? t->p : nullptr; }
+    Norm norm(const std::string& p, int64_t n = D) { Norm r; r.g = vec(p + ".weight", n); r.b = vec(p + ".bias", n); return r; }
+
+    // rows [row0,row0+nrows) of W[Ntot,K] (+ bias rows) -> packed linear
+    PL pack(const std::string& wkey, const std::string& bkey, int64_t Ntot, int64_t K, int row0, int nrows,
+            const float* gamma = nullptr, const float* beta = nullptr) {
+        PL r;
+        const Tensor* W = get(wkey, {Ntot, K});
+        const Tensor* b = bkey.empty() ? nullptr : get(bkey, {Ntot});
+        if (!W || (!bkey.empty() && !b)) return r;
+        const int Kp = (int)((K + 15) / 16 * 16), ldw = (nrows + 3) / 4 * 4;
+        float* Wt = alloc((size_t)Kp * ldw);
+        if (!Wt) return r;
+        const long long tot = (long long)Kp * ldw;
+        transpose_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(W->p, row0, nrows, (int)K, gamma, Wt, ldw, Kp);
+        r.Wt = Wt; r.ldw = ldw; r.K = (int)K; r.N = nrows;
+        if (gamma) {
+            float* cs = alloc(nrows);
+            float* cb = alloc(nrows);
+            if (!cs || !cb) return r;
+            colsum_kernel<<<(nrows + 127) / 128, 128, 0, s>>>(Wt, Kp, ldw, nrows, cs);
+            fold_bias_kernel<<<(nrows + 7) / 8, 256, 0, s>>>(W->p, row0, nrows, (int)K, beta, b ? b->p : nullptr, cb);
+            r.colsum = cs; r.bias = cb;
+        } else {
+            r.bias = b ? b->p + row0 : nullptr;
+        }
+        return r;
+    }
+    PL lin(const std::string& p, int64_t N, int64_t K) { return pack(p + ".weight", p + ".bias", N, K, 0, (int)N); }
+    const float* bias_sum(const float* a, const float* b, int n) {
+        if (!a || !b) return nullptr;
+        float* o = alloc(n);
+        if (o) vec_add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, o, n);
+        return o;
+    }
+    AttnFfn attn_ffn(const std::string& p, bool recon) {
+        AttnFfn L;
+        const std::string iw = p + "self_attn.in_proj_weight", ib = p + "self_attn.in_proj_bias";
+        L.q = pack(iw, ib, 3 * D, D, 0, D);
+        L.kv = pack(iw, ib, 3 * D, D, D, 2 * D);
+        L.qk = pack(iw, ib, 3 * D, D, 0, 2 * D);
+        L.v = pack(iw, ib, 3 * D, D, 2 * D, D);
+        L.out = lin(p + "self_attn.out_proj", D, D);
+        L.l1 = lin(p + "linear1", FF, D);
+        L.l2 = lin(p + "linear2", D, FF);
+        L.n1 = norm(p + "norm1"); L.n2 = norm(p + "norm2");
+        L.prelu = vec(p + "activation.weight", 1);
+        const Tensor* W = get(iw, {3 * D, D});
+        const Tensor* b = get(ib, {3 * D});
+        L.in_w = W ? W->p : nullptr; L.in_b = b ? b->p : nullptr;
+        if (recon) L.vT = L.v.Wt;
+        return L;
+    }
+};
+
+
+}  // namespace
+
+namespace mesm {
+
+thread_local std::string g_create_error;
+int fail(mesm_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code ? code : 1;
+}
+
+// T2V layer (model/transformer.py:508-540).  txt rows: [Bc*Lk] through tmap; vid rows [Bc*Lq] contiguous.
+cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
+                      const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
+                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s) {
+    const int Rt = Bc * Lk, Rv = Bc * Lq;
+    if (pos_txt) {
+        PL kw = L.kv; kw.N = D;
+        MESM_CHECK(Lin(Rt, kw, txt, D, t.KV, 2 * D).amap(tmap).apos(pos_txt).run(s));
+        PL vw = L.v;
+        MESM_CHECK(Lin(Rt, vw, txt, D, t.KV + D, 2 * D).amap(tmap).run(s));
+    } else {
+        MESM_CHECK(Lin(Rt, L.kv, txt, D, t.KV, 2 * D).amap(tmap).run(s));
+    }
+    MESM_CHECK(Lin(Rv, L.q, vid, D, t.Q, D).apos(pos_vid).run(s));
+    MhaRowsArgs a;
+    a.q = t.Q; a.ldq = D; a.k = t.KV; a.ldk = 2 * D; a.v = t.KV + D; a.ldv = 2 * D;
+    a.k_pad = k_pad; a.q_pad = q_pad; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = Lq; a.Lk = Lk; a.b0 = b0; a.Btot = Btot;
+    a.q_scale = kScale32;
+    MESM_CHECK(launch_mha_rows(a, s));
+    MESM_CHECK(Lin(Rv, L.out, t.AO, D, t.Y1, D).res(vid, D).pre_ln(t.X1).ln(L.n1).run(s));
+    MESM_CHECK(Lin(Rv, L.l1, t.Y1, D, t.H, FF).act(ACT_PRELU, L.prelu).run(s));
+    MESM_CHECK(Lin(Rv, L.l2, t.H, FF, out, ldo).omap(omap).res(t.X1, D).ln(L.n2).run(s));
+    return cudaSuccess;
+}
+
+// Encoder layer (model/transformer.py:637-650) on the [Bc, L1, 256] buffer (L1 = Lv + 1, global token first).
+cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
+                      const EncBuffers& t, float* out, cudaStream_t s) {
+    const int R = Bc * L1;
+    MESM_CHECK(Lin(R, L.qk, src, D, t.QKV, 3 * D).apos(pos).run(s));
+    MESM_CHECK(Lin(R, L.v, src, D, t.QKV + 2 * D, 3 * D).run(s));
+    MhaRowsArgs a;
+    a.q = t.QKV; a.ldq = 3 * D; a.k = t.QKV + D; a.ldk = 3 * D; a.v = t.QKV + 2 * D; a.ldv = 3 * D;
+    a.k_pad = pad; a.q_pad = nullptr; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = L1; a.Lk = L1; a.b0 = 0; a.Btot = Bc;
+    a.q_scale = kScale32;
+    MESM_CHECK(launch_mha_rows(a, s));
+    MESM_CHECK(Lin(R, L.out, t.AO, D, t.Y1, D).res(src, D).ln(L.n1).run(s));
+    MESM_CHECK(Lin(R, L.l1, t.Y1, D, t.H, FF).act(ACT_PRELU, L.prelu).run(s));
+    MESM_CHECK(Lin(R, L.l2, t.H, FF, out, D).res(t.Y1, D).ln(L.n2).run(s));
+    return cudaSuccess;
+}
+
+// DAB-DETR decoder + heads (model/transformer.py:333-420, model/model.py:246-252) on a chunk.
+size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl) {
+    const size_t R = (size_t)Bc * nq, Re = (size_t)Bc * L1;
+    d.tgtA = ar.get<float>(R * D); d.tgtB = ar.get<float>(R * D); d.ref = ar.get<float>(R * 2);
+    d.refs = ar.get<float>((size_t)nl * R * 2); d.sine = ar.get<float>(R * D); d.sine_s = ar.get<float>(R * D);
+    d.h1 = ar.get<float>(R * D); d.h2 = ar.get<float>(R * D); d.qpos = ar.get<float>(R * D); d.ptrans = ar.get<float>(R * D);
+    d.anc = ar.get<float>(R); d.qsa = ar.get<float>(R * D); d.ksa = ar.get<float>(R * D); d.vsa = ar.get<float>(R * D);
+    d.ao = ar.get<float>(R * D); d.t1 = ar.get<float>(R * D); d.qca = ar.get<float>(R * D); d.sinep = ar.get<float>(R * D);
+    d.t2 = ar.get<float>(R * D); d.hff = ar.get<float>(R * FF); d.d2 = ar.get<float>(R * 2);
+    d.hs = ar.get<float>((size_t)nl * R * D); d.Kc = ar.get<float>(Re * D); d.Kp = ar.get<float>(Re * D);
+    d.Vd = ar.get<float>(Re * D); d.tmpref = ar.get<float>(R * 2);
+    return ar.off;
+}
+
+cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, const float* posE, const uint8_t* padV, int Lv, int Bc,
+                        const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
+                        long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
+                        long long refs_layer_stride, cudaStream_t s) {
+    const int nq = c->cfg.num_queries, nl = c->cfg.dec_layers, L1 = Lv + 1;
+    const int R = Bc * nq, Re = Bc * L1;
+    MESM_CHECK(launch_fill(d.tgtA, (long long)R * D, 0.f, s));                         // tgt = 0 (transformer.py:201)
+    MESM_CHECK(launch_dec_init_ref(qembed, Bc, nq, d.refs, s));                       // refs[0] = sigmoid(query_embed)
+    float* tgt = d.tgtA;
+    float* tgt_next = d.tgtB;
+    const float* ref = d.refs;
+    for (int lid = 0; lid < nl; ++lid) {
+        const DecLayer& L = c->dec[lid];
+        MESM_CHECK(Lin(R, c->ra0, tgt, D, d.h1, D).act(ACT_RELU).run(s));
+        MESM_CHECK(Lin(R, c->ra1, d.h1, D, d.anc, 1).run(s));
+        const float* ptrans = nullptr;
+        if (lid > 0) {
+            MESM_CHECK(Lin(R, c->qs0, tgt, D, d.h1, D).act(ACT_RELU).run(s));
+            MESM_CHECK(Lin(R, c->qs1, d.h1, D, d.ptrans, D).run(s));
+            ptrans = d.ptrans;
+        }
+        MESM_CHECK(launch_dec_sine(ref, R, ptrans, d.anc, d.sine, d.sine_s, s));
+        MESM_CHECK(Lin(R, c->rph0, d.sine, D, d.h1, D).act(ACT_RELU).run(s));
+        MESM_CHECK(Lin(R, c->rph1, d.h1, D, d.qpos, D).run(s));
+        // self-attention over the queries
+        MESM_CHECK(Lin(R, L.sa_qc, tgt, D, d.qsa, D).second(d.qpos, D, L.sa_qp).bias(L.sa_q_bias).run(s));
+        MESM_CHECK(Lin(R, L.sa_kc, tgt, D, d.ksa, D).second(d.qpos, D, L.sa_kp).bias(L.sa_k_bias).run(s));
+        MESM_CHECK(Lin(R, L.sa_v, tgt, D, d.vsa, D).run(s));
+        MhaSmallArgs a;
+        a.q = d.qsa; a.ldq = D; a.q2 = nullptr; a.ldq2 = 0; a.k = d.ksa; a.ldk = D; a.k2 = nullptr; a.ldk2 = 0;
+        a.v = d.vsa; a.ldv = D; a.k_pad = nullptr; a.out = d.ao; a.ldo = D; a.attn_w = nullptr;
+        a.B = Bc; a.L = nq; a.S = nq; a.nheads = NH; a.hq = HD; a.hv = HD; a.scale = kScale32;
+        a.q_bs = nq; a.q_is = 1; a.k_bs = nq; a.k_is = 1; a.k_off = 0;
+        MESM_CHECK(launch_mha_small(a, s));
+        MESM_CHECK(Lin(R, L.sa_out, d.ao, D, d.t1, D).res(tgt, D).ln(L.n1).run(s));
+        // cross-attention into the encoder memory
+        if (lid == 0) {
+            MESM_CHECK(Lin(R, L.ca_qc, d.t1, D, d.qca, D).second(d.qpos, D, L.ca_qp).bias(L.ca_q_bias0).run(s));
+            MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).second(posE, D, L.ca_kp).bias(L.ca_k_bias0).run(s));
+        } else {
+            MESM_CHECK(Lin(R, L.ca_qc, d.t1, D, d.qca, D).run(s));
+            MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).run(s));
+        }
+        MESM_CHECK(Lin(Re, L.ca_kp, posE, D, d.Kp, D).run(s));
+        MESM_CHECK(Lin(Re, L.ca_v, E, D, d.Vd, D).run(s));
+        MESM_CHECK(Lin(R, L.ca_sine, d.sine_s, D, d.sinep, D).run(s));
+        a.q = d.qca; a.q2 = d.sinep; a.ldq2 = D; a.k = d.Kc; a.k2 = d.Kp; a.ldk2 = D; a.v = d.Vd; a.k_pad = padV;
+        a.S = Lv; a.scale = kScale64; a.k_bs = L1; a.k_is = 1; a.k_off = 1;
+        MESM_CHECK(launch_mha_small(a, s));
+        MESM_CHECK(Lin(R, L.ca_out, d.ao, D, d.t2, D).res(d.t1, D).ln(L.n2).run(s));
+        MESM_CHECK(Lin(R, L.l1, d.t2, D, d.hff, FF).act(ACT_PRELU, L.prelu).run(s));
+        MESM_CHECK(Lin(R, L.l2, d.hff, FF, tgt_next, D).res(d.t2, D).ln(L.n3).run(s));
+        std::swap(tgt, tgt_next);
+        // iterative reference refinement
+        MESM_CHECK(Lin(R, c->bb0, tgt, D, d.h1, D).act(ACT_RELU).run(s));
+        MESM_CHECK(Lin(R, c->bb1, d.h1, D, d.h2, D).act(ACT_RELU).run(s));
+        MESM_CHECK(Lin(R, c->bb2, d.h2, D, d.d2, 2).run(s));
+        float* nref = (lid != nl - 1) ? d.refs + (size_t)(lid + 1) * R * 2 : d.tmpref;
+        MESM_CHECK(launch_ref_update(d.d2, 2, ref, R, nref, s));
+        ref = nref;
+        MESM_CHECK(launch_layernorm_rows(tgt, R, c->dec_norm.g, c->dec_norm.b, d.hs + (size_t)lid * R * D, s));
+    }
+    // heads on every intermediate (aux_outputs = all but the last)
+    for (int lid = 0; lid < nl; ++lid) {
+        const float* hs = d.hs + (size_t)lid * R * D;
+        const float* rf = d.refs + (size_t)lid * R * 2;
+        float* lo = (lid == nl - 1) ? logits_out : (aux_logits ? aux_logits + lid * aux_layer_stride : nullptr);
+        float* so = (lid == nl - 1) ? spans_out : (aux_spans ? aux_spans + lid * aux_layer_stride : nullptr);
+        if (lo) MESM_CHECK(Lin(R, c->cls, hs, D, lo, 2).run(s));
+        if (so) {
+            MESM_CHECK(Lin(R, c->span0, hs, D, d.h1, D).act(ACT_RELU).run(s));
+            MESM_CHECK(Lin(R, c->span1, d.h1, D, d.h2, D).act(ACT_RELU).run(s));
+            MESM_CHECK(Lin(R, c->span2, d.h2, D, d.d2, 2).run(s));
+            MESM_CHECK(launch_ref_update(d.d2, 2, rf, R, so, s));
+        }
+        if (hs_out) MESM_CHECK(cudaMemcpyAsync(hs_out + lid * hs_layer_stride, hs, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (refs_out) MESM_CHECK(cudaMemcpyAsync(refs_out + lid * refs_layer_stride, rf, (size_t)R * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return cudaSuccess;
+}
+
+}  // namespace mesm
+
+namespace {
+
+int check_cfg(const mesm_cfg* c, std::string& why) {
+    if (!c) { why = "cfg is NULL"; return 1; }
+    if (c->hidden_dim != D || c->nheads != NH || c->dim_feedforward != FF) { why = "only hidden_dim=256, nheads=8, dim_feedforward=1024 (every shipped MESM config) are supported"; return 1; }
+    if (c->num_queries < 1 || c->num_queries > 32) { why = "num_queries must be in [1,32]"; return 1; }
+    if (c->n_input_proj != 2) { why = "n_input_proj must be 2"; return 1; }
+    if (c->v_feat_dim < 1 || c->t_feat_dim < 1) { why = "feature dims must be positive"; return 1; }
+    if (c->dec_layers < 1 || c->enc_layers < 0 || c->t2v_layers < 0 || c->num_recfw_layers < 0 || c->num_recss_layers < 0) { why = "bad layer counts"; return 1; }
+    return 0;
+}
+
+}  // namespace
+
+namespace mesm {
+cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) { return launch_linear_simt(op, s); }
+}  // namespace mesm
+
+// =====================================================================================================================
+extern "C" {
+
+int mesm_abi_version(void) { return MESM_ABI_VERSION; }
+
+const char* mesm_last_error(const mesm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+mesm_ctx* mesm_create(const mesm_cfg* cfg, int device) {
+    std::string why;
+    if (check_cfg(cfg, why)) { g_create_error = why; return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (mesm_b200 has no CPU fallback)"; return nullptr; }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return nullptr; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) { g_create_error = std::string("mesm_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor); return nullptr; }
+    cudaSetDevice(device);
+    mesm_ctx* c = new mesm_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    cudaEventCreateWithFlags(&c->tab_event, cudaEventDisableTiming);
+    return c;
+}
+
+void mesm_destroy(mesm_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void* p : ctx->owned) cudaFree(p);
+    for (auto& kv : ctx->w) cudaFree(kv.second.p);
+    if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+    if (ctx->tab_event) cudaEventDestroy(ctx->tab_event);
+    delete ctx;
+}
+
+int mesm_set_chunk_pairs(mesm_ctx* ctx, int32_t pairs) {
+    if (!ctx || pairs < 1) return 1;
+    ctx->chunk_pairs = pairs;
+    return 0;
+}
+
+int64_t mesm_last_launch_count(const mesm_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int mesm_load_weight(mesm_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim, int is_device,
+                     void* stream) {
+    if (!ctx || !key || !data || ndim < 0 || ndim > 4) return fail(ctx, 1, "mesm_load_weight: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    size_t n = 1;
+    std::vector<int64_t> shp;
+    for (int i = 0; i < ndim; ++i) { n *= (size_t)shape[i]; shp.push_back(shape[i]); }
+    Tensor& t = ctx->w[key];
+    if (t.p && t.n != n) { cudaFree(t.p); t.p = nullptr; }
+    if (!t.p) CK(cudaMalloc((void**)&t.p, std::max<size_t>(n, 4) * sizeof(float)));
+    t.n = n; t.shape = shp;
+    CK(cudaMemcpyAsync(t.p, data, n * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    ctx->finalized = false;
+    return 0;
+}
+
+int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
+    if (!ctx) return 1;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaStreamSynchronize(s));                  // previous packed buffers may still be in use
+    for (void* p : ctx->owned) cudaFree(p);
+    ctx->owned.clear();
+    const mesm_cfg& cf = ctx->cfg;
+    Packer P{ctx, s};
+    // input projections: LinearLayer.0 = LN(in)->Linear->ReLU (LN folded into the GEMM), LinearLayer.1 = LN(256)->Linear
+    {
+        const Tensor* g = P.get("input_vid_proj.0.LayerNorm.weight", {cf.v_feat_dim});
+        const Tensor* b = P.get("input_vid_proj.0.LayerNorm.bias", {cf.v_feat_dim});
+        ctx->vid0 = P.pack("input_vid_proj.0.net.1.weight", "input_vid_proj.0.net.1.bias", D, cf.v_feat_dim, 0, D,
+                           g ? g->p : nullptr, b ? b->p : nullptr);
+        ctx->vid1_ln = P.norm("input_vid_proj.1.LayerNorm");
+        ctx->vid1 = P.lin("input_vid_proj.1.net.1", D, D);
+        g = P.get("input_txt_proj.0.LayerNorm.weight", {cf.t_feat_dim});
+        b = P.get("input_txt_proj.0.LayerNorm.bias", {cf.t_feat_dim});
+        ctx->txt0 = P.pack("input_txt_proj.0.net.1.weight", "input_txt_proj.0.net.1.bias", D, cf.t_feat_dim, 0, D,
+                           g ? g->p : nullptr, b ? b->p : nullptr);
+        ctx->txt1_ln = P.norm("input_txt_proj.1.LayerNorm");
+        ctx->txt1 = P.lin("input_txt_proj.1.net.1", D, D);
+    }
+    ctx->enh.clear(); ctx->aln.clear(); ctx->rec.clear(); ctx->enc.clear(); ctx->dec.clear();
+    if (cf.rec_fw)
+        for (int i = 0; i < cf.num_recfw_layers; ++i) ctx->enh.push_back(P.attn_ffn("enhance_encoder.t2v_encoder.layers." + std::to_string(i) + ".", false));
+    for (int i = 0; i < cf.t2v_layers; ++i) ctx->aln.push_back(P.attn_ffn("t2v_encoder.t2v_encoder.layers." + std::to_string(i) + ".", false));
+    if (cf.rec_ss) {
+        for (int i = 0; i < cf.num_recss_layers; ++i) ctx->rec.push_back(P.attn_ffn("ss_reconstructor.recon_trans.layers." + std::to_string(i) + ".", true));
+        ctx->msent = P.vec("ss_reconstructor.masked_sent_token", D);
+        ctx->osp0_ln = P.norm("ss_reconstructor.output_sent_proj.0.LayerNorm");
+        ctx->osp0 = P.lin("ss_reconstructor.output_sent_proj.0.net.1", D, D);
+        ctx->osp1_ln = P.norm("ss_reconstructor.output_sent_proj.1.LayerNorm");
+        ctx->osp1 = P.lin("ss_reconstructor.output_sent_proj.1.net.1", D, D);
+    }
+    for (int i = 0; i < cf.enc_layers; ++i) ctx->enc.push_back(P.attn_ffn("transformer.encoder.layers." + std::to_string(i) + ".", false));
+    for (int i = 0; i < cf.dec_layers; ++i) {
+        const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".";
+        DecLayer L;
+        L.sa_qc = P.lin(p + "sa_qcontent_proj", D, D); L.sa_qp = P.lin(p + "sa_qpos_proj", D, D);
+        L.sa_kc = P.lin(p + "sa_kcontent_proj", D, D); L.sa_kp = P.lin(p + "sa_kpos_proj", D, D);
+        L.sa_v = P.lin(p + "sa_v_proj", D, D); L.sa_out = P.lin(p + "self_attn.out_proj", D, D);
+        L.ca_qc = P.lin(p + "ca_qcontent_proj", D, D); L.ca_kc = P.lin(p + "ca_kcontent_proj", D, D);
+        L.ca_kp = P.lin(p + "ca_kpos_proj", D, D); L.ca_v = P.lin(p + "ca_v_proj", D, D);
+        L.ca_sine = P.lin(p + "ca_qpos_sine_proj", D, D); L.ca_out = P.lin(p + "cross_attn.out_proj", D, D);
+        L.l1 = P.lin(p + "linear1", FF, D); L.l2 = P.lin(p + "linear2", D, FF);
+        L.n1 = P.norm(p + "norm1"); L.n2 = P.norm(p + "norm2"); L.n3 = P.norm(p + "norm3");
+        L.prelu = P.vec(p + "activation.weight", 1);
+        L.sa_q_bias = P.bias_sum(L.sa_qc.bias, L.sa_qp.bias, D);
+        L.sa_k_bias = P.bias_sum(L.sa_kc.bias, L.sa_kp.bias, D);
+        if (i == 0) {
+            L.ca_qp = P.lin(p + "ca_qpos_proj", D, D);
+            L.ca_q_bias0 = P.bias_sum(L.ca_qc.bias, L.ca_qp.bias, D);
+            L.ca_k_bias0 = P.bias_sum(L.ca_kc.bias, L.ca_kp.bias, D);
+        }
+        ctx->dec.push_back(L);
+    }
+    ctx->dec_norm = P.norm("transformer.decoder.norm");
+    ctx->qs0 = P.lin("transformer.decoder.query_scale.layers.0", D, D);
+    ctx->qs1 = P.lin("transformer.decoder.query_scale.layers.1", D, D);
+    ctx->rph0 = P.lin("transformer.decoder.ref_point_head.layers.0", D, D);
+    ctx->rph1 = P.lin("transformer.decoder.ref_point_head.layers.1", D, D);
+    ctx->bb0 = P.lin("transformer.decoder.bbox_embed.layers.0", D, D);
+    ctx->bb1 = P.lin("transformer.decoder.bbox_embed.layers.1", D, D);
+    ctx->bb2 = P.lin("transformer.decoder.bbox_embed.layers.2", 2, D);
+    ctx->ra0 = P.lin("transformer.decoder.ref_anchor_head.layers.0", D, D);
+    ctx->ra1 = P.lin("transformer.decoder.ref_anchor_head.layers.1", 1, D);
+    ctx->span0 = P.lin("span_embed.layers.0", D, D);
+    ctx->span1 = P.lin("span_embed.layers.1", D, D);
+    ctx->span2 = P.lin("span_embed.layers.2", 2, D);
+    ctx->cls = P.lin("class_embed", 2, D);
+    ctx->sal1 = P.lin("saliency_proj1", D, D);
+    ctx->sal2 = P.lin("saliency_proj2", D, D);
+    ctx->gtok = P.vec("global_rep_token", D);
+    ctx->gpos = P.vec("global_rep_pos", D);
+    {
+        const Tensor* q = P.get("query_embed.weight", {cf.num_queries, 2});
+        ctx->qembed = q ? q->p : nullptr;
+    }
+    if (!P.ok) {
+        if (P.cerr != cudaSuccess) return fail(ctx, (int)P.cerr, std::string("weight packing: ") + cudaGetErrorString(P.cerr));
+        return fail(ctx, 2, "state_dict incomplete or mis-shaped; missing: " + P.missing);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    ctx->finalized = true;
+    return 0;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+namespace {
+
+struct FwdPlan {
+    // whole-batch buffers
+    float *wn, *wstat, *t1, *expw, *negw, *projV, *recon;
+    uint8_t *wmask, *emask, *epad, *wpad, *neg_epad, *neg_wpad, *padV_all;
+    int* d_tab;
+    // chunk buffers
+    float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2;
+    uint8_t *padV, *padE;
+    T2VBuffers t2v;
+    EncBuffers encb;
+    DecBuffers dec;
+    float *rS, *rS2, *rq, *rqk, *rpool, *rao, *rX1, *rY1, *rH, *rtmp;
+    size_t total = 0;
+};
+
+void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int Lt, int G, int Bc, bool need_projV) {
+    const mesm_cfg& cf = c->cfg;
+    const size_t Rt = (size_t)B * Lt, Rte = (size_t)B * (Lt + 1);
+    p.wn = ar.get<float>(Rt * cf.t_feat_dim); p.wstat = ar.get<float>(Rt * 2); p.t1 = ar.get<float>(Rt * D);
+    p.expw = ar.get<float>(Rte * D); p.negw = ar.get<float>(Rte * D);
+    p.projV = need_projV ? ar.get<float>((size_t)B * Lv * D) : nullptr;
+    p.recon = ar.get<float>((size_t)B * D);
+    p.wmask = ar.get<uint8_t>(Rt); p.emask = ar.get<uint8_t>(Rte); p.epad = ar.get<uint8_t>(Rte); p.wpad = ar.get<uint8_t>(Rt);
+    p.neg_epad = ar.get<uint8_t>(Rte); p.neg_wpad = ar.get<uint8_t>(Rt); p.padV_all = ar.get<uint8_t>((size_t)B * Lv);
+    p.d_tab = ar.get<int>((size_t)2 * B + 2 * (G + 1));
+    const int L1 = Lv + 1;
+    const size_t Rv = (size_t)Bc * Lv, Re = (size_t)Bc * L1, Rk = (size_t)Bc * (Lt + 1);
+    p.vstat = ar.get<float>(Rv * 2); p.v1 = ar.get<float>(Rv * D); p.posV = ar.get<float>(Rv * D); p.posE = ar.get<float>(Re * D);
+    p.xa = ar.get<float>(Rv * D); p.xb = ar.get<float>(Rv * D); p.enh = ar.get<float>(Rv * D);
+    p.E = ar.get<float>(Re * D); p.E2 = ar.get<float>(Re * D); p.P1 = ar.get<float>(Re * D); p.P2 = ar.get<float>((size_t)Bc * D);
+    p.padV = ar.get<uint8_t>(Rv); p.padE = ar.get<uint8_t>(Re);
+    p.t2v.KV = ar.get<float>(Rk * 2 * D); p.t2v.Q = ar.get<float>(Re * D); p.t2v.AO = ar.get<float>(Re * D);
+    p.t2v.X1 = ar.get<float>(Re * D); p.t2v.Y1 = ar.get<float>(Re * D); p.t2v.H = ar.get<float>(Re * FF);
+    p.encb.QKV = ar.get<float>(Re * 3 * D); p.encb.AO = p.t2v.AO; p.encb.Y1 = p.t2v.Y1; p.encb.H = p.t2v.H;
+    dec_alloc(ar, p.dec, Bc, cf.num_queries, L1, cf.dec_layers);
+    p.rS = ar.get<float>((size_t)Bc * D); p.rS2 = ar.get<float>((size_t)Bc * D); p.rq = ar.get<float>((size_t)Bc * D);
+    p.rqk = ar.get<float>((size_t)Bc * NH * D); p.rpool = ar.get<float>((size_t)Bc * NH * D); p.rao = ar.get<float>((size_t)Bc * D);
+    p.rX1 = ar.get<float>((size_t)Bc * D); p.rY1 = ar.get<float>((size_t)Bc * D); p.rH = ar.get<float>((size_t)Bc * FF);
+    p.rtmp = ar.get<float>((size_t)Bc * D);
+    p.total = ar.off + 256;
+}
+
+}  // namespace
+
+extern "C" size_t mesm_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t Lv, int32_t Lt, int32_t G) {
+    if (!ctx || B < 1 || Lv < 1 || Lt < 1) return 0;
+    Arena ar(nullptr, 0);
+    FwdPlan p;
+    plan_forward(ctx, ar, p, B, Lv, Lt, std::max(G, 1), std::min<int>(B, ctx->chunk_pairs), true);
+    return p.total;
+}
+
+extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_outputs* out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!ctx) return 1;
+    if (!in || !out || !workspace) return fail(ctx, 1, "mesm_forward: NULL argument");
+    if (!ctx->finalized) return fail(ctx, 1, "mesm_forward: weights not finalized (call mesm_finalize_weights)");
+    const mesm_cfg& cf = ctx->cfg;
+    const int B = in->B, Lv = in->Lv, Lt = in->Lt, G = in->G, L1 = Lv + 1, Lk = Lt + 1, nq = cf.num_queries;
+    if (B < 1 || Lv < 1 || Lt < 1 || G < 1 || !in->video_feat || !in->video_mask || !in->words_feat || !in->num_clips)
+        return fail(ctx, 1, "mesm_forward: bad input shapes / NULL input");
+    if (Lv + 1 > 1024) return fail(ctx, 1, "mesm_forward: Lv must be <= 1023");
+    if (!cf.rec_ss) return fail(ctx, 1, "mesm_forward: rec_ss = false is not supported (every shipped config enables it)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long launches0 = g_stats.launches;
+
+    // ---- host tables from num_clips ------------------------------------------------------------------------------
+    long long tot = 0; int max_nc = 0;
+    for (int g = 0; g < G; ++g) { if (in->num_clips[g] < 1) return fail(ctx, 1, "num_clips entries must be >= 1"); tot += in->num_clips[g]; max_nc = std::max<int>(max_nc, (int)in->num_clips[g]); }
+    if (tot != B) return fail(ctx, 1, "sum(num_clips) != B");
+    if (in->neg_index && G < 2) return fail(ctx, 1, "the negative branch needs >= 2 video groups (sample_outclass_neg raises in the reference)");
+    const size_t tab_ints = (size_t)2 * B + (G + 1);
+    if (ctx->h_tab_cap < tab_ints) {
+        if (ctx->tab_event_pending) { CK(cudaEventSynchronize(ctx->tab_event)); ctx->tab_event_pending = false; }
+        if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+        ctx->h_tab = nullptr; ctx->h_tab_cap = 0;
+        CK(cudaMallocHost((void**)&ctx->h_tab, tab_ints * 2 * sizeof(int)));
+        ctx->h_tab_cap = tab_ints * 2;
+    }
+    if (ctx->tab_event_pending) { CK(cudaEventSynchronize(ctx->tab_event)); ctx->tab_event_pending = false; }
+    int* h_group = ctx->h_tab; int* h_slot = h_group + B; int* h_gstart = h_slot + B;
+    std::vector<std::pair<int, int>> chunks;
+    {
+        int b = 0, c0 = 0;
+        for (int g = 0; g < G; ++g) {
+            h_gstart[g] = b;
+            const int n = (int)in->num_clips[g];
+            if (b > c0 && b + n - c0 > ctx->chunk_pairs) { chunks.push_back({c0, b}); c0 = b; }
+            for (int i = 0; i < n; ++i) { h_group[b] = g; h_slot[b] = i; ++b; }
+        }
+        h_gstart[G] = B;
+        chunks.push_back({c0, B});
+    }
+    int Bc_max = 0;
+    for (auto& ch : chunks) Bc_max = std::max(Bc_max, ch.second - ch.first);
+
+    Arena ar(workspace, workspace_bytes);
+    FwdPlan p;
+    float* projV_all = out->projed_video_feat;
+    plan_forward(ctx, ar, p, B, Lv, Lt, G, Bc_max, projV_all == nullptr);
+    if (p.total > workspace_bytes)
+        return fail(ctx, 1, "mesm_forward: workspace too small: need " + std::to_string(p.total) + " bytes, got " + std::to_string(workspace_bytes));
+    if (!projV_all) projV_all = p.projV;
+    int* d_group = p.d_tab; int* d_slot = d_group + B; int* d_gstart = d_slot + B; int* d_glen = d_gstart + (G + 1);
+    CK(cudaMemcpyAsync(d_group, h_group, tab_ints * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->tab_event, s));
+    ctx->tab_event_pending = true;
+    if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));
+
+    // ---- text side, whole batch (model/model.py:145-152, 167) --------------------------------------------------------
+    const int Rt = B * Lt;
+    float* expw = out->expanded_words_feat ? out->expanded_words_feat : p.expw;
+    uint8_t* emask = out->expanded_words_mask ? out->expanded_words_mask : p.emask;
+    CK(launch_text_prep(in->words_feat, Rt, cf.t_feat_dim, p.wn, p.wmask, p.wstat, s));
+    CK(Lin(Rt, ctx->txt0, p.wn, cf.t_feat_dim, p.t1, D).fold(p.wstat, ctx->txt0.colsum).act(ACT_RELU).ln(ctx->txt1_ln).run(s));
+    CK(Lin(Rt, ctx->txt1, p.t1, D, expw, D).omap(RowMap{Lt, Lk, 1}).run(s));
+    CK(launch_expand_mask(p.wmask, B, Lt, emask, p.epad, p.wpad, s));
+
+    CK(launch_invert_mask(in->video_mask, p.padV_all, (long long)B * Lv, s));
+
+    const RowMap wordsMap{Lt, Lk, 1};          // projed_words rows inside the expanded [B, Lt+1, 256] buffer
+    float* recon_all = out->recon_feat ? out->recon_feat : p.recon;
+    const int recon_max_keys = cf.qvh_grouping ? max_nc * Lv : Lv;
+
+    // One chunk of whole video groups through projection -> enhance -> (recon) -> align -> encoder -> (decoder, heads).
+    auto video_chunk = [&](int b0, int b1, bool neg) -> int {
+        const int Bc = b1 - b0, Rv = Bc * Lv, Re = Bc * L1;
+        const float* vfeat = in->video_feat + (size_t)b0 * Lv * cf.v_feat_dim;
+        const uint8_t* vmask = in->video_mask + (size_t)b0 * Lv;
+        float* projV = projV_all + (size_t)b0 * Lv * D;
+        PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos;
+        pa.posV = p.posV; pa.posE = p.posE; pa.encbuf = p.E; pa.padV = p.padV; pa.padE = p.padE;
+        CK(launch_pos_embed(pa, s));
+        if (!neg) {
+            // input projection (model/model.py:166): LayerNorm folded into the GEMM -> ReLU -> LN(256) -> GEMM
+            CK(launch_row_stats(vfeat, Rv, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s));
+            CK(Lin(Rv, ctx->vid0, vfeat, cf.v_feat_dim, p.v1, D).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+            CK(Lin(Rv, ctx->vid1, p.v1, D, projV, D).run(s));
+        }
+        const float* words_c = (neg ? p.negw : expw) + (size_t)b0 * Lk * D;
+        const uint8_t* epad_all = neg ? p.neg_epad : p.epad;
+        const uint8_t* wpad_all = neg ? p.neg_wpad : p.wpad;
+        // ---- FW-MESM enhance encoder (model/model.py:175-182; neg: 281-286): keys = the Lt projected words ----
+        const float* x = projV;
+        float* enh = (!neg && out->enhanced_video_feat) ? out->enhanced_video_feat + (size_t)b0 * Lv * D : p.enh;
+        for (size_t l = 0; l < ctx->enh.size(); ++l) {
+            float* dst = (l + 1 == ctx->enh.size()) ? enh : (l % 2 == 0 ? p.xa : p.xb);
+            CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, p.t2v,
+                         dst, D, identity_map(), s));
+            x = dst;
+        }
+        if (ctx->enh.empty() && !neg && out->enhanced_video_feat)
+            CK(cudaMemcpyAsync(enh, projV, (size_t)Rv * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        // ---- SS-MESM sentence reconstruction (model/model.py:184-222, 467-488) ----
+        if (!neg) {
+            float* S = p.rS; float* S2 = p.rS2;
+            CK(launch_broadcast_row(ctx->msent, S, Bc, s));
+            for (size_t l = 0; l < ctx->rec.size(); ++l) {
+                const AttnFfn& L = ctx->rec[l];
+                CK(Lin(Bc, L.q, S, D, p.rq, D).scale(kScale32).run(s));
+                for (int h = 0; h < NH; ++h) {      // qk[b,h,:] = Wk_h^T q_h : [Bc,32] x [32,256]
+                    PL w; w.Wt = L.in_w + (size_t)(D + h * HD) * D; w.ldw = D; w.K = HD; w.N = D; w.bias = nullptr;
+                    CK(Lin(Bc, w, p.rq + h * HD, D, p.rqk + h * D, NH * D).run(s));
+                }
+                ReconPoolArgs ra;
+                ra.x = projV; ra.ldx = D; ra.vmask = in->video_mask; ra.qk = p.rqk; ra.pooled = p.rpool;
+                ra.pair_group = d_group; ra.pair_slot = d_slot; ra.group_start = d_gstart; ra.group_len = d_glen;
+                ra.B = Bc; ra.Lv = Lv; ra.qvh = cf.qvh_grouping; ra.max_keys = recon_max_keys; ra.b0 = b0; ra.Btot = B;
+                CK(launch_recon_pool(ra, s));
+                for (int h = 0; h < NH; ++h) {      // attn_out[:, h*32:+32] = Wv_h pooled_h + bv_h
+                    PL w; w.Wt = L.vT + h * HD; w.ldw = L.v.ldw; w.K = D; w.N = HD; w.bias = L.v.bias + h * HD;
+                    CK(Lin(Bc, w, p.rpool + h * D, NH * D, p.rao + h * HD, D).run(s));
+                }
+                CK(Lin(Bc, L.out, p.rao, D, p.rY1, D).res(S, D).pre_ln(p.rX1).ln(L.n1).run(s));
+                CK(Lin(Bc, L.l1, p.rY1, D, p.rH, FF).act(ACT_PRELU, L.prelu).run(s));
+                CK(Lin(Bc, L.l2, p.rH, FF, S2, D).res(p.rX1, D).ln(L.n2).run(s));
+                std::swap(S, S2);
+            }
+            // recon_feat = F.normalize(.) -> word slot 0 of the expanded text (model/model.py:217, 486)
+            CK(launch_l2norm_rows(S, Bc, recon_all + (size_t)b0 * D, expw + (size_t)b0 * Lk * D, D, RowMap{1, Lk, 0}, s));
+            if (out->projed_recon_feat) {           // output_sent_proj (model/model.py:487)
+                CK(launch_layernorm_rows(recon_all + (size_t)b0 * D, Bc, ctx->osp0_ln.g, ctx->osp0_ln.b, p.rtmp, s));
+                CK(Lin(Bc, ctx->osp0, p.rtmp, D, p.rY1, D).act(ACT_RELU).ln(ctx->osp1_ln).run(s));
+                CK(Lin(Bc, ctx->osp1, p.rY1, D, out->projed_recon_feat + (size_t)b0 * D, D).run(s));
+            }
+        }
+        // ---- aligner (model/model.py:230-234; neg: 290-294): keys = recon token + words; last layer writes the
+        //      encoder buffer [Bc, Lv+1, 256] behind the global token ----
+        const float* xin = ctx->enh.empty() ? projV : enh;
+        for (size_t l = 0; l < ctx->aln.size(); ++l) {
+            const bool last = (l + 1 == ctx->aln.size());
+            float* dst = last ? p.E : (l % 2 == 0 ? p.xa : p.xb);
+            CK(t2v_layer(ctx->aln[l], words_c, identity_map(), nullptr, Lk, xin, p.posV, Lv, Bc, b0, B, p.padV_all, epad_all,
+                         p.t2v, dst, D, last ? RowMap{Lv, L1, 1} : identity_map(), s));
+            xin = dst;
+        }
+        if (ctx->aln.empty())
+            CK(launch_copy_rows(xin, D, identity_map(), p.E, D, RowMap{Lv, L1, 1}, Rv, s));
+        // ---- transformer encoder (model/transformer.py:185-197) ----
+        float* Ecur = p.E; float* Enext = p.E2;
+        for (size_t l = 0; l < ctx->enc.size(); ++l) {
+            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s));
+            std::swap(Ecur, Enext);
+        }
+        // ---- saliency head (model/model.py:301-302) ----
+        float* sal = neg ? out->neg_saliency_scores : out->saliency_scores;
+        if (sal) {
+            CK(Lin(Re, ctx->sal1, Ecur, D, p.P1, D).run(s));
+            CK(Lin(Bc, ctx->sal2, Ecur, L1 * D, p.P2, D).run(s));
+            CK(launch_saliency(p.P1, RowMap{Lv, L1, 1}, p.P2, Bc, Lv, sal + (size_t)b0 * Lv, s));
+        }
+        if (neg) return 0;
+        if (out->memory) CK(launch_copy_rows(Ecur, D, RowMap{Lv, L1, 1}, out->memory + (size_t)b0 * Lv * D, D, identity_map(), Rv, s));
+        if (out->memory_global) CK(launch_copy_rows(Ecur, D, RowMap{1, L1, 0}, out->memory_global + (size_t)b0 * D, D, identity_map(), Bc, s));
+        // ---- DAB-DETR decoder + class / span heads ----
+        if (out->pred_logits || out->pred_spans || out->aux_logits || out->aux_spans || out->hs) {
+            cudaError_t e = run_decoder(ctx, ctx->qembed, Ecur, p.posE, p.padV, Lv, Bc, p.dec,
+                                        out->pred_logits ? out->pred_logits + (size_t)b0 * nq * 2 : nullptr,
+                                        out->pred_spans ? out->pred_spans + (size_t)b0 * nq * 2 : nullptr,
+                                        out->aux_logits ? out->aux_logits + (size_t)b0 * nq * 2 : nullptr,
+                                        out->aux_spans ? out->aux_spans + (size_t)b0 * nq * 2 : nullptr, (long long)B * nq * 2,
+                                        out->hs ? out->hs + (size_t)b0 * nq * D : nullptr, (long long)B * nq * D, nullptr, 0, s);
+            CK(e);
+        }
+        return 0;
+    };
+
+    for (auto& ch : chunks) { const int rc = video_chunk(ch.first, ch.second, false); if (rc) return rc; }
+
+    // ---- negative branch (model/model.py:260-302): every pair re-scored against the text of another video group ----
+    if (in->neg_index && out->neg_saliency_scores) {
+        CK(launch_gather_blocks(expw, p.negw, in->neg_index, B, (long long)Lk * D, p.epad, p.neg_epad, Lk, s));
+        CK(launch_expand_mask_from_epad(p.neg_epad, B, Lt, p.neg_wpad, s));
+        for (auto& ch : chunks) { const int rc = video_chunk(ch.first, ch.second, true); if (rc) return rc; }
+    }
+    CK(cudaGetLastError());
+    ctx->last_launches = g_stats.launches - launches0;
+    return 0;
+}

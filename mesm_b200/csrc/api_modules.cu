@@ -1,0 +1,164 @@
+// Sub-module entry points of the C ABI: alignment scores, projection-free MHA, T2VEncoder and Transformer
+// (drop-in classes of mesm_b200/model.py call these; the fused mesm_forward does not go through them).
+#include "ctx.h"
+
+using namespace mesm;
+
+namespace {
+__global__ void build_enc_kernel(const float* __restrict__ src, const float* __restrict__ pos, const uint8_t* __restrict__ pad,
+                                 const float* __restrict__ gtok, const float* __restrict__ gpos, int B, int L,
+                                 float* __restrict__ E, float* __restrict__ posE, uint8_t* __restrict__ padE) {
+    const int b = blockIdx.y, i = blockIdx.x, c = threadIdx.x;      // i in [0, L]
+    const long long dst = ((long long)b * (L + 1) + i) * D + c;
+    if (i == 0) {
+        E[dst] = gtok[c]; posE[dst] = gpos[c];
+        if (c == 0) padE[(long long)b * (L + 1)] = 1;
+    } else {
+        const long long srow = ((long long)b * L + i - 1);
+        E[dst] = src[srow * D + c]; posE[dst] = pos[srow * D + c];
+        if (c == 0) padE[(long long)b * (L + 1) + i] = pad[srow];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+size_t mesm_align_workspace_bytes(int32_t B) {
+    const size_t Bp = ((size_t)B + 3) / 4 * 4;
+    return ((size_t)B * D + (size_t)D * Bp) * sizeof(float) + 1024;
+}
+
+int mesm_align_scores(const float* projed_video_feat, const uint8_t* clip_mask, const float* expanded_words_feat,
+                      const uint8_t* expanded_words_mask, int32_t B, int32_t Lv, int32_t Lw, float tau, float* scores,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    mesm_ctx* ctx = nullptr;
+    if (!projed_video_feat || !clip_mask || !expanded_words_feat || !expanded_words_mask || !scores || !workspace || B < 1)
+        return fail(ctx, 1, "mesm_align_scores: bad argument");
+    if (workspace_bytes < mesm_align_workspace_bytes(B)) return fail(ctx, 1, "mesm_align_scores: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Bp = (B + 3) / 4 * 4;
+    Arena ar(workspace, workspace_bytes);
+    float* clipn = ar.get<float>((size_t)B * D);
+    float* wordsT = ar.get<float>((size_t)D * Bp);
+    CK(launch_masked_mean_norm(projed_video_feat, clip_mask, B, Lv, clipn, D, 0, s));
+    CK(launch_masked_mean_norm(expanded_words_feat, expanded_words_mask, B, Lw, wordsT, Bp, 1, s));
+    LinearOp op = make_linear(B, B, D, clipn, D, wordsT, Bp, nullptr, scores, B);
+    op.out_scale = 1.f / tau;
+    CK(launch_linear(op, s));
+    return 0;
+}
+
+size_t mesm_mha_workspace_bytes(int32_t L, int32_t S, int32_t B, int32_t E, int32_t Ev) {
+    (void)S; (void)E;
+    const size_t Kp = ((size_t)Ev + 15) / 16 * 16, ldw = ((size_t)Ev + 3) / 4 * 4;
+    return ((size_t)L * B * Ev + Kp * ldw) * sizeof(float) + 1024;
+}
+
+int mesm_mha_noproj(const float* q, const float* k, const float* v, int32_t L, int32_t S, int32_t B, int32_t E, int32_t Ev,
+                    int32_t nheads, const float* out_w, const float* out_b, const uint8_t* key_padding_mask, float* out,
+                    float* attn_weights, void* workspace, size_t workspace_bytes, void* stream) {
+    mesm_ctx* ctx = nullptr;
+    if (!q || !k || !v || !out_w || !out || !workspace || L < 1 || S < 1 || B < 1 || nheads < 1 || E % nheads || Ev % nheads ||
+        (E / nheads) % 4)
+        return fail(ctx, 1, "mesm_mha_noproj: bad argument");
+    if (workspace_bytes < mesm_mha_workspace_bytes(L, S, B, E, Ev)) return fail(ctx, 1, "mesm_mha_noproj: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    float* attn = ar.get<float>((size_t)L * B * Ev);
+    const int Kp = (Ev + 15) / 16 * 16, ldw = (Ev + 3) / 4 * 4;
+    float* Wt = ar.get<float>((size_t)Kp * ldw);
+    CK(launch_transpose_pack(out_w, 0, Ev, Ev, Wt, ldw, Kp, s));
+    if (attn_weights) CK(launch_fill(attn_weights, (long long)B * L * S, 0.f, s));
+    MhaSmallArgs a;
+    a.q = q; a.ldq = E; a.q2 = nullptr; a.ldq2 = 0; a.k = k; a.ldk = E; a.k2 = nullptr; a.ldk2 = 0; a.v = v; a.ldv = Ev;
+    a.k_pad = key_padding_mask; a.out = attn; a.ldo = Ev; a.attn_w = attn_weights;
+    a.B = B; a.L = L; a.S = S; a.nheads = nheads; a.hq = E / nheads; a.hv = Ev / nheads;
+    a.scale = 1.f / sqrtf((float)(E / nheads));
+    a.q_bs = 1; a.q_is = B; a.k_bs = 1; a.k_is = B; a.k_off = 0;          // seq-first [L,B,E] like the reference
+    CK(launch_mha_small(a, s));
+    LinearOp op = make_linear(L * B, Ev, Ev, attn, Ev, Wt, ldw, out_b, out, Ev);
+    CK(launch_linear(op, s));
+    return 0;
+}
+
+size_t mesm_t2v_workspace_bytes(int32_t B, int32_t Lt, int32_t Lv) {
+    const size_t Rv = (size_t)B * Lv, Rt = (size_t)B * Lt;
+    return (Rt * 2 * D + Rv * D * 6 + Rv * FF) * sizeof(float) + 4096;
+}
+
+int mesm_t2v_encoder(mesm_ctx* ctx, const char* prefix, const float* src_txt, const float* src_vid, const uint8_t* txt_pad,
+                     const uint8_t* vid_pad, const float* pos_txt, const float* pos_vid, int32_t B, int32_t Lt, int32_t Lv,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx) return 1;
+    if (!ctx->finalized) return fail(ctx, 1, "mesm_t2v_encoder: weights not finalized");
+    if (!prefix || !src_txt || !src_vid || !txt_pad || !vid_pad || !out || !workspace || B < 1 || Lt < 1 || Lv < 1 || Lv > 1024)
+        return fail(ctx, 1, "mesm_t2v_encoder: bad argument");
+    const std::vector<AttnFfn>* layers = nullptr;
+    const std::string p(prefix);
+    if (p == "enhance_encoder") layers = &ctx->enh;
+    else if (p == "t2v_encoder") layers = &ctx->aln;
+    else return fail(ctx, 1, "mesm_t2v_encoder: prefix must be enhance_encoder or t2v_encoder");
+    if (workspace_bytes < mesm_t2v_workspace_bytes(B, Lt, Lv)) return fail(ctx, 1, "mesm_t2v_encoder: workspace too small");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    const size_t Rv = (size_t)B * Lv, Rt = (size_t)B * Lt;
+    T2VBuffers t;
+    t.KV = ar.get<float>(Rt * 2 * D); t.Q = ar.get<float>(Rv * D); t.AO = ar.get<float>(Rv * D); t.X1 = ar.get<float>(Rv * D);
+    t.Y1 = ar.get<float>(Rv * D); t.H = ar.get<float>(Rv * FF);
+    float* xa = ar.get<float>(Rv * D); float* xb = ar.get<float>(Rv * D);
+    const float* x = src_vid;
+    for (size_t l = 0; l < layers->size(); ++l) {
+        float* dst = (l + 1 == layers->size()) ? out : (l % 2 == 0 ? xa : xb);
+        CK(t2v_layer((*layers)[l], src_txt, identity_map(), pos_txt, Lt, x, pos_vid, Lv, B, 0, B, vid_pad, txt_pad, t, dst, D,
+                     identity_map(), s));
+        x = dst;
+    }
+    if (layers->empty()) CK(cudaMemcpyAsync(out, src_vid, Rv * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+size_t mesm_transformer_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t L) {
+    if (!ctx) return 0;
+    Arena ar(nullptr, 0);
+    const size_t Re = (size_t)B * (L + 1);
+    ar.get<float>(Re * D); ar.get<float>(Re * D); ar.get<float>(Re * D); ar.get<uint8_t>(Re);
+    ar.get<float>(Re * 3 * D); ar.get<float>(Re * D); ar.get<float>(Re * D); ar.get<float>(Re * FF);
+    DecBuffers d;
+    dec_alloc(ar, d, B, ctx->cfg.num_queries, L + 1, ctx->cfg.dec_layers);
+    return ar.off + 4096;
+}
+
+int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const float* query_embed, const float* pos_embed,
+                     const float* global_token, const float* global_token_pos, int32_t B, int32_t L, float* hs,
+                     float* references, float* memory_local, float* memory_global, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    if (!ctx) return 1;
+    if (!ctx->finalized) return fail(ctx, 1, "mesm_transformer: weights not finalized");
+    if (!src || !pad || !query_embed || !pos_embed || !global_token || !global_token_pos || !workspace || B < 1 || L < 1 || L > 1023)
+        return fail(ctx, 1, "mesm_transformer: bad argument");
+    if (workspace_bytes < mesm_transformer_workspace_bytes(ctx, B, L)) return fail(ctx, 1, "mesm_transformer: workspace too small");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int L1 = L + 1, nq = ctx->cfg.num_queries;
+    const size_t Re = (size_t)B * L1;
+    Arena ar(workspace, workspace_bytes);
+    float* E = ar.get<float>(Re * D); float* E2 = ar.get<float>(Re * D); float* posE = ar.get<float>(Re * D);
+    uint8_t* padE = ar.get<uint8_t>(Re);
+    EncBuffers eb;
+    eb.QKV = ar.get<float>(Re * 3 * D); eb.AO = ar.get<float>(Re * D); eb.Y1 = ar.get<float>(Re * D); eb.H = ar.get<float>(Re * FF);
+    DecBuffers d;
+    dec_alloc(ar, d, B, nq, L1, ctx->cfg.dec_layers);
+    build_enc_kernel<<<dim3(L1, B), D, 0, s>>>(src, pos_embed, pad, global_token, global_token_pos, B, L, E, posE, padE);
+    g_stats.launches++;
+    float* cur = E; float* nxt = E2;
+    for (size_t l = 0; l < ctx->enc.size(); ++l) { CK(enc_layer(ctx->enc[l], cur, posE, padE, L1, B, eb, nxt, s)); std::swap(cur, nxt); }
+    if (memory_local) CK(launch_copy_rows(cur, D, RowMap{L, L1, 1}, memory_local, D, identity_map(), (long long)B * L, s));
+    if (memory_global) CK(launch_copy_rows(cur, D, RowMap{1, L1, 0}, memory_global, D, identity_map(), B, s));
+    if (hs || references)
+        CK(run_decoder(ctx, query_embed, cur, posE, pad, L, B, d, nullptr, nullptr, nullptr, nullptr, 0, hs, (long long)B * nq * D,
+                       references, (long long)B * nq * 2, s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// Attention cores of the MESM path (fp32 SIMT; QK^T / PV are ~2-5 % of the path's FLOPs).
+//
+//   mha_rows_kernel   one thread per query row, K_h / V_h of one (pair, head) resident in shared memory,
+//                     blocked online softmax.  Used for the T2V cross-attention (<= 33 text keys, with the
+//                     reference's attn_mask quirk) and the encoder self-attention (<= Lv+1 keys).
+//   dec_self_attn     10 x 10 decoder self-attention, one CTA per pair, one warp per head.
+//   dec_cross_attn    10 queries x Lv keys, per-head [content ; sine] operands (hd 64), value hd 32.
+//   recon_pool        SS-MESM single-query attention evaluated on the *unprojected* clip rows
+//                     (scores = (Wk_h^T q_h) . x_k, output = Wv_h (sum_k p_k x_k) + b): no K/V projection of the clips.
+#include "kernels.h"
+#include <math_constants.h>
+
+namespace mesm {
+
+// ---------------------------------------------------------------------------------------------------------------
+// mha_rows_kernel
+// ---------------------------------------------------------------------------------------------------------------
+
+template <bool QUIRK>
+__global__ void mha_rows_kernel(const MhaRowsArgs a) {
+    extern __shared__ float smem[];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int Lk = a.Lk;
+    float* Ks = smem;                       // [Lk][33]
+    float* Vs = Ks + Lk * 33;               // [Lk][33]
+    uint8_t* pad_own = reinterpret_cast<uint8_t*>(Vs + Lk * 33);     // [Lk]
+    uint8_t* pad_oth = pad_own + Lk;                                  // [Lk]   k_pad of pair b'
+    const int bg = a.b0 + b;                                           // global pair index
+    const int bp = QUIRK ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
+
+    for (int idx = threadIdx.x; idx < Lk * 32; idx += blockDim.x) {
+        const int kk = idx >> 5, j = idx & 31;
+        const long long row = (long long)b * Lk + kk;
+        Ks[kk * 33 + j] = a.k[row * a.ldk + h * 32 + j];
+        Vs[kk * 33 + j] = a.v[row * a.ldv + h * 32 + j];
+    }
+    for (int kk = threadIdx.x; kk < Lk; kk += blockDim.x) {
+        pad_own[kk] = a.k_pad[(long long)bg * Lk + kk];
+        pad_oth[kk] = QUIRK ? a.k_pad[(long long)bp * Lk + kk] : 0;
+    }
+    __syncthreads();
+
+    const int i = threadIdx.x;
+    if (i >= a.Lq) return;
+    const long long qrow = (long long)b * a.Lq + i;
+    float q[32], o[32];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(a.q + qrow * a.ldq + h * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = qp[j];
+            q[4 * j] = t.x * a.q_scale; q[4 * j + 1] = t.y * a.q_scale; q[4 * j + 2] = t.z * a.q_scale; q[4 * j + 3] = t.w * a.q_scale;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = 0.f;
+    const bool qpad_oth = QUIRK ? (a.q_pad[(long long)bp * a.Lq + i] != 0) : false;
+    float m = -CUDART_INF_F, l = 0.f;
+
+    for (int k0 = 0; k0 < Lk; k0 += 4) {
+        float s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int kk = k0 + u;
+            float acc = -CUDART_INF_F;
+            if (kk < Lk) {
+                const bool masked = pad_own[kk] || (qpad_oth && pad_oth[kk]);
+                if (!masked) {
+                    acc = 0.f;
+                    const float* kr = Ks + kk * 33;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc = fmaf(q[j], kr[j], acc);
+                }
+            }
+            s[u] = acc;
+        }
+        const float bm = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+        if (bm == -CUDART_INF_F) continue;
+        const float mn = fmaxf(m, bm);
+        const float sc = __expf(m - mn);      // m = -inf on first block -> 0
+        l *= sc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] *= sc;
+        m = mn;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (s[u] == -CUDART_INF_F) continue;
+            const float p = __expf(s[u] - mn);
+            l += p;
+            const float* vr = Vs + (k0 + u) * 33;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaf(p, vr[j], o[j]);
+        }
+    }
+    const float inv = 1.f / l;                 // l == 0 (all keys masked) -> inf*0 = NaN like the reference
+    float4* op = reinterpret_cast<float4*>(a.out + qrow * a.ldo + h * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) op[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+}
+
+cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s) {
+    if (a.B <= 0 || a.Lq <= 0) return cudaSuccess;
+    const int threads = ((a.Lq + 31) / 32) * 32;
+    if (threads > 1024) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)a.Lk * 33 * 2 * sizeof(float) + 2 * (size_t)a.Lk;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    dim3 grid(NH, a.B);
+    if (a.q_pad) {
+        if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(mha_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mha_rows_kernel<true><<<grid, threads, smem, s>>>(a);
+    } else {
+        if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(mha_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mha_rows_kernel<false><<<grid, threads, smem, s>>>(a);
+    }
+    g_stats.launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic projection-free MHA (model/attention.py:185-394) for the drop-in MultiheadAttention class and the decoder:
+// q rows (b*L + i) with E = nheads*hq columns, k rows (b*S + j), v rows with nheads*hv columns.  One CTA per
+// (head, pair); thread-per-key scores into shared memory, warp-per-query softmax, thread-per-(query,dim) PV.
+// ---------------------------------------------------------------------------------------------------------------
+
+__global__ void mha_small_kernel(const MhaSmallArgs a) {
+    extern __shared__ float smem[];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int L = a.L, S = a.S, hq = a.hq, hv = a.hv;
+    const int nparts = a.q2 ? 2 : 1;
+    const int E = hq * nparts;
+    float* Qs = smem;                 // [L][E]
+    float* Sc = Qs + L * E;           // [L][S]
+    for (int idx = threadIdx.x; idx < L * E; idx += blockDim.x) {
+        const int i = idx / E, c = idx % E;
+        const long long row = (long long)b * a.q_bs + (long long)i * a.q_is;
+        const float val = c < hq ? a.q[row * a.ldq + h * hq + c] : a.q2[row * a.ldq2 + h * hq + (c - hq)];
+        Qs[idx] = val * a.scale;
+    }
+    __syncthreads();
+    // scores: thread per key
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const bool masked = a.k_pad && a.k_pad[(long long)b * S + j];
+        const long long krow = (long long)b * a.k_bs + (long long)j * a.k_is + a.k_off;
+        for (int i0 = 0; i0 < L; i0 += 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!masked) {
+                for (int part = 0; part < nparts; ++part) {
+                    const float* kp = part == 0 ? a.k + krow * a.ldk + h * hq : a.k2 + krow * a.ldk2 + h * hq;
+                    for (int c = 0; c < hq; c += 4) {
+                        const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (i0 + u < L) {
+                                const float* qr = Qs + (i0 + u) * E + part * hq + c;
+                                acc[u] = fmaf(qr[0], kv.x, fmaf(qr[1], kv.y, fmaf(qr[2], kv.z, fmaf(qr[3], kv.w, acc[u]))));
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u < L) Sc[(i0 + u) * S + j] = masked ? -CUDART_INF_F : acc[u];
+        }
+    }
+    __syncthreads();
+    // softmax: warp per query row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < L; i += nwarps) {
+        float* row = Sc + i * S;
+        float m = -CUDART_INF_F;
+        for (int j = lane; j < S; j += 32) m = fmaxf(m, row[j]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < S; j += 32) { const float p = __expf(row[j] - m); row[j] = p; sum += p; }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        for (int j = lane; j < S; j += 32) {
+            const float p = row[j] * inv;
+            row[j] = p;
+            if (a.attn_w) atomicAdd(a.attn_w + ((long long)b * L + i) * S + j, p / a.nheads);
+        }
+    }
+    __syncthreads();
+    // PV: thread per (query, dim)
+    for (int idx = threadIdx.x; idx < L * hv; idx += blockDim.x) {
+        const int i = idx / hv, c = idx % hv;
+        const float* prow = Sc + i * S;
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const long long vrow = (long long)b * a.k_bs + (long long)j * a.k_is + a.k_off;
+            acc = fmaf(prow[j], a.v[vrow * a.ldv + h * hv + c], acc);
+        }
+        a.out[((long long)b * a.q_bs + (long long)i * a.q_is) * a.ldo + h * hv + c] = acc;
+    }
+}
+
+cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s) {
+    if (a.B <= 0 || a.L <= 0) return cudaSuccess;
+    const int E = a.hq * (a.q2 ? 2 : 1);
+    const size_t smem = ((size_t)a.L * E + (size_t)a.L * a.S) * sizeof(float);
+    if (smem > 220 * 1024 || (a.hq & 3)) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.nheads, a.B);
+    mha_small_kernel<<<grid, 128, smem, s>>>(a);
+    g_stats.launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// recon_pool: one masked sentence slot per pair attends over the projected clips of its video group (SegSenRecon,
+// model/model.py:467-488) — evaluated without projecting the clips:
+//   score[h][k] = qk[b,h,:] . x_k          (qk = Wk_h^T q_h, built by the caller; the q.bk term cancels in softmax)
+//   pooled[b,h,:] = sum_k softmax_k(score[h][.]) x_k     (caller applies Wv_h and bv)
+// Key set of pair b: its own Lv rows (charades / tacos branch, model.py:186-189) or the valid rows of every pair of
+// its group, concatenated (qvhighlights branch, model.py:191-195).  Mask = reference quirk (see t2v_mask in the
+// oracle): masked = kpad[b,k] | (qpad[b',slot_b] & kpad[b',k]), b' = (b*H+h) % B, qpad[b',s] = s >= num_clips[g(b')].
+// ---------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) recon_pool_kernel(const ReconPoolArgs a) {
+    extern __shared__ float smem[];
+    float* Sc = smem;                                  // [8][max_keys]
+    int* krow = reinterpret_cast<int*>(Sc + 8 * a.max_keys);   // [max_keys] global row index of key k (-1 = padded)
+    __shared__ int s_nkeys;
+    const int bl = blockIdx.x, b = a.b0 + blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = a.pair_group[b], slot = a.pair_slot[b];
+    const int Lv = a.Lv;
+
+    // key list
+    if (a.qvh) {
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int p = a.group_start[g]; p < a.group_start[g + 1]; ++p)
+                for (int i = 0; i < Lv; ++i)
+                    if (a.vmask[(long long)p * Lv + i]) krow[n++] = (p - a.b0) * Lv + i;
+            s_nkeys = n;
+        }
+    } else {
+        for (int i = threadIdx.x; i < Lv; i += blockDim.x) krow[i] = a.vmask[(long long)b * Lv + i] ? bl * Lv + i : -1;
+        if (threadIdx.x == 0) s_nkeys = Lv;
+    }
+    __syncthreads();
+    const int nk = s_nkeys;
+
+    // quirk partner of this (pair, head)
+    const int bp = (int)(((long long)b * NH + h) % a.Btot);
+    const int gp = a.pair_group[bp];
+    const bool qpad_oth = slot >= (a.group_start[gp + 1] - a.group_start[gp]);
+
+    float qv[8];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(a.qk + ((long long)bl * NH + h) * D + lane * 8);
+        const float4 t0 = qp[0], t1 = qp[1];
+        qv[0] = t0.x; qv[1] = t0.y; qv[2] = t0.z; qv[3] = t0.w; qv[4] = t1.x; qv[5] = t1.y; qv[6] = t1.z; qv[7] = t1.w;
+    }
+    float* sc = Sc + h * a.max_keys;
+    for (int k = 0; k < nk; ++k) {
+        const int r = krow[k];
+        bool masked = r < 0;
+        if (!masked && qpad_oth) {
+            const bool kpad_oth = a.qvh ? (k >= a.group_len[gp]) : (a.vmask[(long long)bp * Lv + k] == 0);
+            masked = kpad_oth;
+        }
+        float s = -CUDART_INF_F;
+        if (!masked) {
+            const float4* xp = reinterpret_cast<const float4*>(a.x + (long long)r * a.ldx + lane * 8);
+            const float4 t0 = xp[0], t1 = xp[1];
+            float d = qv[0] * t0.x;
+            d = fmaf(qv[1], t0.y, d); d = fmaf(qv[2], t0.z, d); d = fmaf(qv[3], t0.w, d);
+            d = fmaf(qv[4], t1.x, d); d = fmaf(qv[5], t1.y, d); d = fmaf(qv[6], t1.z, d); d = fmaf(qv[7], t1.w, d);
+            s = warp_sum(d);
+        }
+        if (lane == 0) sc[k] = s;
+    }
+    __syncwarp();
+    float m = -CUDART_INF_F;
+    for (int k = lane; k < nk; k += 32) m = fmaxf(m, sc[k]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < nk; k += 32) { const float p = __expf(sc[k] - m); sc[k] = p; sum += p; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    __syncwarp();
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nk; ++k) {
+        const float p = sc[k];
+        if (p == 0.f) continue;                        // warp-uniform
+        const float4* xp = reinterpret_cast<const float4*>(a.x + (long long)krow[k] * a.ldx + lane * 8);
+        const float4 t0 = xp[0], t1 = xp[1];
+        acc[0] = fmaf(p, t0.x, acc[0]); acc[1] = fmaf(p, t0.y, acc[1]); acc[2] = fmaf(p, t0.z, acc[2]); acc[3] = fmaf(p, t0.w, acc[3]);
+        acc[4] = fmaf(p, t1.x, acc[4]); acc[5] = fmaf(p, t1.y, acc[5]); acc[6] = fmaf(p, t1.z, acc[6]); acc[7] = fmaf(p, t1.w, acc[7]);
+    }
+    float4* op = reinterpret_cast<float4*>(a.pooled + ((long long)bl * NH + h) * D + lane * 8);
+    op[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    op[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+}
+
+cudaError_t launch_recon_pool(const ReconPoolArgs& a, cudaStream_t s) {
+    if (a.B <= 0) return cudaSuccess;
+    const size_t smem = (size_t)a.max_keys * (8 * sizeof(float) + sizeof(int));
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(recon_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    recon_pool_kernel<<<a.B, 256, smem, s>>>(a);
+    g_stats.launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace mesm

@@ -1,0 +1,85 @@
+// Shared declarations of the mesm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mesm {
+
+constexpr int D = 256;      // hidden_dim of every shipped config (config/*/*.json: "hidden_dim": 256)
+constexpr int NH = 8;       // nheads
+constexpr int HD = 32;      // head dim
+constexpr int FF = 1024;    // dim_feedforward
+
+// Rows of a [groups, rows_per_group, C] tensor embedded in a buffer whose groups are `stride` rows apart and start
+// `offset` rows in (e.g. the Lv clip rows inside the [B, Lv+1, 256] encoder buffer that carries the global token).
+struct RowMap {
+    int group;    // rows per group in the logical row index; 0 = identity
+    int stride;   // rows between group starts in the buffer
+    int offset;   // first row of the group in the buffer
+    __host__ __device__ inline long long operator()(int r) const {
+        if (group == 0) return r;
+        int g = r / group;
+        return (long long)g * stride + offset + (r - g * group);
+    }
+};
+static inline RowMap identity_map() { return RowMap{0, 0, 0}; }
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_PRELU = 2, ACT_SIGMOID = 3 };
+
+// out = epilogue( (A (+ Apos)) [M,K] . Wt[K,N]  (+ (A2)[M,K2] . Wt2[K2,N]) )
+// epilogue order: LN-fold (rowstat/colsum) -> + bias -> * out_scale -> activation -> + residual -> LayerNorm(N)
+struct LinearOp {
+    int M, N, K;
+    const float* A;   int lda;   RowMap amap;     // A[M,K] fp32 row-major (lda floats between rows)
+    const float* Apos;                            // optional addend on A (same shape / lda / map), e.g. positional enc.
+    const float* Wt;  int ldw;                    // weights pre-transposed: Wt[k*ldw + n], K rows zero-padded to /16
+    int K2; const float* A2; int lda2; RowMap a2map; const float* Wt2;   // optional second input (same ldw)
+    const float* bias;                            // [N] or null
+    const float* rowstat;                         // [M,2] (mean, rstd) of A rows: LayerNorm folded into the GEMM
+    const float* colsum;                          // [N]  sum_k Wt[k,n]  (weights already carry gamma)
+    float out_scale;                              // applied after bias (attention q scaling); 1 = none
+    int act; const float* prelu;                  // PReLU slope (1 element, device)
+    const float* residual; int ldr; RowMap rmap;  // optional fp32 addend [M,N]
+    const float* ln_g; const float* ln_b;         // optional LayerNorm over N (requires N == 256)
+    float* out; int ldo; RowMap omap;
+    float* out2; int ldo2; RowMap o2map;          // optional duplicate store of the final value
+    float* pre_ln;                                // optional store of the value before LayerNorm ([M,N], ld = N)
+};
+
+static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda, const float* Wt, int ldw,
+                                   const float* bias, float* out, int ldo) {
+    LinearOp op;
+    op.M = M; op.N = N; op.K = K; op.A = A; op.lda = lda; op.amap = identity_map(); op.Apos = nullptr;
+    op.Wt = Wt; op.ldw = ldw; op.K2 = 0; op.A2 = nullptr; op.lda2 = 0; op.a2map = identity_map(); op.Wt2 = nullptr;
+    op.bias = bias; op.rowstat = nullptr; op.colsum = nullptr; op.out_scale = 1.f; op.act = ACT_NONE; op.prelu = nullptr;
+    op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
+    op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr;
+    return op;
+}
+
+// Launch counter + error capture shared by all launchers.
+struct LaunchStats { long long launches = 0; };
+extern thread_local LaunchStats g_stats;
+
+cudaError_t launch_linear(const LinearOp& op, cudaStream_t s);        // dispatcher (tcgen05 when eligible)
+cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s);   // fp32 SIMT kernel
+
+#define MESM_CHECK(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) return _e;                                                        \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace mesm

@@ -1,0 +1,150 @@
+// Internal: context layout and the layer helpers shared by api.cu (fused forward) and api_modules.cu (sub-module
+// entry points).  Not part of the C ABI.
+#pragma once
+#include "../../include/mesm_b200.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace mesm {
+
+struct Tensor {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    size_t n = 0;
+};
+
+struct PL {              // packed linear: Wt[Kp, ldw] (k-major), bias[N]
+    const float* Wt = nullptr;
+    int ldw = 0, K = 0, N = 0;
+    const float* bias = nullptr;
+    const float* colsum = nullptr;   // LayerNorm-folded layers only
+};
+
+struct Norm { const float* g = nullptr; const float* b = nullptr; };
+
+struct AttnFfn {         // T2V / recon / encoder layer
+    PL q, kv, qk, v, out, l1, l2;
+    const float* k_only_Wt = nullptr;      // K rows of in_proj (for the explicit pos_txt path)
+    const float* in_w = nullptr;           // raw in_proj_weight [768,256] (recon back-projection uses row slices)
+    const float* in_b = nullptr;
+    const float* vT = nullptr;             // Wv^T packed [256,256] (recon)
+    Norm n1, n2;
+    const float* prelu = nullptr;
+};
+
+struct DecLayer {
+    PL sa_qc, sa_qp, sa_kc, sa_kp, sa_v, sa_out;
+    PL ca_qc, ca_qp, ca_kc, ca_kp, ca_v, ca_sine, ca_out, l1, l2;
+    const float* sa_q_bias = nullptr;      // b(qcontent)+b(qpos)
+    const float* sa_k_bias = nullptr;
+    const float* ca_q_bias0 = nullptr;     // b(ca_qcontent)+b(ca_qpos)   (layer 0)
+    const float* ca_k_bias0 = nullptr;     // b(ca_kcontent)+b(ca_kpos)   (layer 0)
+    Norm n1, n2, n3;
+    const float* prelu = nullptr;
+};
+
+}  // namespace mesm
+
+using mesm::Tensor; using mesm::PL; using mesm::Norm; using mesm::AttnFfn; using mesm::DecLayer;
+
+struct mesm_ctx {
+    mesm_cfg cfg{};
+    int device = 0;
+    std::string err;
+    std::unordered_map<std::string, Tensor> w;
+    std::vector<void*> owned;
+    bool finalized = false;
+    int chunk_pairs = 256;
+    long long last_launches = 0;
+
+    PL vid0, vid1, txt0, txt1;
+    Norm vid1_ln, txt1_ln;
+    std::vector<AttnFfn> enh, aln, rec, enc;
+    std::vector<DecLayer> dec;
+    Norm dec_norm;
+    PL qs0, qs1, rph0, rph1, bb0, bb1, bb2, ra0, ra1;
+    PL span0, span1, span2, cls, sal1, sal2, osp0, osp1;
+    Norm osp0_ln, osp1_ln;
+    const float *gtok = nullptr, *gpos = nullptr, *msent = nullptr, *qembed = nullptr;
+
+    int* h_tab = nullptr;
+    size_t h_tab_cap = 0;
+    cudaEvent_t tab_event = nullptr;
+    bool tab_event_pending = false;
+};
+
+
+namespace mesm {
+
+int fail(mesm_ctx* c, int code, const std::string& msg);
+
+#define CK(expr)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return mesm::fail(ctx, (int)_e, std::string(#expr) + " failed at " + __FILE__ + ":" + std::to_string(__LINE__) + \
+                                                ": " + cudaGetErrorString(_e));                              \
+    } while (0)
+
+// ---- workspace arena -----------------------------------------------------------------------------------------------
+struct Arena {
+    char* base; size_t off = 0, cap;
+    Arena(void* b, size_t c) : base((char*)b), cap(c) {}
+    template <class T> T* get(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : (T*)nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+    bool fits() const { return base == nullptr || off <= cap; }
+};
+
+struct Lin {    // thin builder around LinearOp
+    LinearOp op;
+    Lin(int M, const PL& w, const float* A, int lda, float* out, int ldo) {
+        op = make_linear(M, w.N, w.K, A, lda, w.Wt, w.ldw, w.bias, out, ldo);
+    }
+    Lin& bias(const float* b) { op.bias = b; return *this; }
+    Lin& amap(RowMap m) { op.amap = m; return *this; }
+    Lin& omap(RowMap m) { op.omap = m; return *this; }
+    Lin& apos(const float* p) { op.Apos = p; return *this; }
+    Lin& second(const float* A2, int lda2, const PL& w2, RowMap m = identity_map()) {
+        op.A2 = A2; op.lda2 = lda2; op.K2 = w2.K; op.Wt2 = w2.Wt; op.a2map = m; return *this;
+    }
+    Lin& act(int a, const float* slope = nullptr) { op.act = a; op.prelu = slope; return *this; }
+    Lin& scale(float s) { op.out_scale = s; return *this; }
+    Lin& fold(const float* rowstat, const float* colsum) { op.rowstat = rowstat; op.colsum = colsum; return *this; }
+    Lin& res(const float* r, int ldr, RowMap m = identity_map()) { op.residual = r; op.ldr = ldr; op.rmap = m; return *this; }
+    Lin& ln(const Norm& n) { op.ln_g = n.g; op.ln_b = n.b; return *this; }
+    Lin& pre_ln(float* p) { op.pre_ln = p; return *this; }
+    cudaError_t run(cudaStream_t s) { return launch_linear(op, s); }
+};
+
+
+constexpr float kScale32 = 0.17677669529663687f;   // 32^-0.5
+constexpr float kScale64 = 0.125f;                 // 64^-0.5
+
+struct T2VBuffers { float *KV, *Q, *AO, *X1, *Y1, *H; };
+struct EncBuffers { float *QKV, *AO, *Y1, *H; };
+struct DecBuffers {
+    float *tgtA, *tgtB, *ref, *refs, *sine, *sine_s, *h1, *h2, *qpos, *ptrans, *anc, *qsa, *ksa, *vsa, *ao, *t1, *qca,
+        *sinep, *t2, *hff, *d2, *hs, *Kc, *Kp, *Vd, *tmpref;
+};
+
+cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
+                      const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
+                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s);
+cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
+                      const EncBuffers& t, float* out, cudaStream_t s);
+size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl);
+cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, float* Wt, int ldw, int Kp, cudaStream_t s);
+cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, const float* posE, const uint8_t* padV, int Lv, int Bc,
+                        const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
+                        long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
+                        long long refs_layer_stride, cudaStream_t s);
+
+}  // namespace mesm

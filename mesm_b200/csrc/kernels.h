@@ -1,0 +1,75 @@
+// Internal launcher prototypes (definitions in attention.cu / elementwise.cu / linear_*.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mesm {
+
+struct MhaRowsArgs {
+    const float* q; int ldq;
+    const float* k; int ldk;
+    const float* v; int ldv;
+    const uint8_t* k_pad;
+    const uint8_t* q_pad;
+    float* out; int ldo;
+    int B, Lq, Lk;
+    int b0, Btot;
+    float q_scale;
+};
+cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s);
+
+struct MhaSmallArgs {
+    const float* q; int ldq;  const float* q2; int ldq2;
+    const float* k; int ldk;  const float* k2; int ldk2;
+    const float* v; int ldv;
+    const uint8_t* k_pad;
+    float* out; int ldo;
+    float* attn_w;
+    int B, L, S, nheads, hq, hv;
+    float scale;
+    int q_bs, q_is;            // row of query (b,i) = b*q_bs + i*q_is  (same for out; attn_w is always [B,L,S])
+    int k_bs, k_is, k_off;     // row of key/value (b,j) = b*k_bs + j*k_is + k_off
+};
+cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s);
+
+struct ReconPoolArgs {
+    const float* x; int ldx;
+    const uint8_t* vmask;
+    const float* qk;
+    float* pooled;
+    const int* pair_group;
+    const int* pair_slot;
+    const int* group_start;
+    const int* group_len;
+    int B, Lv, qvh, max_keys;
+    int b0, Btot;
+};
+cudaError_t launch_recon_pool(const ReconPoolArgs& a, cudaStream_t s);
+
+struct PosArgs {
+    const uint8_t* vmask; int B, Lv;
+    const float* gtok; const float* gpos;
+    float* posV; float* posE; float* encbuf; uint8_t* padV; uint8_t* padE;
+};
+cudaError_t launch_pos_embed(const PosArgs& a, cudaStream_t s);
+
+cudaError_t launch_text_prep(const float* x, int R, int Dt, float* y, uint8_t* mask, float* rowstat, cudaStream_t s);
+cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float* rowstat, cudaStream_t s);
+cudaError_t launch_invert_mask(const uint8_t* in, uint8_t* out, long long n, cudaStream_t s);
+cudaError_t launch_expand_mask(const uint8_t* wmask, int B, int Lt, uint8_t* emask, uint8_t* epad, uint8_t* wpad, cudaStream_t s);
+cudaError_t launch_expand_mask_from_epad(const uint8_t* epad, int B, int Lt, uint8_t* wpad, cudaStream_t s);
+cudaError_t launch_gather_blocks(const float* src, float* dst, const int64_t* idx, int B, long long block_elems,
+                                 const uint8_t* msrc, uint8_t* mdst, int mlen, cudaStream_t s);
+cudaError_t launch_copy_rows(const float* src, int lds, RowMap imap, float* dst, int ldd, RowMap omap, long long R, cudaStream_t s);
+cudaError_t launch_broadcast_row(const float* vec, float* dst, long long R, cudaStream_t s);
+cudaError_t launch_l2norm_rows(const float* x, long long R, float* out1, float* out2, int ld2, RowMap map2, cudaStream_t s);
+cudaError_t launch_saliency(const float* p1, RowMap map1, const float* p2, int B, int Lv, float* out, cudaStream_t s);
+cudaError_t launch_dec_init_ref(const float* qe, int B, int nq, float* ref, cudaStream_t s);
+cudaError_t launch_dec_sine(const float* ref, long long R, const float* pos_trans, const float* anchor, float* sine,
+                            float* scaled, cudaStream_t s);
+cudaError_t launch_ref_update(const float* delta, int ldd, const float* ref, long long rows, float* out, cudaStream_t s);
+cudaError_t launch_layernorm_rows(const float* x, long long R, const float* g, const float* b, float* out, cudaStream_t s);
+cudaError_t launch_group_len(const uint8_t* vmask, int Lv, const int* group_start, int G, int* group_len, cudaStream_t s);
+cudaError_t launch_masked_mean_norm(const float* x, const uint8_t* mask, int B, int L, float* out, int ldo, int transposed, cudaStream_t s);
+cudaError_t launch_fill(float* p, long long n, float v, cudaStream_t s);
+
+}  // namespace mesm

@@ -1,0 +1,56 @@
+"""GPU parity of the fused forward (through the C ABI) against the committed reference outputs and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import engine_cfg, golden_cases, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # north star: <= 1e-3 relative (max|a-b| / max|ref|) on logits, spans, saliency
+
+
+def _run(name, chunk_pairs=256):
+    import mesm_b200
+    cfg, sd, inp, neg, gold, meta = load_case(name)
+    eng = mesm_b200.Engine(engine_cfg(cfg), chunk_pairs=chunk_pairs)
+    eng.load_state_dict(sd)
+    dev = eng.device
+    out = eng.forward(inp["video_feat"].to(dev), inp["video_mask"].to(dev), inp["words_feat"].to(dev), inp["num_clips"],
+                      neg_index=neg.to(dev), want=("core", "aux", "rec", "taps"))
+    torch.cuda.synchronize()
+    return cfg, inp, gold, out
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases()))
+def test_forward_matches_reference_golden(name):
+    cfg, inp, gold, out = _run(name)
+    vm = inp["video_mask"]
+    errs = {
+        "pred_logits": rel_err(out["pred_logits"], gold["pred_logits"]),
+        "pred_spans": rel_err(out["pred_spans"], gold["pred_spans"]),
+        "saliency_scores": rel_err(out["saliency_scores"], gold["saliency_scores"], vm),
+        "neg_saliency_scores": rel_err(out["neg_saliency_scores"], gold["neg_saliency_scores"], vm),
+        "recon_feat": rel_err(out["recon_feat"], gold["recon_feat"]),
+        "projed_recon_feat": rel_err(out["projed_recon_feat"], gold["projed_recon_feat"]),
+        "aux_logits": rel_err(out["aux_logits"][0], gold["aux_logits"]),
+        "aux_spans": rel_err(out["aux_spans"][0], gold["aux_spans"]),
+        "projed_words_feat": rel_err(out["expanded_words_feat"][:, 1:], gold["projed_words_feat"]),
+        "projed_video_row0": rel_err(out["projed_video_feat"][:, 0], gold["projed_video_row0"]),
+        "enhanced_video_row0": rel_err(out["enhanced_video_feat"][:, 0], gold["enhanced_video_row0"]),
+    }
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+    # saliency additionally after the .half() of eval.py:68
+    sal_h = out["saliency_scores"].half().float().cpu()
+    ref_h = torch.from_numpy(gold["saliency_scores"]).half().float()
+    assert rel_err(sal_h, ref_h, vm) <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "charades_csf_ragged"])
+def test_chunking_is_invisible(name):
+    """Chunking by video group must not change results (the mask quirk and the negative branch reach across chunks)."""
+    _, inp, gold, a = _run(name, chunk_pairs=256)
+    _, _, _, b = _run(name, chunk_pairs=3)
+    for k in ("pred_logits", "pred_spans", "saliency_scores", "neg_saliency_scores", "recon_feat"):
+        assert torch.equal(a[k], b[k]), k
