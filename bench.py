@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — video-query pairs/sec of the MESM per-pair inference path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W]                 our CUDA path (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference [...]                          the reference algorithm on the host CPU cores
+
+A step = one pass of the whole hot path (MESM.forward incl. the negative branch + span decode / post-processing / NMS)
+over one batch of synthetic pairs of BASELINE.json configs[1]: Charades-STA C+SF shape, 4096 pairs per GPU, inputs
+resident in HBM (9 GB per GPU, far larger than L2).  `e2e` is the same work through the public Python API with the
+inputs starting in pinned HOST memory (H2D inside the timed region) and the ranked windows read back to the host.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHARADES_CSF = dict(dataset_name="charades", v_feat_dim=2818, t_feat_dim=512, hidden_dim=256, nheads=8, dim_feedforward=1024,
+                    num_queries=10, num_recfw_layers=2, t2v_layers=2, enc_layers=2, dec_layers=2, num_recss_layers=4,
+                    n_input_proj=2, rec_fw=True, rec_ss=True, share_MLP=True, max_words_l=16, max_video_l=194,
+                    aux_loss=True, vocab_size=1111, clip_len=1.0, max_ts_val=150.0)
+NMS_THD = 0.7           # shipped configs disable NMS (nms_thd -1); 0.7 is Moment-DETR's convention
+ALGO_FLOPS_PER_PAIR = 2.51e9        # positive path, video projected once, Lv=194
+ALGO_BYTES_PER_PAIR = 2219746       # fp32 feature bytes read per pair
+
+
+def make_workload(cfg, B, seed, device):
+    """Synthetic Charades C+SF batch: video groups of 1-4 queries, ragged Lv ~ U{97..194}, per-source
+    L2-normalised N(0,1) features + tef columns, words N(0,1) with lengths U{3..16}, durations U(10,60)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Lv, Lt, Dv, Dt = cfg["max_video_l"], cfg["max_words_l"], cfg["v_feat_dim"], cfg["t_feat_dim"]
+    nc = []
+    while sum(nc) < B:
+        nc.append(min(int(torch.randint(1, 5, (1,), generator=g)), B - sum(nc)))
+    G = len(nc)
+    vlen_g = torch.randint(Lv // 2, Lv + 1, (G,), generator=g)
+    vlen_g[0] = Lv
+    nct = torch.tensor(nc)
+    vlen = torch.repeat_interleave(vlen_g, nct)
+    dur = torch.repeat_interleave(torch.rand(G, generator=g) * 50 + 10, nct).float()
+    wl = torch.randint(3, Lt + 1, (B,), generator=g)
+    gd = torch.Generator(device=device).manual_seed(seed)
+    video = torch.empty(B, Lv, Dv, dtype=torch.float32, device=device)
+    ar = torch.arange(Lv, device=device)
+    start = 0
+    for gi in range(0, G, 64):                      # build group-wise so that queries of a group share the video
+        gs = list(range(gi, min(gi + 64, G)))
+        x = torch.randn(len(gs), Lv, Dv - 2, device=device, generator=gd)
+        x[..., :512] = torch.nn.functional.normalize(x[..., :512], dim=-1)
+        x[..., 512:] = torch.nn.functional.normalize(x[..., 512:], dim=-1)
+        L = vlen_g[gs].to(device).float()[:, None]
+        tef = torch.stack([ar[None] / L, (ar[None] + 1) / L], dim=-1)
+        x = torch.cat([x, tef], dim=-1) * (ar[None] < L)[..., None]
+        rep = nct[gs].to(device)
+        xr = torch.repeat_interleave(x, rep, dim=0)
+        video[start:start + xr.shape[0]] = xr
+        start += xr.shape[0]
+    mask = ar[None] < vlen.to(device)[:, None]
+    words = torch.randn(B, Lt, Dt, device=device, generator=gd)
+    words = words * (torch.arange(Lt, device=device)[None] < wl.to(device)[:, None])[..., None]
+    # negative index: another video group (vectorised sample_outclass_neg)
+    from mesm_b200.model import sample_outclass_neg
+    neg = sample_outclass_neg(nct, generator=g)
+    return dict(video_feat=video, video_mask=mask, words_feat=words, num_clips=nct, duration=dur.to(device),
+                neg_index=neg.to(device))
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons)}
+
+
+def cpu_reference_pairs_per_s(cfg_name, state_dict, batch, steps, warmup, threads):
+    """The reference algorithm (oracle port, checker code used here only as the CPU baseline) on the host cores."""
+    from oracle import decode_oracle, mesm_oracle
+    from oracle.config import CONFIGS
+    ocfg = CONFIGS[cfg_name]
+    torch.set_num_threads(threads)
+    sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    vf, vm, wf = batch["video_feat"].cpu(), batch["video_mask"].cpu(), batch["words_feat"].cpu()
+    nc, neg, dur = batch["num_clips"].cpu(), batch["neg_index"].cpu(), batch["duration"].cpu()
+    B = vf.shape[0]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        o = mesm_oracle.mesm_forward(sd, ocfg, vf, vm, wf, nc, neg_index=neg)
+        lg, sp = o["pred_logits"].numpy(), o["pred_spans"].numpy()
+        for i in range(B):
+            decode_oracle.decode_pair(lg[i], sp[i], float(dur[i]), ocfg.clip_len, ocfg.max_ts_val, NMS_THD, 10, 10)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return B * len(times) / sum(times), sum(times) / len(times)
+
+
+def take_groups(wl, n_pairs):
+    """First whole video groups covering >= n_pairs pairs (CPU sample of the same workload)."""
+    nc = wl["num_clips"].tolist()
+    tot, k = 0, 0
+    while tot < n_pairs and k < len(nc):
+        tot += nc[k]
+        k += 1
+    from mesm_b200.model import sample_outclass_neg
+    sub = dict(video_feat=wl["video_feat"][:tot], video_mask=wl["video_mask"][:tot], words_feat=wl["words_feat"][:tot],
+               num_clips=wl["num_clips"][:k], duration=wl["duration"][:tot])
+    sub["neg_index"] = sample_outclass_neg(sub["num_clips"], generator=torch.Generator().manual_seed(5))
+    return sub
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="pairs per GPU per step")
+    ap.add_argument("--chunk-pairs", type=int, default=256)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=32)
+    ap.add_argument("--topk", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    cfg = dict(CHARADES_CSF)
+    config = {"workload": "charades_sta_c+sf_inference_batch4096", "config": "configs[1]", "pairs_per_gpu": args.pairs,
+              "Lv": cfg["max_video_l"], "Lt": cfg["max_words_l"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": 512,
+              "ragged_video": "U{97..194}", "negative_branch": True, "nms_thd": NMS_THD, "parallelism": f"dp{world}",
+              "l2": "inputs (9 GB/GPU) larger than L2; no flush needed"}
+
+    from mesm_b200.model import build_model
+    torch.manual_seed(0)
+    model = build_model(cfg)                       # random-init weights of the architecture (no checkpoints offline)
+    with torch.no_grad():                          # exercise the tensors the reference initialises to constants
+        for n, p in model.named_parameters():
+            if n.endswith("bbox_embed.layers.2.weight") or n.endswith("masked_sent_token"):
+                p.normal_(0, 0.02)
+
+    # ------------------------------------------------------------------ reference arm: host CPU cores -----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        wl = make_workload(cfg, 64, 1234, "cpu")
+        sub = take_groups(wl, args.cpu_sample_pairs)
+        pps, sec = cpu_reference_pairs_per_s("charades_csf", model.state_dict(), sub, max(args.steps, 1), min(args.warmup, 2), threads)
+        line = {"impl": "reference", "metric": "video-query pairs/sec", "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                 "sample": f"{sub['video_feat'].shape[0]} pairs of the same workload per step (oracle port of the "
+                                           "reference forward + decode/NMS, torch CPU fp32, all host threads)"},
+                "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm ----------------------------------------
+    import mesm_b200
+    from mesm_b200 import _lib
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    model = model.to(dev)
+    model.chunk_pairs = args.chunk_pairs
+    wl = make_workload(cfg, args.pairs, 1234 + rank, dev)
+    B, Lv = args.pairs, cfg["max_video_l"]
+    lib = _lib.lib()
+    from mesm_b200.sharding import gather_topk
+
+    def step():
+        out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"],
+                    dataset_name="charades", is_training=False, neg_index=wl["neg_index"])
+        win, order, keep, cnt = mesm_b200.decode_nms(out["pred_logits"], out["pred_spans"], wl["duration"], cfg["clip_len"],
+                                                     cfg["max_ts_val"], NMS_THD, 10, 10)
+        return out, win, order, keep, cnt
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            out, win, order, keep, cnt = step()
+            launches += model._eng.last_launch_count + 1
+        top = gather_topk(win, wl["num_clips"], args.topk, rank, world, B)      # one NCCL all_gather of top-k spans
+        ev1.record()
+        torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (fused linear): one extra step with CUDA events around each launch ----------
+    lib.mesm_profile_begin()
+    step()
+    prof = (ctypes.c_double * 7)()
+    lib.mesm_profile_end(prof)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    lin_ms, lin_flops = prof[0], prof[1]
+    roof = {"bound": "tensor", "kernel": "fused linear (all GEMM launches of one step)", "achieved": lin_flops / (lin_ms * 1e-3) / 1e12 if lin_ms else None,
+            "peak": peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback B200_PROFILING.md",
+            "unit": "TFLOP/s", "frac": (lin_flops / (lin_ms * 1e-3) / 1e12 / peak_tf) if lin_ms else None, "traffic": None,
+            "launches_per_step": int(prof[3]), "kernel_ms_per_step": lin_ms, "share_of_step": lin_ms / (ms / args.steps),
+            "hbm_frac_whole_step": (ALGO_BYTES_PER_PAIR * B / (ms / args.steps * 1e-3)) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))}
+
+    # ---- e2e: same work through the public API from pinned host memory, sub-batches double-buffered over two streams -----
+    sub = 512 if B >= 512 else B
+    nsub = B // sub
+    ncs = wl["num_clips"].tolist()
+    # sub-batches must hold whole groups: rebuild a 512-pair slice with its own grouping
+    sb = take_groups(wl, sub)
+    Bs = sb["video_feat"].shape[0]
+    host = {k: sb[k].cpu().pin_memory() for k in ("video_feat", "video_mask", "words_feat", "duration", "neg_index")}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
+    hkeep = [torch.empty(Bs, 10, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def e2e_pass():
+        for i in range(nsub):
+            s, d = streams[i % 2], dbuf[i % 2]
+            with torch.cuda.stream(s):
+                for k, v in host.items():
+                    d[k].copy_(v, non_blocking=True)
+                o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
+                          dataset_name="charades", is_training=False, neg_index=d["neg_index"])
+                w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
+                                                     cfg["max_ts_val"], NMS_THD, 10, 10)
+                hres[i % 2].copy_(w, non_blocking=True)
+                hkeep[i % 2].copy_(kp, non_blocking=True)
+        for s in streams:
+            s.synchronize()
+
+    d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
+    e2e_pass()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_pass()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * Bs * nsub * e2e_steps / float(t)
+
+    line = {"metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d * nsub, "d2h_bytes_per_step": d2h * nsub,
+                    "note": f"{nsub} sub-batches of {Bs} pairs, pinned host -> device on two streams, windows + keep sets back to host"},
+            "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        cs = take_groups(wl, args.cpu_sample_pairs)
+        pps, sec = cpu_reference_pairs_per_s("charades_csf", model.state_dict(), cs, 3, 1, threads)
+        line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": f"{cs['video_feat'].shape[0]} pairs of the same workload, 3 timed iterations after 1 warm-up "
+                                          "(oracle port of the reference forward + decode/NMS, torch CPU fp32)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,12 @@ int    mesm_set_chunk_pairs(mesm_ctx* ctx, int32_t pairs);
 /* Number of kernel launches the last mesm_forward issued (bench.py's gpu_launches). */
 int64_t mesm_last_launch_count(const mesm_ctx* ctx);
 
+/* Measurement aid for bench.py: between begin/end every fused-linear launch of the calling thread is bracketed by CUDA
+ * events on its stream.  end() synchronises those events and writes {linear ms, algorithmic flops, algorithmic bytes,
+ * launches, ms / flops / launches of the launches with M >= 16384}. */
+void mesm_profile_begin(void);
+void mesm_profile_end(double* out7);
+
 /* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
 /* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),
  * PostProcessorDETR as configured at eval.py:111-115 (utils/post_processing.py:22-47) and, when nms_thd != -1,
@@ -134,6 +140,11 @@ int mesm_decode_nms(const float* pred_logits,   /* dev [B,nq,2] */
  * keep[i, :keep_count[i]] = positions (within list i) of the survivors in output order. */
 int mesm_temporal_nms(const double* windows, const int64_t* offsets, int32_t n_lists, double nms_thd,
                       int32_t max_after_nms, int32_t* keep, int32_t* keep_count, void* stream);
+
+/* replaces PostProcessorDETR.__call__ (utils/post_processing.py:22-47) with process_func_names ("clip_ts",
+ * "round_multiple") [clip_len == -1: ("clip_ts",)] on n already-decoded fp64 rows [st, ed, score]. */
+int mesm_post_process(const double* windows, double* out, int64_t n, double clip_len, double min_ts_val,
+                      double max_ts_val, void* stream);
 
 /* replaces utils/span_utils.py: temporal_iou (45-72), generalized_temporal_iou (92-121) on fp32 [N,2] x [M,2] -> [N,M];
  * any output may be NULL. */

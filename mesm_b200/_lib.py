@@ -48,9 +48,12 @@ SYMBOLS = {
     "mesm_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "mesm_forward": (c_int, [c_void_p, POINTER(MesmInputs), POINTER(MesmOutputs), c_void_p, c_size_t, c_void_p]),
     "mesm_last_launch_count": (c_int64, [c_void_p]),
+    "mesm_profile_begin": (None, []),
+    "mesm_profile_end": (None, [POINTER(c_double)]),
     "mesm_decode_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(MesmDecodeParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mesm_temporal_nms": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),
+    "mesm_post_process": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p]),
     "mesm_temporal_iou": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mesm_span_convert": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "mesm_align_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p,

@@ -76,12 +76,8 @@ struct Packer {
     }
     const Tensor* get(const std::string& key, std::initializer_list<int64_t> shape) {
         auto it = ctx->w.find(key);
-        if (it == ctx->w.end()) { ok = false; if (missing.size() < 400) missing += key + " "; return nullptr; }
-        if (std::vector<int64_t>(shape) != it->second.shape) {
-            ok = false;
-            if (missing.size() < 400) missing += key + "(shape) ";
-            return nullptr;
-        }
+        if (it == ctx->w.end()) { missing += key + " "; return nullptr; }
+        if (std::vector<int64_t>(shape) != it->second.shape) { missing += key + "(shape) "; return nullptr; }
         return &it->second;
     }
     const float* vec(const std::string& key, int64_t n) { const Tensor* t = get(key, {n}); return t ? t->p : nullptr; }
@@ -304,7 +300,32 @@ int check_cfg(const mesm_cfg* c, std::string& why) {
 }  // namespace
 
 namespace mesm {
-cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) { return launch_linear_simt(op, s); }
+struct ProfRec { cudaEvent_t a, b; double flops, bytes; int M; };
+static thread_local std::vector<ProfRec> g_prof;
+cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) {
+    if (!g_stats.profile) return launch_linear_simt(op, s);
+    ProfRec r;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    r.flops = 2.0 * op.M * (double)op.N * ((double)op.K + op.K2);
+    r.bytes = 4.0 * ((double)op.M * (op.K + op.K2) + (double)op.M * op.N + (double)op.N * (op.K + op.K2));
+    r.M = op.M;
+    cudaEventRecord(r.a, s);
+    cudaError_t e = launch_linear_simt(op, s);
+    cudaEventRecord(r.b, s);
+    g_prof.push_back(r);
+    return e;
+}
+void profile_collect() {
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        g_stats.lin_ms += ms; g_stats.lin_flops += r.flops; g_stats.lin_bytes += r.bytes; g_stats.lin_launches++;
+        if (r.M >= 16384) { g_stats.big_ms += ms; g_stats.big_flops += r.flops; g_stats.big_launches++; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+}
 }  // namespace mesm
 
 // =====================================================================================================================
@@ -350,6 +371,21 @@ int mesm_set_chunk_pairs(mesm_ctx* ctx, int32_t pairs) {
 
 int64_t mesm_last_launch_count(const mesm_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
 
+void mesm_profile_begin(void) {
+    g_stats.profile = true;
+    g_stats.lin_ms = g_stats.lin_flops = g_stats.lin_bytes = 0; g_stats.lin_launches = 0;
+    g_stats.big_ms = g_stats.big_flops = 0; g_stats.big_launches = 0;
+}
+
+void mesm_profile_end(double* out7) {
+    mesm::profile_collect();
+    g_stats.profile = false;
+    if (out7) {
+        out7[0] = g_stats.lin_ms; out7[1] = g_stats.lin_flops; out7[2] = g_stats.lin_bytes; out7[3] = (double)g_stats.lin_launches;
+        out7[4] = g_stats.big_ms; out7[5] = g_stats.big_flops; out7[6] = (double)g_stats.big_launches;
+    }
+}
+
 int mesm_load_weight(mesm_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim, int is_device,
                      void* stream) {
     if (!ctx || !key || !data || ndim < 0 || ndim > 4) return fail(ctx, 1, "mesm_load_weight: bad argument");
@@ -392,19 +428,20 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
     }
     ctx->enh.clear(); ctx->aln.clear(); ctx->rec.clear(); ctx->enc.clear(); ctx->dec.clear();
     if (cf.rec_fw)
-        for (int i = 0; i < cf.num_recfw_layers; ++i) ctx->enh.push_back(P.attn_ffn("enhance_encoder.t2v_encoder.layers." + std::to_string(i) + ".", false));
-    for (int i = 0; i < cf.t2v_layers; ++i) ctx->aln.push_back(P.attn_ffn("t2v_encoder.t2v_encoder.layers." + std::to_string(i) + ".", false));
+        for (int i = 0; i < cf.num_recfw_layers; ++i) { const size_t m0 = P.missing.size(); AttnFfn L = P.attn_ffn("enhance_encoder.t2v_encoder.layers." + std::to_string(i) + ".", false); if (P.missing.size() == m0) ctx->enh.push_back(L); }
+    for (int i = 0; i < cf.t2v_layers; ++i) { const size_t m0 = P.missing.size(); AttnFfn L = P.attn_ffn("t2v_encoder.t2v_encoder.layers." + std::to_string(i) + ".", false); if (P.missing.size() == m0) ctx->aln.push_back(L); }
     if (cf.rec_ss) {
-        for (int i = 0; i < cf.num_recss_layers; ++i) ctx->rec.push_back(P.attn_ffn("ss_reconstructor.recon_trans.layers." + std::to_string(i) + ".", true));
+        for (int i = 0; i < cf.num_recss_layers; ++i) { const size_t m0 = P.missing.size(); AttnFfn L = P.attn_ffn("ss_reconstructor.recon_trans.layers." + std::to_string(i) + ".", true); if (P.missing.size() == m0) ctx->rec.push_back(L); }
         ctx->msent = P.vec("ss_reconstructor.masked_sent_token", D);
         ctx->osp0_ln = P.norm("ss_reconstructor.output_sent_proj.0.LayerNorm");
         ctx->osp0 = P.lin("ss_reconstructor.output_sent_proj.0.net.1", D, D);
         ctx->osp1_ln = P.norm("ss_reconstructor.output_sent_proj.1.LayerNorm");
         ctx->osp1 = P.lin("ss_reconstructor.output_sent_proj.1.net.1", D, D);
     }
-    for (int i = 0; i < cf.enc_layers; ++i) ctx->enc.push_back(P.attn_ffn("transformer.encoder.layers." + std::to_string(i) + ".", false));
+    for (int i = 0; i < cf.enc_layers; ++i) { const size_t m0 = P.missing.size(); AttnFfn L = P.attn_ffn("transformer.encoder.layers." + std::to_string(i) + ".", false); if (P.missing.size() == m0) ctx->enc.push_back(L); }
     for (int i = 0; i < cf.dec_layers; ++i) {
         const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".";
+        const size_t dec_m0 = P.missing.size();
         DecLayer L;
         L.sa_qc = P.lin(p + "sa_qcontent_proj", D, D); L.sa_qp = P.lin(p + "sa_qpos_proj", D, D);
         L.sa_kc = P.lin(p + "sa_kcontent_proj", D, D); L.sa_kp = P.lin(p + "sa_kpos_proj", D, D);
@@ -422,7 +459,7 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
             L.ca_q_bias0 = P.bias_sum(L.ca_qc.bias, L.ca_qp.bias, D);
             L.ca_k_bias0 = P.bias_sum(L.ca_kc.bias, L.ca_kp.bias, D);
         }
-        ctx->dec.push_back(L);
+        if (P.missing.size() == dec_m0) ctx->dec.push_back(L);
     }
     ctx->dec_norm = P.norm("transformer.decoder.norm");
     ctx->qs0 = P.lin("transformer.decoder.query_scale.layers.0", D, D);
@@ -446,10 +483,8 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
         const Tensor* q = P.get("query_embed.weight", {cf.num_queries, 2});
         ctx->qembed = q ? q->p : nullptr;
     }
-    if (!P.ok) {
-        if (P.cerr != cudaSuccess) return fail(ctx, (int)P.cerr, std::string("weight packing: ") + cudaGetErrorString(P.cerr));
-        return fail(ctx, 2, "state_dict incomplete or mis-shaped; missing: " + P.missing);
-    }
+    if (P.cerr != cudaSuccess) return fail(ctx, (int)P.cerr, std::string("weight packing: ") + cudaGetErrorString(P.cerr));
+    ctx->missing = P.missing;       // sub-module contexts (T2VEncoder / Transformer) legitimately hold a partial state_dict
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     ctx->finalized = true;
@@ -520,6 +555,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     if (!ctx) return 1;
     if (!in || !out || !workspace) return fail(ctx, 1, "mesm_forward: NULL argument");
     if (!ctx->finalized) return fail(ctx, 1, "mesm_forward: weights not finalized (call mesm_finalize_weights)");
+    if (!ctx->missing.empty()) return fail(ctx, 2, "mesm_forward: state_dict incomplete or mis-shaped; missing: " + ctx->missing.substr(0, 600));
     const mesm_cfg& cf = ctx->cfg;
     const int B = in->B, Lv = in->Lv, Lt = in->Lt, G = in->G, L1 = Lv + 1, Lk = Lt + 1, nq = cf.num_queries;
     if (B < 1 || Lv < 1 || Lt < 1 || G < 1 || !in->video_feat || !in->video_mask || !in->words_feat || !in->num_clips)

@@ -98,6 +98,8 @@ int mesm_t2v_encoder(mesm_ctx* ctx, const char* prefix, const float* src_txt, co
     if (p == "enhance_encoder") layers = &ctx->enh;
     else if (p == "t2v_encoder") layers = &ctx->aln;
     else return fail(ctx, 1, "mesm_t2v_encoder: prefix must be enhance_encoder or t2v_encoder");
+    if ((int)layers->size() != (p == "enhance_encoder" ? ctx->cfg.num_recfw_layers : ctx->cfg.t2v_layers))
+        return fail(ctx, 2, "mesm_t2v_encoder: layer weights incomplete; missing: " + ctx->missing.substr(0, 600));
     if (workspace_bytes < mesm_t2v_workspace_bytes(B, Lt, Lv)) return fail(ctx, 1, "mesm_t2v_encoder: workspace too small");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -135,6 +137,9 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
                      void* stream) {
     if (!ctx) return 1;
     if (!ctx->finalized) return fail(ctx, 1, "mesm_transformer: weights not finalized");
+    if ((int)ctx->enc.size() != ctx->cfg.enc_layers || (int)ctx->dec.size() != ctx->cfg.dec_layers || !ctx->dec_norm.g ||
+        !ctx->bb2.Wt || !ctx->ra1.Wt || !ctx->qs1.Wt || !ctx->rph1.Wt)
+        return fail(ctx, 2, "mesm_transformer: transformer weights incomplete; missing: " + ctx->missing.substr(0, 600));
     if (!src || !pad || !query_embed || !pos_embed || !global_token || !global_token_pos || !workspace || B < 1 || L < 1 || L > 1023)
         return fail(ctx, 1, "mesm_transformer: bad argument");
     if (workspace_bytes < mesm_transformer_workspace_bytes(ctx, B, L)) return fail(ctx, 1, "mesm_transformer: workspace too small");

@@ -58,9 +58,15 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
     return op;
 }
 
-// Launch counter + error capture shared by all launchers.
-struct LaunchStats { long long launches = 0; };
+// Launch counter + optional per-launch CUDA-event timing of the fused-linear kernels (bench.py's roofline object).
+struct LaunchStats {
+    long long launches = 0;
+    bool profile = false;
+    double lin_ms = 0, lin_flops = 0, lin_bytes = 0; long long lin_launches = 0;      // collected totals
+    double big_ms = 0, big_flops = 0; long long big_launches = 0;                     // launches with M >= 16384 only
+};
 extern thread_local LaunchStats g_stats;
+void profile_collect();     // synchronises the recorded events and folds them into g_stats
 
 cudaError_t launch_linear(const LinearOp& op, cudaStream_t s);        // dispatcher (tcgen05 when eligible)
 cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s);   // fp32 SIMT kernel

@@ -55,6 +55,7 @@ struct mesm_ctx {
     mesm_cfg cfg{};
     int device = 0;
     std::string err;
+    std::string missing;               // state_dict keys absent / mis-shaped at the last finalize
     std::unordered_map<std::string, Tensor> w;
     std::vector<void*> owned;
     bool finalized = false;

@@ -186,9 +186,34 @@ __global__ void span_convert_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+// PostProcessorDETR on already-decoded windows (utils/post_processing.py:22-47): fp64 rows -> fp32 -> clamp ->
+// round to multiples of clip_len -> score re-rounded to 4 decimals.
+__global__ void post_process_kernel(const double* __restrict__ in, double* __restrict__ out, long long n, float clip_len,
+                                    float min_ts, float max_ts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float v = fminf(fmaxf((float)in[i * 3 + c], min_ts), max_ts);
+        if (clip_len != -1.f) v = __fmul_rn(rintf(__fdiv_rn(v, clip_len)), clip_len);
+        out[i * 3 + c] = (double)v;
+    }
+    out[i * 3 + 2] = round4((double)(float)in[i * 3 + 2]);
+}
+
 }  // namespace mesm
 
 using namespace mesm;
+
+extern "C" int mesm_post_process(const double* windows, double* out, int64_t n, double clip_len, double min_ts_val,
+                                 double max_ts_val, void* stream) {
+    if (!windows || !out) return (int)cudaErrorInvalidValue;
+    if (n <= 0) return 0;
+    post_process_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(windows, out, n, (float)clip_len,
+                                                                                        (float)min_ts_val, (float)max_ts_val);
+    g_stats.launches++;
+    return (int)cudaGetLastError();
+}
 
 extern "C" int mesm_decode_nms(const float* pred_logits, const float* pred_spans, const float* duration, int32_t B,
                                int32_t nq, const mesm_decode_params* p, double* windows, int32_t* order, int32_t* keep,

@@ -1,0 +1,127 @@
+"""GPU parity of span decode / post-processing / temporal NMS and the span_utils device functions (bit-exact work)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_oracle
+from tests.helpers import golden_cases, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_batch(lg, sp, dur, clip_len, max_ts, thd, nb, na):
+    import mesm_b200
+    win, order, keep, cnt = mesm_b200.decode_nms(torch.from_numpy(lg).cuda(), torch.from_numpy(sp).cuda(),
+                                                 torch.from_numpy(dur).cuda(), clip_len, max_ts, thd, nb, na)
+    win, order, keep, cnt = win.cpu().numpy(), order.cpu().numpy(), keep.cpu().numpy(), cnt.cpu().numpy()
+    n_score_ulp = 0
+    for i in range(lg.shape[0]):
+        od = decode_oracle.decode_pair(lg[i], sp[i], float(dur[i]), clip_len, max_ts, thd, nb, na)
+        w = np.asarray(od["windows"])
+        assert od["order"] == order[i].tolist(), i
+        assert np.array_equal(w[:, :2], win[i, :, :2]), i                     # st / ed bit-exact
+        d = np.abs(w[:, 2] - win[i, :, 2])
+        assert d.max() <= 1.0001e-4, i                                         # score: <= one 4-decimal quantum (expf ulp)
+        n_score_ulp += int((d > 0).sum())
+        assert od["keep"] == keep[i, :cnt[i]].tolist(), i                      # identical kept-span index sets
+        assert (keep[i, cnt[i]:] == -1).all()
+    return n_score_ulp
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases()))
+def test_decode_matches_reference_golden(name):
+    import mesm_b200
+    cfg, sd, inp, neg, gold, meta = load_case(name)
+    win, order, keep, cnt = mesm_b200.decode_nms(torch.from_numpy(gold["pred_logits"]).cuda(), torch.from_numpy(gold["pred_spans"]).cuda(),
+                                                 inp["duration"].cuda(), cfg.clip_len, cfg.max_ts_val, meta["nms_thd"], 10, 10)
+    assert np.array_equal(order.cpu().numpy(), gold["order"])
+    assert np.array_equal(win.cpu().numpy()[..., :2], gold["windows"][..., :2])
+    assert np.abs(win.cpu().numpy()[..., 2] - gold["windows"][..., 2]).max() <= 1.0001e-4
+    for i in range(len(gold["nms_count"])):
+        n = int(gold["nms_count"][i])
+        assert int(cnt[i]) == n
+        kept_rows = [gold["order"][i].tolist().index(q) for q in keep[i, :n].tolist()]
+        assert np.array_equal(gold["windows"][i][kept_rows][:, :2], gold["nms_windows"][i, :n, :2])
+
+
+@pytest.mark.parametrize("clip_len,max_ts,thd", [(2.0, 150.0, 0.7), (1.0, 150.0, 0.5), (0.17, 150.0, 0.7), (-1.0, 1000.0, 0.3),
+                                                 (2.0, 150.0, -1.0)])
+def test_decode_random_vs_oracle(clip_len, max_ts, thd):
+    rng = np.random.default_rng(7)
+    B, nq = 2048, 10
+    lg = rng.normal(size=(B, nq, 2)).astype(np.float32) * 2
+    sp = np.stack([rng.uniform(0, 1, (B, nq)), rng.uniform(0, 0.6, (B, nq))], -1).astype(np.float32)
+    # edge cases: exact score ties, identical windows, spans outside [0,1], zero width
+    lg[::7, 3] = lg[::7, 5]
+    sp[::5, 2] = sp[::5, 4]
+    sp[::11, 6, 1] = 0
+    sp[::13, 1] = [0.02, 0.5]
+    dur = rng.uniform(5, 150, B).astype(np.float32)
+    _check_batch(lg, sp, dur, clip_len, max_ts, thd, 10, 10)
+    _check_batch(lg[:256], sp[:256], dur[:256], clip_len, max_ts, thd, 6, 3)
+
+
+def test_decode_other_query_counts():
+    rng = np.random.default_rng(3)
+    for nq in (1, 2, 17, 32):
+        lg = rng.normal(size=(64, nq, 2)).astype(np.float32)
+        sp = np.stack([rng.uniform(0, 1, (64, nq)), rng.uniform(0, 0.5, (64, nq))], -1).astype(np.float32)
+        dur = rng.uniform(5, 150, 64).astype(np.float32)
+        _check_batch(lg, sp, dur, 2.0, 150.0, 0.7, nq, nq)
+
+
+def test_temporal_nms_dense_candidates():
+    """TACoS-style dense candidate lists (100 candidates / pair) + ragged / degenerate lists."""
+    import mesm_b200
+    rng = np.random.default_rng(11)
+    sizes = [100] * 40 + [1, 2, 0, 3, 1000, 57]
+    lists = []
+    for n in sizes:
+        st = rng.uniform(0, 140, n).round(2)
+        w = np.stack([st, st + rng.uniform(0, 30, n).round(2), rng.uniform(0, 1, n).round(3)], 1)
+        if n >= 10:
+            w[5] = w[2]                      # duplicates + score ties
+            w[7, 2] = w[3, 2]
+        lists.append(w)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    flat = torch.from_numpy(np.concatenate([l for l in lists if len(l)] or [np.zeros((0, 3))])).cuda()
+    for thd, na in ((0.7, 10), (0.3, 100), (0.5, 1)):
+        keep, cnt = mesm_b200.temporal_nms_lists(flat, torch.from_numpy(offs).cuda(), thd, na)
+        keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+        for i, w in enumerate(lists):
+            exp = decode_oracle.temporal_nms(w.tolist(), thd, na)[1] if len(w) else []
+            assert keep[i, :cnt[i]].tolist() == exp, (i, thd, na)
+
+
+def test_span_utils_known_answers(golden_dir):
+    """Doctest vectors of utils/span_utils.py (12-19, 31-38, 54-60, 105-109) + random bit-exact comparison."""
+    from mesm_b200 import utils as U
+    g = np.load(os.path.join(golden_dir, "span_utils_doctest.npz"))
+    s1, s2 = torch.from_numpy(g["s1"]).cuda(), torch.from_numpy(g["s2"]).cuda()
+    iou, union = U.temporal_iou(s1, s2)
+    assert np.array_equal(iou.cpu().numpy(), g["iou"]) and np.array_equal(union.cpu().numpy(), g["union"])
+    assert np.array_equal(U.generalized_temporal_iou(s1, s2).cpu().numpy(), g["giou"])
+    assert np.array_equal(U.span_xx_to_cxw(torch.tensor([[0, 1], [0.2, 0.4]]).cuda()).cpu().numpy(), g["cxw"])
+    assert np.array_equal(U.span_cxw_to_xx(torch.tensor([[[0.5, 1.0], [0.3, 0.2]]]).cuda()).cpu().numpy()[0], g["xx"])
+    rng = np.random.default_rng(0)
+    a = np.sort(rng.uniform(0, 1, (37, 2)).astype(np.float32), axis=1)
+    b = np.sort(rng.uniform(0, 1, (53, 2)).astype(np.float32), axis=1)
+    iou, union = U.temporal_iou(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    ri, ru = decode_oracle.temporal_iou(a, b)
+    assert np.array_equal(iou.cpu().numpy(), ri.astype(np.float32)) and np.array_equal(union.cpu().numpy(), ru.astype(np.float32))
+    assert np.array_equal(U.generalized_temporal_iou(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy(),
+                          decode_oracle.generalized_temporal_iou(a, b))
+
+
+def test_python_wrappers_keep_reference_signatures():
+    """utils.temporal_nms(predictions, nms_thd, max_after_nms) and PostProcessorDETR(...)(lines) as thin wrappers."""
+    from mesm_b200 import utils as U
+    preds = [[0.0, 10.0, 0.9], [3.0, 10.0, 0.8], [1.0, 9.5, 0.85], [50.0, 60.0, 0.1]]
+    assert U.temporal_nms(preds, 0.7, 10) == decode_oracle.temporal_nms(preds, 0.7, 10)[0]
+    lines = [dict(qid=1, pred_relevant_windows=[[1.23456, 151.0, 0.55555], [-3.0, 7.1, 0.4]])]
+    pp = U.PostProcessorDETR(clip_length=2, min_ts_val=0, max_ts_val=150, process_func_names=("clip_ts", "round_multiple"))
+    out = pp(lines)[0]["pred_relevant_windows"]
+    assert out == decode_oracle.post_process_windows([[1.23456, 151.0, 0.55555], [-3.0, 7.1, 0.4]], 2, 150)
