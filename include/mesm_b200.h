@@ -192,6 +192,13 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
                      void* workspace, size_t workspace_bytes, void* stream);
 size_t mesm_transformer_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t L);
 
+/* Test hook (tests/test_gpu_linear.py): one fused linear out = epilogue(A (+Apos) . W^T) through the fp32 SIMT kernel
+ * (use_tc = 0) or the tcgen05 split-bf16 kernel (use_tc = 1); synchronises the stream. */
+int mesm_debug_linear(const float* A, const float* Apos, const float* W, const float* bias, const float* residual,
+                      const float* ln_g, const float* ln_b, const float* rowstat, const float* prelu, int32_t M, int32_t N,
+                      int32_t K, int32_t lda, int32_t act, float out_scale, float* out, float* pre_ln, int32_t use_tc,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -51,6 +52,11 @@ __global__ void vec_add_kernel(const float* a, const float* b, float* o, int n) 
 
 }  // namespace
 namespace mesm {
+cudaError_t launch_colsum(const float* Wt, int Kp, int ldw, int N, float* out, cudaStream_t s) {
+    colsum_kernel<<<(N + 127) / 128, 128, 0, s>>>(Wt, Kp, ldw, N, out);
+    g_stats.launches++;
+    return cudaGetLastError();
+}
 cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, float* Wt, int ldw, int Kp, cudaStream_t s) {
     const long long tot = (long long)Kp * ldw;
     transpose_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(W, row0, nrows, K, nullptr, Wt, ldw, Kp);
@@ -96,6 +102,14 @@ struct Packer {
         const long long tot = (long long)Kp * ldw;
         transpose_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(W->p, row0, nrows, (int)K, gamma, Wt, ldw, Kp);
         r.Wt = Wt; r.ldw = ldw; r.K = (int)K; r.N = nrows;
+        if (nrows >= 64) {
+            void* wp = nullptr;
+            cudaError_t e = cudaMalloc(&wp, tc_packed_bytes(nrows, (int)K));
+            if (e != cudaSuccess) { ok = false; cerr = e; return r; }
+            ctx->owned.push_back(wp);
+            launch_pack_tc(W->p, row0, nrows, (int)K, gamma, wp, s);
+            r.Wp = wp;
+        }
         if (gamma) {
             float* cs = alloc(nrows);
             float* cb = alloc(nrows);
@@ -302,15 +316,24 @@ int check_cfg(const mesm_cfg* c, std::string& why) {
 namespace mesm {
 struct ProfRec { cudaEvent_t a, b; double flops, bytes; int M; };
 static thread_local std::vector<ProfRec> g_prof;
+static int force_simt() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MESM_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+static cudaError_t dispatch_linear(const LinearOp& op, cudaStream_t s) {
+    if (!force_simt() && linear_tc_eligible(op)) return launch_linear_tc(op, s);
+    return launch_linear_simt(op, s);
+}
 cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) {
-    if (!g_stats.profile) return launch_linear_simt(op, s);
+    if (!g_stats.profile) return dispatch_linear(op, s);
     ProfRec r;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     r.flops = 2.0 * op.M * (double)op.N * ((double)op.K + op.K2);
     r.bytes = 4.0 * ((double)op.M * (op.K + op.K2) + (double)op.M * op.N + (double)op.N * (op.K + op.K2));
     r.M = op.M;
     cudaEventRecord(r.a, s);
-    cudaError_t e = launch_linear_simt(op, s);
+    cudaError_t e = dispatch_linear(op, s);
     cudaEventRecord(r.b, s);
     g_prof.push_back(r);
     return e;

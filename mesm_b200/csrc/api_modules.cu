@@ -166,4 +166,39 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
     return 0;
 }
 
+/* Test hook: one fused linear through either kernel.  W [N,K] fp32 (out,in); every optional pointer may be NULL.
+ * use_tc: 0 = fp32 SIMT kernel, 1 = tcgen05 kernel (error if the shape is not eligible). */
+int mesm_debug_linear(const float* A, const float* Apos, const float* W, const float* bias, const float* residual,
+                      const float* ln_g, const float* ln_b, const float* rowstat, const float* prelu, int32_t M, int32_t N,
+                      int32_t K, int32_t lda, int32_t act, float out_scale, float* out, float* pre_ln, int32_t use_tc,
+                      void* stream) {
+    mesm_ctx* ctx = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Kp = (K + 15) / 16 * 16, ldw = (N + 3) / 4 * 4;
+    float* Wt = nullptr; void* Wp = nullptr; float* cs = nullptr;
+    CK(cudaMalloc((void**)&Wt, (size_t)Kp * ldw * sizeof(float)));
+    CK(cudaMalloc(&Wp, tc_packed_bytes(N, K)));
+    CK(cudaMalloc((void**)&cs, (size_t)N * sizeof(float) + 16));
+    CK(launch_transpose_pack(W, 0, N, K, Wt, ldw, Kp, s));
+    CK(launch_pack_tc(W, 0, N, K, nullptr, Wp, s));
+    LinearOp op = make_linear(M, N, K, A, lda, Wt, ldw, bias, out, N);
+    op.Apos = Apos; op.Wp = Wp; op.act = act; op.prelu = prelu; op.out_scale = out_scale;
+    op.residual = residual; op.ldr = N; op.ln_g = ln_g; op.ln_b = ln_b; op.pre_ln = pre_ln;
+    if (rowstat) {      // colsum of the (unfolded) weights: the caller folds gamma into W beforehand
+        CK(launch_colsum(Wt, Kp, ldw, N, cs, s));
+        op.rowstat = rowstat; op.colsum = cs;
+    }
+    int rc = 0;
+    if (use_tc) {
+        if (!linear_tc_eligible(op)) rc = fail(ctx, 3, "mesm_debug_linear: shape not eligible for the tcgen05 kernel");
+        else { cudaError_t e = launch_linear_tc(op, s); if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e)); }
+    } else {
+        cudaError_t e = launch_linear_simt(op, s); if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && rc == 0) rc = fail(ctx, (int)e, std::string("mesm_debug_linear: ") + cudaGetErrorString(e));
+    cudaFree(Wt); cudaFree(Wp); cudaFree(cs);
+    return rc;
+}
+
 }  // extern "C"

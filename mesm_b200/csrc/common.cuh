@@ -34,6 +34,7 @@ struct LinearOp {
     const float* A;   int lda;   RowMap amap;     // A[M,K] fp32 row-major (lda floats between rows)
     const float* Apos;                            // optional addend on A (same shape / lda / map), e.g. positional enc.
     const float* Wt;  int ldw;                    // weights pre-transposed: Wt[k*ldw + n], K rows zero-padded to /16
+    const void* Wp; const void* Wp2;              // same weights as packed bf16 hi/lo tcgen05 tiles (null: SIMT only)
     int K2; const float* A2; int lda2; RowMap a2map; const float* Wt2;   // optional second input (same ldw)
     const float* bias;                            // [N] or null
     const float* rowstat;                         // [M,2] (mean, rstd) of A rows: LayerNorm folded into the GEMM
@@ -51,7 +52,7 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
                                    const float* bias, float* out, int ldo) {
     LinearOp op;
     op.M = M; op.N = N; op.K = K; op.A = A; op.lda = lda; op.amap = identity_map(); op.Apos = nullptr;
-    op.Wt = Wt; op.ldw = ldw; op.K2 = 0; op.A2 = nullptr; op.lda2 = 0; op.a2map = identity_map(); op.Wt2 = nullptr;
+    op.Wt = Wt; op.ldw = ldw; op.Wp = nullptr; op.Wp2 = nullptr; op.K2 = 0; op.A2 = nullptr; op.lda2 = 0; op.a2map = identity_map(); op.Wt2 = nullptr;
     op.bias = bias; op.rowstat = nullptr; op.colsum = nullptr; op.out_scale = 1.f; op.act = ACT_NONE; op.prelu = nullptr;
     op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
     op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr;
@@ -70,6 +71,10 @@ void profile_collect();     // synchronises the recorded events and folds them i
 
 cudaError_t launch_linear(const LinearOp& op, cudaStream_t s);        // dispatcher (tcgen05 when eligible)
 cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s);   // fp32 SIMT kernel
+cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s);     // tcgen05 split-bf16 kernel
+bool linear_tc_eligible(const LinearOp& op);
+size_t tc_packed_bytes(int nrows, int K);
+cudaError_t launch_pack_tc(const float* W, int row0, int nrows, int K, const float* gamma, void* out, cudaStream_t s);
 
 #define MESM_CHECK(expr)                                                                         \
     do {                                                                                         \

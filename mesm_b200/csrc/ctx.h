@@ -22,6 +22,7 @@ struct PL {              // packed linear: Wt[Kp, ldw] (k-major), bias[N]
     int ldw = 0, K = 0, N = 0;
     const float* bias = nullptr;
     const float* colsum = nullptr;   // LayerNorm-folded layers only
+    const void* Wp = nullptr;        // tcgen05 packed tiles (null for tiny layers)
 };
 
 struct Norm { const float* g = nullptr; const float* b = nullptr; };
@@ -108,13 +109,14 @@ struct Lin {    // thin builder around LinearOp
     LinearOp op;
     Lin(int M, const PL& w, const float* A, int lda, float* out, int ldo) {
         op = make_linear(M, w.N, w.K, A, lda, w.Wt, w.ldw, w.bias, out, ldo);
+        op.Wp = w.Wp;
     }
     Lin& bias(const float* b) { op.bias = b; return *this; }
     Lin& amap(RowMap m) { op.amap = m; return *this; }
     Lin& omap(RowMap m) { op.omap = m; return *this; }
     Lin& apos(const float* p) { op.Apos = p; return *this; }
     Lin& second(const float* A2, int lda2, const PL& w2, RowMap m = identity_map()) {
-        op.A2 = A2; op.lda2 = lda2; op.K2 = w2.K; op.Wt2 = w2.Wt; op.a2map = m; return *this;
+        op.A2 = A2; op.lda2 = lda2; op.K2 = w2.K; op.Wt2 = w2.Wt; op.Wp2 = w2.Wp; op.a2map = m; return *this;
     }
     Lin& act(int a, const float* slope = nullptr) { op.act = a; op.prelu = slope; return *this; }
     Lin& scale(float s) { op.out_scale = s; return *this; }
@@ -142,6 +144,7 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
                       const EncBuffers& t, float* out, cudaStream_t s);
 size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl);
+cudaError_t launch_colsum(const float* Wt, int Kp, int ldw, int N, float* out, cudaStream_t s);
 cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, float* Wt, int ldw, int Kp, cudaStream_t s);
 cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, const float* posE, const uint8_t* padV, int Lv, int Bc,
                         const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
