@@ -23,7 +23,7 @@ struct RowMap {
         return (long long)g * stride + offset + (r - g * group);
     }
 };
-static inline RowMap identity_map() { return RowMap{0, 0, 0}; }
+__host__ __device__ static inline RowMap identity_map() { return RowMap{0, 0, 0}; }
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_PRELU = 2, ACT_SIGMOID = 3 };
 

@@ -22,13 +22,20 @@
 namespace mesm {
 namespace tc {
 
+#ifdef MESM_TC_TIMING
+__device__ long long g_tc_times[64];
+#define TSTAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_tc_times[i] = clock64(); } while (0)
+#else
+#define TSTAMP(i) do {} while (0)
+#endif
+
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;                       // bytes of one bf16 plane of the A tile
 constexpr int W_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;      // 98304
 constexpr int NCONV = 256;                                // converter / epilogue threads (8 warps)
 constexpr int THREADS = 64 + NCONV;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*barriers + LN exchange*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 + 1024 + 4096 + 3072 /*barriers, LN exchange, epilogue vectors, row offsets*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -134,7 +141,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
     const uint32_t bar_full_w = bar_base, bar_full_a = bar_base + 16, bar_empty = bar_base + 32, bar_tmem = bar_base + 48;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 56);
     float* ln_x = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 64);      // [2][128] partial sums
+    float* vec_s = ln_x + 256;                                                      // [4][256]: bias, colsum, ln_g, ln_b of this N tile
+    long long* rowoff = reinterpret_cast<long long*>(vec_s + 1024);                 // [3][128]: out, out2, residual row offsets (-1: no row)
 
+    if (threadIdx.x == 0) TSTAMP(0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, nt = blockIdx.y, n0 = nt * BN;
     const int nkb = nkb1 + nkb2;
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) TSTAMP(1);
 
     if (warp == 0) {
         // ===================== weight producer =====================
@@ -180,7 +191,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(bar_full_w + 8 * s, ph);
+                if (kb < 8) TSTAMP(8 + kb);
                 mbar_wait(bar_full_a + 8 * s, ph);
+                if (kb < 8) TSTAMP(16 + kb);
                 tc_fence_after();
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
                 const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + W_TILE;
@@ -196,6 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
                 umma_commit(bar_empty + 8 * s);            // stage reusable once these MMAs retire
             }
             umma_commit(bar_tmem);                         // accumulator complete
+            TSTAMP(2);
         }
     } else {
         // ===================== A converters, then epilogue =====================
@@ -205,60 +219,114 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
         constexpr int ROW_STEP = NCONV / PER_ROW;          // 16 or 8
         const int cv = tc % PER_ROW, r0 = tc / PER_ROW;
 
-        float cur[NV * VEC], nxa[NV * VEC];
-        auto load_block = [&](int kb, float* dst) {
+        // Global loads are issued branch-free (clamped addresses, validity applied later) so that all NV vector loads
+        // of a K block are in flight together; the block after the one being converted is always outstanding.
+        float cur[NV * VEC], nxa[NV * VEC], nxp[NV * VEC];
+        const bool has_pos = op.Apos != nullptr;
+        long long roff1[NV], roff2[NV];
+        unsigned rowok = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int m = m0 + r0 + i * ROW_STEP;
+            const bool ok = m < op.M;
+            rowok |= (ok ? 1u : 0u) << i;
+            roff1[i] = ok ? op.amap(m) * (long long)op.lda : 0;
+            roff2[i] = (ok && op.A2) ? op.a2map(m) * (long long)op.lda2 : 0;
+        }
+        auto load_block = [&](int kb) {
             const bool second = kb >= nkb1;
             const float* A = second ? op.A2 : op.A;
             const float* P = second ? nullptr : op.Apos;
             const int K = second ? op.K2 : op.K;
-            const int lda = second ? op.lda2 : op.lda;
-            const RowMap map = second ? op.a2map : op.amap;
             const int k = (second ? kb - nkb1 : kb) * BK + cv * VEC;
+            const int kc = (k + VEC <= K) ? k : 0;                 // clamped (tail handled below)
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                const int m = m0 + r0 + i * ROW_STEP;
-                float v[VEC];
+                const long long off = (second ? roff2[i] : roff1[i]) + kc;
+                if (VEC == 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(A + off));
+                    nxa[i * 4] = t.x; nxa[i * 4 + 1] = t.y; nxa[i * 4 + 2] = t.z; nxa[i * 4 + 3] = t.w;
+                } else {
+                    const float2 t = __ldg(reinterpret_cast<const float2*>(A + off));
+                    nxa[i * 2] = t.x; nxa[i * 2 + 1] = t.y;
+                }
+            }
+            if (P) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) v[j] = 0.f;
-                if (m < op.M && k < K) {
-                    const long long off = map(m) * (long long)lda + k;
-                    if (k + VEC <= K) {
-                        if (VEC == 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(A + off));
-                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                            if (P) { const float4 q = __ldg(reinterpret_cast<const float4*>(P + off)); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
-                        } else {
-                            const float2 t = __ldg(reinterpret_cast<const float2*>(A + off));
-                            v[0] = t.x; v[1] = t.y;
-                            if (P) { const float2 q = __ldg(reinterpret_cast<const float2*>(P + off)); v[0] += q.x; v[1] += q.y; }
-                        }
+                for (int i = 0; i < NV; ++i) {
+                    const long long off = roff1[i] + kc;
+                    if (VEC == 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(P + off));
+                        nxp[i * 4] = t.x; nxp[i * 4 + 1] = t.y; nxp[i * 4 + 2] = t.z; nxp[i * 4 + 3] = t.w;
                     } else {
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j)
-                            if (k + j < K) v[j] = A[off + j] + (P ? P[off + j] : 0.f);
+                        const float2 t = __ldg(reinterpret_cast<const float2*>(P + off));
+                        nxp[i * 2] = t.x; nxp[i * 2 + 1] = t.y;
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) dst[i * VEC + j] = v[j];
             }
         };
+        // validity of the block's k range for this thread: 2 = whole vector, 1 = partial tail (scalar reload), 0 = none
+        auto kstate = [&](int kb) {
+            const bool second = kb >= nkb1;
+            const int K = second ? op.K2 : op.K;
+            const int k = (second ? kb - nkb1 : kb) * BK + cv * VEC;
+            return (k + VEC <= K) ? 2 : (k < K ? 1 : 0);
+        };
 
-        load_block(0, nxa);
+        {   // stage the per-column epilogue vectors of this N tile once (read by every row of the tile)
+            const int n = n0 + tc;
+            const bool nok = n < op.N;
+            vec_s[tc] = (op.bias && nok) ? __ldg(op.bias + n) : 0.f;
+            vec_s[256 + tc] = (op.colsum && nok) ? __ldg(op.colsum + n) : 0.f;
+            vec_s[512 + tc] = (op.ln_g && nok) ? __ldg(op.ln_g + n) : 0.f;
+            vec_s[768 + tc] = (op.ln_b && nok) ? __ldg(op.ln_b + n) : 0.f;
+            if (tc < 128) {
+                const int m = m0 + tc;
+                const bool ok = m < op.M;
+                rowoff[tc] = ok ? op.omap(m) * (long long)op.ldo : -1;
+                rowoff[128 + tc] = (ok && op.out2) ? op.o2map(m) * (long long)op.ldo2 : -1;
+                rowoff[256 + tc] = (ok && op.residual) ? op.rmap(m) * (long long)op.ldr : -1;
+            }
+        }
+        load_block(0);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
+            const int ks = kstate(kb);
+            const bool use_pos = has_pos && kb < nkb1;
 #pragma unroll
-            for (int i = 0; i < NV * VEC; ++i) cur[i] = nxa[i];
-            if (kb + 1 < nkb) load_block(kb + 1, nxa);
+            for (int i = 0; i < NV * VEC; ++i) cur[i] = use_pos ? nxa[i] + nxp[i] : nxa[i];
+            if (ks != 2) {                                          // K tail: zero / scalar reload (rare: last block only)
+                const bool second = kb >= nkb1;
+                const float* A = second ? op.A2 : op.A;
+                const float* P = second ? nullptr : op.Apos;
+                const int K = second ? op.K2 : op.K;
+                const int k = (second ? kb - nkb1 : kb) * BK + cv * VEC;
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        float v = 0.f;
+                        if (ks == 1 && k + j < K && ((rowok >> i) & 1u)) {
+                            const long long off = (second ? roff2[i] : roff1[i]) + k + j;
+                            v = A[off] + (P ? P[off] : 0.f);
+                        }
+                        cur[i * VEC + j] = v;
+                    }
+            }
+            if (kb + 1 < nkb) load_block(kb + 1);
+            if (tc == 0 && kb < 8) TSTAMP(24 + kb);
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (tc == 0 && kb < 8) TSTAMP(32 + kb);
             uint8_t* a_hi = smem + s * STAGE_BYTES;
             uint8_t* a_lo = a_hi + A_TILE;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int row = r0 + i * ROW_STEP;
+                const float keep = ((rowok >> i) & 1u) ? 1.f : 0.f;
                 __nv_bfloat16 h[VEC], l[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) split_bf16(cur[i * VEC + j], h[j], l[j]);
+                for (int j = 0; j < VEC; ++j) split_bf16(keep != 0.f ? cur[i * VEC + j] : 0.f, h[j], l[j]);
                 const int kel = cv * VEC;                                        // k element index inside the 64-wide row
                 const int byte = row * 128 + ((((kel >> 3) ^ (row & 7)) << 4) | ((kel & 7) << 1));
                 if (VEC == 4) {
@@ -279,18 +347,21 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
             fence_proxy_async();                     // make the generic-proxy stores visible to the tensor-core (async) proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full_a + 8 * s);
+            if (tc == 0 && kb < 8) TSTAMP(40 + kb);
         }
 
         // ---------------- epilogue: TMEM -> registers -> global ----------------
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // vec_s written by all converter threads
         mbar_wait(bar_tmem, 0);
         tc_fence_after();
+        if (tc == 0) TSTAMP(3);
         const int q = warp & 3;                            // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;                  // column half handled by this warp
         const int row = q * 32 + lane;
         const int m = m0 + row;
         const bool mok = m < op.M;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
-        const float slope = (op.act == ACT_PRELU) ? __ldg(op.prelu) : 0.f;
+        const float slope_eff = op.act == ACT_PRELU ? __ldg(op.prelu) : (op.act == ACT_RELU ? 0.f : 1.f);
         float mean_in = 0.f, rstd_in = 1.f;
         if (op.rowstat && mok) { mean_in = __ldg(op.rowstat + 2 * m); rstd_in = __ldg(op.rowstat + 2 * m + 1); }
         const float* res = (op.residual && mok) ? op.residual + op.rmap(m) * (long long)op.ldr : nullptr;
@@ -302,14 +373,44 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
                             (!op.out2 || (((op.ldo2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.out2) & 15) == 0))) &&
                             (!op.residual || (((op.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.residual) & 15) == 0)));
 
-        auto store_row = [&](float* dst, int n, const float* v) {       // 32 consecutive columns starting at n
-            if (vec_ok && n + 32 <= op.N) {
+        // Per-warp 32 x 32 transpose buffer (the operand stages are idle once the accumulator is complete): TMEM hands each
+        // thread one ROW; global memory wants a warp instruction to cover whole 128-byte row segments.  Row stride 36
+        // floats keeps both the thread-per-row float4 writes and the 4-rows-per-instruction float4 reads conflict-free.
+        float* T = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        const int trow0 = q * 32;                           // first tile row of this warp's quadrant
+        (void)vec_ok; (void)out; (void)out2; (void)pre; (void)res; (void)row;
+
+        // transposed pass over the staged 32x32 chunk starting at column n: each instruction moves 4 rows x 128 bytes
+        auto rows_pass = [&](int n, bool add_res, bool keep_in_T, float* dst0, const long long* off0, float* dst1,
+                             const long long* off1, float* dstp) {
+            const int nn = n + c4;
+            const bool nok = nn < op.N;                     // N % 4 == 0 is an eligibility condition
+            float4 x[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(dst + n + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
+            for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(&T[(4 * i + rsub) * 36 + c4]);
+            if (add_res) {
+                float4 r[8];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (n + j < op.N) dst[n + j] = v[j];
+                for (int i = 0; i < 8; ++i) {
+                    const long long o = rowoff[2 * 128 + trow0 + 4 * i + rsub];
+                    r[i] = (o >= 0 && nok) ? __ldg(reinterpret_cast<const float4*>(op.residual + o + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { x[i].x += r[i].x; x[i].y += r[i].y; x[i].z += r[i].z; x[i].w += r[i].w; }
+            }
+            if (keep_in_T) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&T[(4 * i + rsub) * 36 + c4]) = x[i];
+            }
+            if (nok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int tr = trow0 + 4 * i + rsub;
+                    if (dst0) { const long long o = off0[tr]; if (o >= 0) *reinterpret_cast<float4*>(dst0 + o + nn) = x[i]; }
+                    if (dst1) { const long long o = off1[tr]; if (o >= 0) *reinterpret_cast<float4*>(dst1 + o + nn) = x[i]; }
+                    if (dstp && m0 + tr < op.M) *reinterpret_cast<float4*>(dstp + (long long)(m0 + tr) * op.N + nn) = x[i];
+                }
             }
         };
 
@@ -317,45 +418,52 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             const int n = n0 + half * 128 + c * 32;
+            if (n >= op.N) break;                           // warp-uniform
             float v[32];
+            if (tc == 0 && c < 2) TSTAMP(48 + 4 * c);
             tmem_ld32(taddr0 + c * 32, v);
-            if (n < op.N) {
+            if (tc == 0 && c < 2) TSTAMP(49 + 4 * c);
+            {   // lean per-element math: LN-fold (identity when unused), bias, scale, leaky activation (slope_eff)
+                const int cl0 = n - n0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int nn = n + j;
-                    const bool nok = nn < op.N;
-                    float x = v[j];
-                    if (op.rowstat) x = rstd_in * (x - mean_in * ((nok) ? __ldg(op.colsum + nn) : 0.f));
-                    x = (x + ((op.bias && nok) ? __ldg(op.bias + nn) : 0.f)) * op.out_scale;
-                    v[j] = act_fn(x, op.act, slope);
-                }
-                if (res) {
-                    if (vec_ok && n + 32 <= op.N) {
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&vec_s[cl0 + 4 * j]);
+                    const float4 c4v = *reinterpret_cast<const float4*>(&vec_s[256 + cl0 + 4 * j]);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4v.x, c4v.y, c4v.z, c4v.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(res + n + 4 * j);
-                            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n + j < op.N) v[j] += res[n + j];
+                    for (int u = 0; u < 4; ++u) {
+                        float x = rstd_in * fmaf(-mean_in, cc[u], v[4 * j + u]);
+                        x = (x + bb[u]) * op.out_scale;
+                        v[4 * j + u] = x >= 0.f ? x : slope_eff * x;
                     }
                 }
-                if (pre) store_row(pre, n, v);
-                if (do_ln) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sum += v[j];
-                    tmem_st32(taddr0 + c * 32, v);
-                } else if (mok) {
-                    store_row(out, n, v);
-                    if (out2) store_row(out2, n, v);
-                }
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(&T[lane * 36 + 4 * j]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            if (tc == 0 && c < 2) TSTAMP(50 + 4 * c);
+            if (do_ln) {
+                // residual added and pre-LN value stored in the transposed (coalesced) domain; result kept for the stats
+                rows_pass(n, op.residual != nullptr, true, nullptr, nullptr, nullptr, nullptr, op.pre_ln);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = *reinterpret_cast<const float4*>(&T[lane * 36 + 4 * j]);
+                    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                    sum += (t.x + t.y) + (t.z + t.w);
+                }
+                tmem_st32(taddr0 + c * 32, v);
+            } else {
+                rows_pass(n, op.residual != nullptr, false, op.out, rowoff, op.out2, rowoff + 128, nullptr);
+            }
+            __syncwarp();
+            if (tc == 0 && c < 2) TSTAMP(51 + 4 * c);
         }
+        if (tc == 0) TSTAMP(4);
         if (do_ln) {                                       // N == 256: this thread holds half of row `row`
-            ln_x[half * 128 + row] = sum;
+            ln_x[half * 128 + q * 32 + lane] = sum;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float mu = (ln_x[row] + ln_x[128 + row]) * (1.f / 256.f);
+            const float mu = (ln_x[q * 32 + lane] + ln_x[128 + q * 32 + lane]) * (1.f / 256.f);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             float sq = 0.f;
 #pragma unroll 1
@@ -365,25 +473,31 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; sq = fmaf(d, d, sq); }
             }
-            ln_x[half * 128 + row] = sq;
+            ln_x[half * 128 + q * 32 + lane] = sq;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float rs = rsqrtf((ln_x[row] + ln_x[128 + row]) * (1.f / 256.f) + 1e-5f);
+            const float rs = rsqrtf((ln_x[q * 32 + lane] + ln_x[128 + q * 32 + lane]) * (1.f / 256.f) + 1e-5f);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int n = n0 + half * 128 + c * 32;
                 float v[32];
                 tmem_ld32(taddr0 + c * 32, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (v[j] - mu) * rs * __ldg(op.ln_g + n + j) + __ldg(op.ln_b + n + j);
-                if (mok) {
-                    store_row(out, n, v);
-                    if (out2) store_row(out2, n, v);
+                for (int j = 0; j < 32; ++j) {
+                    const int cl = n - n0 + j;
+                    v[j] = (v[j] - mu) * rs * vec_s[512 + cl] + vec_s[768 + cl];
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(&T[lane * 36 + 4 * j]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                rows_pass(n, false, false, op.out, rowoff, op.out2, rowoff + 128, nullptr);
+                __syncwarp();
             }
         }
     }
+    if (threadIdx.x == 64) TSTAMP(5);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TSTAMP(6);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
@@ -435,10 +549,17 @@ cudaError_t launch_pack_tc(const float* W, int row0, int nrows, int K, const flo
     return cudaGetLastError();
 }
 
+#ifdef MESM_TC_TIMING
+void tc_read_times(long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_times, sizeof(long long) * 64); }
+#endif
+
 bool linear_tc_eligible(const LinearOp& op) {
     if (!op.Wp || (op.A2 && !op.Wp2)) return false;
     if (op.M < 128 || op.N < 64) return false;
     if (op.ln_g && op.N != 256) return false;
+    if (op.act == ACT_SIGMOID) return false;
+    auto al16 = [](const float* p, long long ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); };
+    if ((op.N & 3) || !al16(op.out, op.ldo) || !al16(op.out2, op.ldo2) || !al16(op.residual, op.ldr) || !al16(op.pre_ln, op.N)) return false;
     auto ok = [](const float* p, int ld, int K) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 7) == 0) && (ld % 2 == 0) && (K % 2 == 0)); };
     if (!ok(op.A, op.lda, op.K) || !ok(op.Apos, op.lda, op.K) || !ok(op.A2, op.lda2, op.K2)) return false;
     return true;
