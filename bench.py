@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="pairs per GPU per step")
-    ap.add_argument("--chunk-pairs", type=int, default=256)
+    ap.add_argument("--chunk-pairs", type=int, default=384)
     ap.add_argument("--cpu-sample-pairs", type=int, default=32)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -248,6 +248,10 @@ def main():
     step()
     prof = (ctypes.c_double * 7)()
     lib.mesm_profile_end(prof)
+    if os.environ.get("MESM_PROFILE_REPORT"):
+        rep = sorted((l.split("\t") for l in lib.mesm_profile_report().decode().strip().split("\n")), key=lambda r: -float(r[2]))
+        for r in rep:
+            print(f"{float(r[2]):9.3f} ms  n={int(r[1]):5d}  {r[0]}", file=sys.stderr)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:

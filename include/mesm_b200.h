@@ -110,6 +110,8 @@ int64_t mesm_last_launch_count(const mesm_ctx* ctx);
  * launches, ms / flops / launches of the launches with M >= 16384}. */
 void mesm_profile_begin(void);
 void mesm_profile_end(double* out7);
+/* per-kernel-class text report of the last profiled region: lines "name<TAB>launches<TAB>ms" */
+const char* mesm_profile_report(void);
 
 /* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
 /* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),

@@ -50,6 +50,7 @@ SYMBOLS = {
     "mesm_last_launch_count": (c_int64, [c_void_p]),
     "mesm_profile_begin": (None, []),
     "mesm_profile_end": (None, [POINTER(c_double)]),
+    "mesm_profile_report": (c_char_p, []),
     "mesm_decode_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(MesmDecodeParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mesm_temporal_nms": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),

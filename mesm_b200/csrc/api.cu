@@ -314,41 +314,48 @@ int check_cfg(const mesm_cfg* c, std::string& why) {
 }  // namespace
 
 namespace mesm {
-struct ProfRec { cudaEvent_t a, b; double flops, bytes; int M; };
+struct ProfRec { cudaEvent_t a, b; double flops; int M; const char* name; };
 static thread_local std::vector<ProfRec> g_prof;
+static thread_local std::string g_prof_report;
+ProfScope::ProfScope(const char* name_, cudaStream_t s_, double flops_, int M_) : s(s_), name(name_), flops(flops_), M(M_), a(nullptr), on(g_stats.profile) {
+    if (on) { cudaEventCreate(&a); cudaEventRecord(a, s); }
+}
+ProfScope::~ProfScope() {
+    if (!on) return;
+    ProfRec r; r.a = a; cudaEventCreate(&r.b); cudaEventRecord(r.b, s); r.flops = flops; r.M = M; r.name = name;
+    g_prof.push_back(r);
+}
 static int force_simt() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MESM_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
     return v;
 }
-static cudaError_t dispatch_linear(const LinearOp& op, cudaStream_t s) {
-    if (!force_simt() && linear_tc_eligible(op)) return launch_linear_tc(op, s);
-    return launch_linear_simt(op, s);
-}
 cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) {
-    if (!g_stats.profile) return dispatch_linear(op, s);
-    ProfRec r;
-    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
-    r.flops = 2.0 * op.M * (double)op.N * ((double)op.K + op.K2);
-    r.bytes = 4.0 * ((double)op.M * (op.K + op.K2) + (double)op.M * op.N + (double)op.N * (op.K + op.K2));
-    r.M = op.M;
-    cudaEventRecord(r.a, s);
-    cudaError_t e = dispatch_linear(op, s);
-    cudaEventRecord(r.b, s);
-    g_prof.push_back(r);
-    return e;
+    const bool tc = !force_simt() && linear_tc_eligible(op);
+    const double flops = 2.0 * op.M * (double)op.N * ((double)op.K + op.K2) * (op.nbatch > 1 ? op.nbatch : 1);
+    const char* name = "linear_simt";
+    if (tc) name = op.K > 1024 ? "linear_tc K>1024" : (op.K == 1024 ? "linear_tc K=1024" : (op.N > 256 ? "linear_tc K<=512 N>256" : (op.ln_g ? "linear_tc K<=512 N=256 +LN" : "linear_tc K<=512 N=256")));
+    ProfScope ps(name, s, flops, op.M);
+    return tc ? launch_linear_tc(op, s) : launch_linear_simt(op, s);
 }
 void profile_collect() {
+    std::unordered_map<std::string, std::pair<double, long long>> by;
     for (auto& r : g_prof) {
         cudaEventSynchronize(r.b);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
-        g_stats.lin_ms += ms; g_stats.lin_flops += r.flops; g_stats.lin_bytes += r.bytes; g_stats.lin_launches++;
-        if (r.M >= 16384) { g_stats.big_ms += ms; g_stats.big_flops += r.flops; g_stats.big_launches++; }
+        by[r.name].first += ms; by[r.name].second++;
+        if (r.flops > 0) {
+            g_stats.lin_ms += ms; g_stats.lin_flops += r.flops; g_stats.lin_launches++;
+            if (r.M >= 16384) { g_stats.big_ms += ms; g_stats.big_flops += r.flops; g_stats.big_launches++; }
+        }
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     g_prof.clear();
+    g_prof_report.clear();
+    for (auto& kv : by) g_prof_report += kv.first + "\t" + std::to_string(kv.second.second) + "\t" + std::to_string(kv.second.first) + "\n";
 }
+const char* profile_report() { return g_prof_report.c_str(); }
 }  // namespace mesm
 
 // =====================================================================================================================
@@ -399,6 +406,8 @@ void mesm_profile_begin(void) {
     g_stats.lin_ms = g_stats.lin_flops = g_stats.lin_bytes = 0; g_stats.lin_launches = 0;
     g_stats.big_ms = g_stats.big_flops = 0; g_stats.big_launches = 0;
 }
+
+const char* mesm_profile_report(void) { return mesm::profile_report(); }
 
 void mesm_profile_end(double* out7) {
     mesm::profile_collect();
@@ -546,9 +555,10 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.wmask = ar.get<uint8_t>(Rt); p.emask = ar.get<uint8_t>(Rte); p.epad = ar.get<uint8_t>(Rte); p.wpad = ar.get<uint8_t>(Rt);
     p.neg_epad = ar.get<uint8_t>(Rte); p.neg_wpad = ar.get<uint8_t>(Rt); p.padV_all = ar.get<uint8_t>((size_t)B * Lv);
     p.d_tab = ar.get<int>((size_t)2 * B + 2 * (G + 1));
+    p.vstat = ar.get<float>((size_t)B * Lv * 2); p.v1 = ar.get<float>((size_t)B * Lv * D);
     const int L1 = Lv + 1;
     const size_t Rv = (size_t)Bc * Lv, Re = (size_t)Bc * L1, Rk = (size_t)Bc * (Lt + 1);
-    p.vstat = ar.get<float>(Rv * 2); p.v1 = ar.get<float>(Rv * D); p.posV = ar.get<float>(Rv * D); p.posE = ar.get<float>(Re * D);
+    p.posV = ar.get<float>(Rv * D); p.posE = ar.get<float>(Re * D);
     p.xa = ar.get<float>(Rv * D); p.xb = ar.get<float>(Rv * D); p.enh = ar.get<float>(Rv * D);
     p.E = ar.get<float>(Re * D); p.E2 = ar.get<float>(Re * D); p.P1 = ar.get<float>(Re * D); p.P2 = ar.get<float>((size_t)Bc * D);
     p.padV = ar.get<uint8_t>(Rv); p.padE = ar.get<uint8_t>(Re);
@@ -556,10 +566,10 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.t2v.X1 = ar.get<float>(Re * D); p.t2v.Y1 = ar.get<float>(Re * D); p.t2v.H = ar.get<float>(Re * FF);
     p.encb.QKV = ar.get<float>(Re * 3 * D); p.encb.AO = p.t2v.AO; p.encb.Y1 = p.t2v.Y1; p.encb.H = p.t2v.H;
     dec_alloc(ar, p.dec, Bc, cf.num_queries, L1, cf.dec_layers);
-    p.rS = ar.get<float>((size_t)Bc * D); p.rS2 = ar.get<float>((size_t)Bc * D); p.rq = ar.get<float>((size_t)Bc * D);
-    p.rqk = ar.get<float>((size_t)Bc * NH * D); p.rpool = ar.get<float>((size_t)Bc * NH * D); p.rao = ar.get<float>((size_t)Bc * D);
-    p.rX1 = ar.get<float>((size_t)Bc * D); p.rY1 = ar.get<float>((size_t)Bc * D); p.rH = ar.get<float>((size_t)Bc * FF);
-    p.rtmp = ar.get<float>((size_t)Bc * D);
+    p.rS = ar.get<float>((size_t)B * D); p.rS2 = ar.get<float>((size_t)B * D); p.rq = ar.get<float>((size_t)B * D);
+    p.rqk = ar.get<float>((size_t)B * NH * D); p.rpool = ar.get<float>((size_t)B * NH * D); p.rao = ar.get<float>((size_t)B * D);
+    p.rX1 = ar.get<float>((size_t)B * D); p.rY1 = ar.get<float>((size_t)B * D); p.rH = ar.get<float>((size_t)B * FF);
+    p.rtmp = ar.get<float>((size_t)B * D);
     p.total = ar.off + 256;
 }
 
@@ -569,7 +579,7 @@ extern "C" size_t mesm_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t L
     if (!ctx || B < 1 || Lv < 1 || Lt < 1) return 0;
     Arena ar(nullptr, 0);
     FwdPlan p;
-    plan_forward(ctx, ar, p, B, Lv, Lt, std::max(G, 1), std::min<int>(B, ctx->chunk_pairs), true);
+    plan_forward(ctx, ar, p, B, Lv, Lt, std::max(G, 1), std::min<int>(B, 2 * ctx->chunk_pairs), true);
     return p.total;
 }
 
@@ -606,6 +616,8 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     int* h_group = ctx->h_tab; int* h_slot = h_group + B; int* h_gstart = h_slot + B;
     std::vector<std::pair<int, int>> chunks;
     {
+        // chunks of whole video groups, greedily filled to chunk_pairs; a small tail chunk is re-balanced with its
+        // predecessor so that no launch sequence runs on a handful of pairs
         int b = 0, c0 = 0;
         for (int g = 0; g < G; ++g) {
             h_gstart[g] = b;
@@ -615,6 +627,13 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         }
         h_gstart[G] = B;
         chunks.push_back({c0, B});
+        const size_t nc = chunks.size();
+        if (nc >= 2 && chunks[nc - 1].second - chunks[nc - 1].first < ctx->chunk_pairs / 2) {
+            const int lo = chunks[nc - 2].first, hi = B, mid = lo + (hi - lo) / 2;
+            int g = h_group[mid], cut = h_gstart[g];                 // split on a group boundary near the middle
+            if (cut <= lo) cut = h_gstart[g + 1];
+            if (cut > lo && cut < hi) { chunks[nc - 2] = {lo, cut}; chunks[nc - 1] = {cut, hi}; }
+        }
     }
     int Bc_max = 0;
     for (auto& ch : chunks) Bc_max = std::max(Bc_max, ch.second - ch.first);
@@ -647,21 +666,56 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     float* recon_all = out->recon_feat ? out->recon_feat : p.recon;
     const int recon_max_keys = cf.qvh_grouping ? max_nc * Lv : Lv;
 
-    // One chunk of whole video groups through projection -> enhance -> (recon) -> align -> encoder -> (decoder, heads).
+    // ---- whole batch: input projection of the clips (model/model.py:166) — row-wise, no reason to chunk ---------------
+    {
+        const long long Rall = (long long)B * Lv;
+        CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s));
+        CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+        CK(Lin((int)Rall, ctx->vid1, p.v1, D, projV_all, D).run(s));
+    }
+    // ---- whole batch: SS-MESM sentence reconstruction (model/model.py:184-222, 467-488).  One masked sentence slot per
+    //      pair -> M = B rows; the per-head back-projections are batched over blockIdx.z. ------------------------------
+    {
+        float* S = p.rS; float* S2 = p.rS2;
+        CK(launch_broadcast_row(ctx->msent, S, B, s));
+        for (size_t l = 0; l < ctx->rec.size(); ++l) {
+            const AttnFfn& L = ctx->rec[l];
+            CK(Lin(B, L.q, S, D, p.rq, D).scale(kScale32).run(s));
+            {   // qk[b,h,:] = Wk_h^T q_h : per head [B,32] x [32,256]
+                PL w; w.Wt = L.in_w + (size_t)D * D; w.ldw = D; w.K = HD; w.N = D; w.bias = nullptr;
+                CK(Lin(B, w, p.rq, D, p.rqk, NH * D).batch(NH, HD, (long long)HD * D, 0, D).run(s));
+            }
+            ReconPoolArgs ra;
+            ra.x = projV_all; ra.ldx = D; ra.vmask = in->video_mask; ra.qk = p.rqk; ra.pooled = p.rpool;
+            ra.pair_group = d_group; ra.pair_slot = d_slot; ra.group_start = d_gstart; ra.group_len = d_glen;
+            ra.B = B; ra.Lv = Lv; ra.qvh = cf.qvh_grouping; ra.max_keys = recon_max_keys; ra.b0 = 0; ra.Btot = B;
+            CK(launch_recon_pool(ra, s));
+            {   // attn_out[:, h*32:+32] = Wv_h pooled_h + bv_h
+                PL w; w.Wt = L.vT; w.ldw = L.v.ldw; w.K = D; w.N = HD; w.bias = L.v.bias;
+                CK(Lin(B, w, p.rpool, NH * D, p.rao, D).batch(NH, D, HD, HD, HD).run(s));
+            }
+            CK(Lin(B, L.out, p.rao, D, p.rY1, D).res(S, D).pre_ln(p.rX1).ln(L.n1).run(s));
+            CK(Lin(B, L.l1, p.rY1, D, p.rH, FF).act(ACT_PRELU, L.prelu).run(s));
+            CK(Lin(B, L.l2, p.rH, FF, S2, D).res(p.rX1, D).ln(L.n2).run(s));
+            std::swap(S, S2);
+        }
+        // recon_feat = F.normalize(.) -> word slot 0 of the expanded text (model/model.py:217, 486)
+        CK(launch_l2norm_rows(S, B, recon_all, expw, D, RowMap{1, Lk, 0}, s));
+        if (out->projed_recon_feat) {           // output_sent_proj (model/model.py:487)
+            CK(launch_layernorm_rows(recon_all, B, ctx->osp0_ln.g, ctx->osp0_ln.b, p.rtmp, s));
+            CK(Lin(B, ctx->osp0, p.rtmp, D, p.rY1, D).act(ACT_RELU).ln(ctx->osp1_ln).run(s));
+            CK(Lin(B, ctx->osp1, p.rY1, D, out->projed_recon_feat, D).run(s));
+        }
+    }
+
+    // One chunk of whole video groups through enhance -> align -> encoder -> (decoder, heads).
     auto video_chunk = [&](int b0, int b1, bool neg) -> int {
         const int Bc = b1 - b0, Rv = Bc * Lv, Re = Bc * L1;
-        const float* vfeat = in->video_feat + (size_t)b0 * Lv * cf.v_feat_dim;
         const uint8_t* vmask = in->video_mask + (size_t)b0 * Lv;
         float* projV = projV_all + (size_t)b0 * Lv * D;
         PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos;
         pa.posV = p.posV; pa.posE = p.posE; pa.encbuf = p.E; pa.padV = p.padV; pa.padE = p.padE;
         CK(launch_pos_embed(pa, s));
-        if (!neg) {
-            // input projection (model/model.py:166): LayerNorm folded into the GEMM -> ReLU -> LN(256) -> GEMM
-            CK(launch_row_stats(vfeat, Rv, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s));
-            CK(Lin(Rv, ctx->vid0, vfeat, cf.v_feat_dim, p.v1, D).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
-            CK(Lin(Rv, ctx->vid1, p.v1, D, projV, D).run(s));
-        }
         const float* words_c = (neg ? p.negw : expw) + (size_t)b0 * Lk * D;
         const uint8_t* epad_all = neg ? p.neg_epad : p.epad;
         const uint8_t* wpad_all = neg ? p.neg_wpad : p.wpad;
@@ -676,39 +730,6 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         }
         if (ctx->enh.empty() && !neg && out->enhanced_video_feat)
             CK(cudaMemcpyAsync(enh, projV, (size_t)Rv * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        // ---- SS-MESM sentence reconstruction (model/model.py:184-222, 467-488) ----
-        if (!neg) {
-            float* S = p.rS; float* S2 = p.rS2;
-            CK(launch_broadcast_row(ctx->msent, S, Bc, s));
-            for (size_t l = 0; l < ctx->rec.size(); ++l) {
-                const AttnFfn& L = ctx->rec[l];
-                CK(Lin(Bc, L.q, S, D, p.rq, D).scale(kScale32).run(s));
-                for (int h = 0; h < NH; ++h) {      // qk[b,h,:] = Wk_h^T q_h : [Bc,32] x [32,256]
-                    PL w; w.Wt = L.in_w + (size_t)(D + h * HD) * D; w.ldw = D; w.K = HD; w.N = D; w.bias = nullptr;
-                    CK(Lin(Bc, w, p.rq + h * HD, D, p.rqk + h * D, NH * D).run(s));
-                }
-                ReconPoolArgs ra;
-                ra.x = projV; ra.ldx = D; ra.vmask = in->video_mask; ra.qk = p.rqk; ra.pooled = p.rpool;
-                ra.pair_group = d_group; ra.pair_slot = d_slot; ra.group_start = d_gstart; ra.group_len = d_glen;
-                ra.B = Bc; ra.Lv = Lv; ra.qvh = cf.qvh_grouping; ra.max_keys = recon_max_keys; ra.b0 = b0; ra.Btot = B;
-                CK(launch_recon_pool(ra, s));
-                for (int h = 0; h < NH; ++h) {      // attn_out[:, h*32:+32] = Wv_h pooled_h + bv_h
-                    PL w; w.Wt = L.vT + h * HD; w.ldw = L.v.ldw; w.K = D; w.N = HD; w.bias = L.v.bias + h * HD;
-                    CK(Lin(Bc, w, p.rpool + h * D, NH * D, p.rao + h * HD, D).run(s));
-                }
-                CK(Lin(Bc, L.out, p.rao, D, p.rY1, D).res(S, D).pre_ln(p.rX1).ln(L.n1).run(s));
-                CK(Lin(Bc, L.l1, p.rY1, D, p.rH, FF).act(ACT_PRELU, L.prelu).run(s));
-                CK(Lin(Bc, L.l2, p.rH, FF, S2, D).res(p.rX1, D).ln(L.n2).run(s));
-                std::swap(S, S2);
-            }
-            // recon_feat = F.normalize(.) -> word slot 0 of the expanded text (model/model.py:217, 486)
-            CK(launch_l2norm_rows(S, Bc, recon_all + (size_t)b0 * D, expw + (size_t)b0 * Lk * D, D, RowMap{1, Lk, 0}, s));
-            if (out->projed_recon_feat) {           // output_sent_proj (model/model.py:487)
-                CK(launch_layernorm_rows(recon_all + (size_t)b0 * D, Bc, ctx->osp0_ln.g, ctx->osp0_ln.b, p.rtmp, s));
-                CK(Lin(Bc, ctx->osp0, p.rtmp, D, p.rY1, D).act(ACT_RELU).ln(ctx->osp1_ln).run(s));
-                CK(Lin(Bc, ctx->osp1, p.rY1, D, out->projed_recon_feat + (size_t)b0 * D, D).run(s));
-            }
-        }
         // ---- aligner (model/model.py:230-234; neg: 290-294): keys = recon token + words; last layer writes the
         //      encoder buffer [Bc, Lv+1, 256] behind the global token ----
         const float* xin = ctx->enh.empty() ? projV : enh;

@@ -21,9 +21,10 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
     extern __shared__ float smem[];
     const int h = blockIdx.x, b = blockIdx.y;
     const int Lk = a.Lk;
-    float* Ks = smem;                       // [Lk][33]
-    float* Vs = Ks + Lk * 33;               // [Lk][33]
-    uint8_t* pad_own = reinterpret_cast<uint8_t*>(Vs + Lk * 33);     // [Lk]
+    // every thread of a warp reads the SAME key row (broadcast): rows stay 16-byte aligned for LDS.128, no padding needed
+    float* Ks = smem;                       // [Lk][32]
+    float* Vs = Ks + Lk * 32;               // [Lk][32]
+    uint8_t* pad_own = reinterpret_cast<uint8_t*>(Vs + Lk * 32);     // [Lk]
     uint8_t* pad_oth = pad_own + Lk;                                  // [Lk]   k_pad of pair b'
     const int bg = a.b0 + b;                                           // global pair index
     const int bp = QUIRK ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
@@ -31,8 +32,8 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
     for (int idx = threadIdx.x; idx < Lk * 32; idx += blockDim.x) {
         const int kk = idx >> 5, j = idx & 31;
         const long long row = (long long)b * Lk + kk;
-        Ks[kk * 33 + j] = a.k[row * a.ldk + h * 32 + j];
-        Vs[kk * 33 + j] = a.v[row * a.ldv + h * 32 + j];
+        Ks[kk * 32 + j] = a.k[row * a.ldk + h * 32 + j];
+        Vs[kk * 32 + j] = a.v[row * a.ldv + h * 32 + j];
     }
     for (int kk = threadIdx.x; kk < Lk; kk += blockDim.x) {
         pad_own[kk] = a.k_pad[(long long)bg * Lk + kk];
@@ -66,10 +67,15 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
             if (kk < Lk) {
                 const bool masked = pad_own[kk] || (qpad_oth && pad_oth[kk]);
                 if (!masked) {
-                    acc = 0.f;
-                    const float* kr = Ks + kk * 33;
+                    const float4* kr = reinterpret_cast<const float4*>(Ks + kk * 32);
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc = fmaf(q[j], kr[j], acc);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = kr[j];
+                        a0 = fmaf(q[4 * j], t.x, a0); a1 = fmaf(q[4 * j + 1], t.y, a1);
+                        a2 = fmaf(q[4 * j + 2], t.z, a2); a3 = fmaf(q[4 * j + 3], t.w, a3);
+                    }
+                    acc = (a0 + a1) + (a2 + a3);
                 }
             }
             s[u] = acc;
@@ -87,9 +93,13 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
             if (s[u] == -CUDART_INF_F) continue;
             const float p = __expf(s[u] - mn);
             l += p;
-            const float* vr = Vs + (k0 + u) * 33;
+            const float4* vr = reinterpret_cast<const float4*>(Vs + (k0 + u) * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = fmaf(p, vr[j], o[j]);
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = vr[j];
+                o[4 * j] = fmaf(p, t.x, o[4 * j]); o[4 * j + 1] = fmaf(p, t.y, o[4 * j + 1]);
+                o[4 * j + 2] = fmaf(p, t.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(p, t.w, o[4 * j + 3]);
+            }
         }
     }
     const float inv = 1.f / l;                 // l == 0 (all keys masked) -> inf*0 = NaN like the reference
@@ -99,10 +109,11 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
 }
 
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s) {
+    ProfScope _ps("mha_rows", s);
     if (a.B <= 0 || a.Lq <= 0) return cudaSuccess;
     const int threads = ((a.Lq + 31) / 32) * 32;
     if (threads > 1024) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)a.Lk * 33 * 2 * sizeof(float) + 2 * (size_t)a.Lk;
+    const size_t smem = (size_t)a.Lk * 32 * 2 * sizeof(float) + 2 * (size_t)a.Lk;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
     dim3 grid(NH, a.B);
     if (a.q_pad) {
@@ -196,6 +207,7 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
 }
 
 cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s) {
+    ProfScope _ps("mha_small", s);
     if (a.B <= 0 || a.L <= 0) return cudaSuccess;
     const int E = a.hq * (a.q2 ? 2 : 1);
     const size_t smem = ((size_t)a.L * E + (size_t)a.L * a.S) * sizeof(float);
@@ -296,6 +308,7 @@ __global__ void __launch_bounds__(256) recon_pool_kernel(const ReconPoolArgs a) 
 }
 
 cudaError_t launch_recon_pool(const ReconPoolArgs& a, cudaStream_t s) {
+    ProfScope _ps("recon_pool", s);
     if (a.B <= 0) return cudaSuccess;
     const size_t smem = (size_t)a.max_keys * (8 * sizeof(float) + sizeof(int));
     if (smem > 200 * 1024) return cudaErrorInvalidValue;

@@ -46,6 +46,8 @@ struct LinearOp {
     float* out; int ldo; RowMap omap;
     float* out2; int ldo2; RowMap o2map;          // optional duplicate store of the final value
     float* pre_ln;                                // optional store of the value before LayerNorm ([M,N], ld = N)
+    int nbatch;                                   // >1: blockIdx.z batches (per-head GEMMs); element strides below
+    long long bsA, bsW, bsBias, bsOut;
 };
 
 static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda, const float* Wt, int ldw,
@@ -56,6 +58,7 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
     op.bias = bias; op.rowstat = nullptr; op.colsum = nullptr; op.out_scale = 1.f; op.act = ACT_NONE; op.prelu = nullptr;
     op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
     op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr;
+    op.nbatch = 1; op.bsA = op.bsW = op.bsBias = op.bsOut = 0;
     return op;
 }
 
@@ -67,7 +70,14 @@ struct LaunchStats {
     double big_ms = 0, big_flops = 0; long long big_launches = 0;                     // launches with M >= 16384 only
 };
 extern thread_local LaunchStats g_stats;
+const char* profile_report();
 void profile_collect();     // synchronises the recorded events and folds them into g_stats
+// RAII CUDA-event bracket around one launch (active only between mesm_profile_begin / _end)
+struct ProfScope {
+    cudaStream_t s; const char* name; double flops; int M; cudaEvent_t a; bool on;
+    ProfScope(const char* name_, cudaStream_t s_, double flops_ = 0, int M_ = 0);
+    ~ProfScope();
+};
 
 cudaError_t launch_linear(const LinearOp& op, cudaStream_t s);        // dispatcher (tcgen05 when eligible)
 cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s);   // fp32 SIMT kernel

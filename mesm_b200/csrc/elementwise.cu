@@ -35,6 +35,7 @@ __global__ void text_prep_kernel(const float* __restrict__ x, int R, int Dt, flo
     }
 }
 cudaError_t launch_text_prep(const float* x, int R, int Dt, float* y, uint8_t* mask, float* rowstat, cudaStream_t s) {
+    ProfScope _ps("text_prep", s);
     if (R <= 0) return cudaSuccess;
     text_prep_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, R, Dt, y, mask, rowstat);
     LAUNCH_END();
@@ -68,6 +69,7 @@ __global__ void row_stats_kernel(const float* __restrict__ x, long long R, int D
     }
 }
 cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float* rowstat, cudaStream_t s) {
+    ProfScope _ps("row_stats", s);
     if (R <= 0) return cudaSuccess;
     row_stats_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, R, Dv, ldx, rowstat);
     LAUNCH_END();
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(256) pos_embed_kernel(const PosArgs a) {
     if (a.encbuf) a.encbuf[(long long)b * (Lv + 1) * D + c] = a.gtok[c];
 }
 cudaError_t launch_pos_embed(const PosArgs& a, cudaStream_t s) {
+    ProfScope _ps("pos_embed", s);
     if (a.B <= 0) return cudaSuccess;
     pos_embed_kernel<<<a.B, 256, a.Lv * sizeof(float), s>>>(a);
     LAUNCH_END();
@@ -115,6 +118,7 @@ __global__ void invert_mask_kernel(const uint8_t* __restrict__ in, uint8_t* __re
     if (i < n) out[i] = in[i] ? 0 : 1;
 }
 cudaError_t launch_invert_mask(const uint8_t* in, uint8_t* out, long long n, cudaStream_t s) {
+    ProfScope _ps("invert_mask", s);
     if (n <= 0) return cudaSuccess;
     invert_mask_kernel<<<blocks_for(n, 256), 256, 0, s>>>(in, out, n);
     LAUNCH_END();
@@ -132,6 +136,7 @@ __global__ void expand_mask_kernel(const uint8_t* __restrict__ wmask, int B, int
     if (wpad && j > 0) wpad[b * Lt + j - 1] = v ? 0 : 1;
 }
 cudaError_t launch_expand_mask(const uint8_t* wmask, int B, int Lt, uint8_t* emask, uint8_t* epad, uint8_t* wpad, cudaStream_t s) {
+    ProfScope _ps("expand_mask", s);
     if (B <= 0) return cudaSuccess;
     expand_mask_kernel<<<blocks_for((long long)B * (Lt + 1), 256), 256, 0, s>>>(wmask, B, Lt, emask, epad, wpad);
     LAUNCH_END();
@@ -144,6 +149,7 @@ __global__ void wpad_from_epad_kernel(const uint8_t* __restrict__ epad, int B, i
     wpad[idx] = epad[b * (Lt + 1) + 1 + j];
 }
 cudaError_t launch_expand_mask_from_epad(const uint8_t* epad, int B, int Lt, uint8_t* wpad, cudaStream_t s) {
+    ProfScope _ps("expand_mask_from_epad", s);
     if (B <= 0) return cudaSuccess;
     wpad_from_epad_kernel<<<blocks_for((long long)B * Lt, 256), 256, 0, s>>>(epad, B, Lt, wpad);
     LAUNCH_END();
@@ -164,6 +170,7 @@ __global__ void gather_blocks_kernel(const float* __restrict__ src, float* __res
 }
 cudaError_t launch_gather_blocks(const float* src, float* dst, const int64_t* idx, int B, long long block_elems,
                                  const uint8_t* msrc, uint8_t* mdst, int mlen, cudaStream_t s) {
+    ProfScope _ps("gather_blocks", s);
     if (B <= 0) return cudaSuccess;
     if (block_elems & 3) return cudaErrorInvalidValue;
     dim3 grid((unsigned)min((long long)8, (block_elems / 4 + 255) / 256), B);
@@ -180,6 +187,7 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int lds, RowMap 
     *reinterpret_cast<float4*>(dst + omap((int)r) * ldd + c) = *reinterpret_cast<const float4*>(src + imap((int)r) * lds + c);
 }
 cudaError_t launch_copy_rows(const float* src, int lds, RowMap imap, float* dst, int ldd, RowMap omap, long long R, cudaStream_t s) {
+    ProfScope _ps("copy_rows", s);
     if (R <= 0) return cudaSuccess;
     copy_rows_kernel<<<blocks_for(R, 4), 256, 0, s>>>(src, lds, imap, dst, ldd, omap, R);
     LAUNCH_END();
@@ -193,6 +201,7 @@ __global__ void broadcast_row_kernel(const float* __restrict__ vec, float* __res
     *reinterpret_cast<float4*>(dst + r * D + c) = *reinterpret_cast<const float4*>(vec + c);
 }
 cudaError_t launch_broadcast_row(const float* vec, float* dst, long long R, cudaStream_t s) {
+    ProfScope _ps("broadcast_row", s);
     if (R <= 0) return cudaSuccess;
     broadcast_row_kernel<<<blocks_for(R, 4), 256, 0, s>>>(vec, dst, R);
     LAUNCH_END();
@@ -214,6 +223,7 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, long long R, flo
     if (out2) { float4* o = reinterpret_cast<float4*>(out2 + map2((int)r) * ld2 + lane * 8); o[0] = a; o[1] = b; }
 }
 cudaError_t launch_l2norm_rows(const float* x, long long R, float* out1, float* out2, int ld2, RowMap map2, cudaStream_t s) {
+    ProfScope _ps("l2norm_rows", s);
     if (R <= 0) return cudaSuccess;
     l2norm_rows_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, R, out1, out2, ld2, map2);
     LAUNCH_END();
@@ -234,6 +244,7 @@ __global__ void saliency_kernel(const float* __restrict__ p1, RowMap map1, const
     if (lane == 0) out[r] = d / 16.f;
 }
 cudaError_t launch_saliency(const float* p1, RowMap map1, const float* p2, int B, int Lv, float* out, cudaStream_t s) {
+    ProfScope _ps("saliency", s);
     if (B <= 0) return cudaSuccess;
     saliency_kernel<<<blocks_for((long long)B * Lv, 8), 256, 0, s>>>(p1, map1, p2, B, Lv, out);
     LAUNCH_END();
@@ -253,6 +264,7 @@ __global__ void dec_init_ref_kernel(const float* __restrict__ qe, int B, int nq,
     ref[idx] = sigmoidf(qe[idx % (nq * 2)]);
 }
 cudaError_t launch_dec_init_ref(const float* qe, int B, int nq, float* ref, cudaStream_t s) {
+    ProfScope _ps("dec_init_ref", s);
     dec_init_ref_kernel<<<blocks_for((long long)B * nq * 2, 256), 256, 0, s>>>(qe, B, nq, ref);
     LAUNCH_END();
 }
@@ -279,6 +291,7 @@ __global__ void dec_sine_kernel(const float* __restrict__ ref, long long R, cons
 }
 cudaError_t launch_dec_sine(const float* ref, long long R, const float* pos_trans, const float* anchor, float* sine,
                             float* scaled, cudaStream_t s) {
+    ProfScope _ps("dec_sine", s);
     if (R <= 0) return cudaSuccess;
     dec_sine_kernel<<<(unsigned)R, 256, 0, s>>>(ref, R, pos_trans, anchor, sine, scaled);
     LAUNCH_END();
@@ -293,6 +306,7 @@ __global__ void ref_update_kernel(const float* __restrict__ delta, int ldd, cons
     out[i] = sigmoidf(delta[r * ldd + c] + inv_sigmoid(ref[i]));
 }
 cudaError_t launch_ref_update(const float* delta, int ldd, const float* ref, long long rows, float* out, cudaStream_t s) {
+    ProfScope _ps("ref_update", s);
     if (rows <= 0) return cudaSuccess;
     ref_update_kernel<<<blocks_for(rows * 2, 256), 256, 0, s>>>(delta, ldd, ref, rows * 2, out);
     LAUNCH_END();
@@ -323,6 +337,7 @@ __global__ void layernorm_rows_kernel(const float* __restrict__ x, long long R, 
     op[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 cudaError_t launch_layernorm_rows(const float* x, long long R, const float* g, const float* b, float* out, cudaStream_t s) {
+    ProfScope _ps("layernorm_rows", s);
     if (R <= 0) return cudaSuccess;
     layernorm_rows_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, R, g, b, out);
     LAUNCH_END();
@@ -345,6 +360,7 @@ __global__ void group_len_kernel(const uint8_t* __restrict__ vmask, int Lv, cons
     if (threadIdx.x == 0) group_len[g] = tot;
 }
 cudaError_t launch_group_len(const uint8_t* vmask, int Lv, const int* group_start, int G, int* group_len, cudaStream_t s) {
+    ProfScope _ps("group_len", s);
     if (G <= 0) return cudaSuccess;
     group_len_kernel<<<G, 128, 0, s>>>(vmask, Lv, group_start, G, group_len);
     LAUNCH_END();
@@ -371,6 +387,7 @@ __global__ void masked_mean_norm_kernel(const float* __restrict__ x, const uint8
     if (transposed) out[(long long)c * ldo + b] = o; else out[(long long)b * ldo + c] = o;
 }
 cudaError_t launch_masked_mean_norm(const float* x, const uint8_t* mask, int B, int L, float* out, int ldo, int transposed, cudaStream_t s) {
+    ProfScope _ps("masked_mean_norm", s);
     if (B <= 0) return cudaSuccess;
     masked_mean_norm_kernel<<<B, 256, 0, s>>>(x, mask, B, L, out, ldo, transposed);
     LAUNCH_END();
@@ -381,6 +398,7 @@ __global__ void fill_kernel(float* p, long long n, float v) {
     if (i < n) p[i] = v;
 }
 cudaError_t launch_fill(float* p, long long n, float v, cudaStream_t s) {
+    ProfScope _ps("fill", s);
     if (n <= 0) return cudaSuccess;
     fill_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);
     LAUNCH_END();

@@ -23,7 +23,13 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v;
 }
 
-__global__ void __launch_bounds__(NT, 2) linear_simt_kernel(const LinearOp op) {
+__global__ void __launch_bounds__(NT, 2) linear_simt_kernel(const LinearOp op_in) {
+    LinearOp op = op_in;
+    if (op.nbatch > 1) {           // per-head batch: shift the operand / output pointers
+        const long long z = blockIdx.z;
+        op.A += z * op.bsA; op.Wt += z * op.bsW; op.out += z * op.bsOut;
+        if (op.bias) op.bias += z * op.bsBias;
+    }
     __shared__ __align__(16) float As[BK][AS_LD];
     __shared__ __align__(16) float Ws[BK][BN];
 
@@ -215,7 +221,7 @@ cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s) {
     if (op.M <= 0 || op.N <= 0) return cudaSuccess;
     if (op.ln_g && op.N != 256) return cudaErrorInvalidValue;
     if ((op.ldw & 3) != 0) return cudaErrorInvalidValue;
-    dim3 grid((op.M + BM - 1) / BM, (op.N + BN - 1) / BN);
+    dim3 grid((op.M + BM - 1) / BM, (op.N + BN - 1) / BN, op.nbatch > 1 ? op.nbatch : 1);
     linear_simt_kernel<<<grid, NT, 0, s>>>(op);
     g_stats.launches++;
     return cudaGetLastError();

@@ -29,13 +29,13 @@ __device__ long long g_tc_times[64];
 #define TSTAMP(i) do {} while (0)
 #endif
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;                       // bytes of one bf16 plane of the A tile
 constexpr int W_TILE = BN * BK * 2;
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;      // 98304
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;      // 49152: two CTAs (2 x ~105 KB) share one SM
 constexpr int NCONV = 256;                                // converter / epilogue threads (8 warps)
 constexpr int THREADS = 64 + NCONV;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 + 1024 + 4096 + 3072 /*barriers, LN exchange, epilogue vectors, row offsets*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 + 1024 + 4096 + 3072 + 2048 /*barriers, LN exchange, epilogue vectors, row offsets*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -67,15 +67,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
-// LBO (unused for swizzled K-major) [16,30), SBO = 1024 B (8 rows x 128 B) [32,46), version 1 [46,48), layout 2 [61,64).
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO (unused for swizzled K-major) [16,30), SBO = 512 B (8 rows x 64 B) [32,46), version 1 [46,48), layout type
+// SWIZZLE_64B = 4 in [61,64).  Rows are 64 bytes (32 bf16 of K); the 16-byte chunk index is XORed with (row >> 1) & 3.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128.
@@ -118,6 +119,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// byte offset of element (row, k) inside a K-major SWIZZLE_64B tile whose rows hold BK = 32 bf16
+__device__ __forceinline__ int sw64(int row, int k) { return row * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) << 4) | ((k & 7) << 1)); }
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
@@ -132,7 +136,9 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
 
 // VEC = floats per global load of the A operand (4: 16-byte aligned rows; 2: 8-byte aligned rows such as Dv = 2818)
 template <int VEC>
-__global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op, const int nkb1, const int nkb2) {
+__global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op, const int nkb1, const int nkb2) {
+    // K sweeps accumulated into one tile: A.W^T, then (if present) Apos.W^T with the same weights, then A2.W2^T.
+    const int nkbp = op.Apos ? nkb1 : 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -143,11 +149,12 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
     float* ln_x = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 64);      // [2][128] partial sums
     float* vec_s = ln_x + 256;                                                      // [4][256]: bias, colsum, ln_g, ln_b of this N tile
     long long* rowoff = reinterpret_cast<long long*>(vec_s + 1024);                 // [3][128]: out, out2, residual row offsets (-1: no row)
+    long long* rowoffA = rowoff + 3 * 128;                                          // [2][128]: A / A2 operand row offsets
 
     if (threadIdx.x == 0) TSTAMP(0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, nt = blockIdx.y, n0 = nt * BN;
-    const int nkb = nkb1 + nkb2;
+    const int nkb = nkb1 + nkbp + nkb2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -175,9 +182,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint8_t* src = kb < nkb1
-                                         ? reinterpret_cast<const uint8_t*>(op.Wp) + ((size_t)nt * nkb1 + kb) * (2 * W_TILE)
-                                         : reinterpret_cast<const uint8_t*>(op.Wp2) + ((size_t)nt * nkb2 + (kb - nkb1)) * (2 * W_TILE);
+                const int kk = kb < nkb1 ? kb : (kb < nkb1 + nkbp ? kb - nkb1 : kb - nkb1 - nkbp);
+                const uint8_t* src = kb < nkb1 + nkbp
+                                         ? reinterpret_cast<const uint8_t*>(op.Wp) + ((size_t)nt * nkb1 + kk) * (2 * W_TILE)
+                                         : reinterpret_cast<const uint8_t*>(op.Wp2) + ((size_t)nt * nkb2 + kk) * (2 * W_TILE);
                 mbar_arrive_expect_tx(bar_full_w + 8 * s, 2 * W_TILE);
                 const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_TILE;
                 bulk_copy_g2s(dst, src, W_TILE, bar_full_w + 8 * s);
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
                 const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + W_TILE;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                    const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes along K inside the 128B swizzle row
+                    const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes along K inside the 64B swizzle row
                     const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
                     const uint64_t dwh = make_desc(w_hi + koff), dwl = make_desc(w_lo + koff);
                     umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u);
@@ -219,60 +227,13 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
         constexpr int ROW_STEP = NCONV / PER_ROW;          // 16 or 8
         const int cv = tc % PER_ROW, r0 = tc / PER_ROW;
 
-        // Global loads are issued branch-free (clamped addresses, validity applied later) so that all NV vector loads
-        // of a K block are in flight together; the block after the one being converted is always outstanding.
-        float cur[NV * VEC], nxa[NV * VEC], nxp[NV * VEC];
-        const bool has_pos = op.Apos != nullptr;
-        long long roff1[NV], roff2[NV];
-        unsigned rowok = 0;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int m = m0 + r0 + i * ROW_STEP;
+        // Row offsets of the tile's 128 rows for the A / A2 operands, once (RowMap needs an integer division).
+        if (tc < 128) {
+            const int m = m0 + tc;
             const bool ok = m < op.M;
-            rowok |= (ok ? 1u : 0u) << i;
-            roff1[i] = ok ? op.amap(m) * (long long)op.lda : 0;
-            roff2[i] = (ok && op.A2) ? op.a2map(m) * (long long)op.lda2 : 0;
+            rowoffA[tc] = ok ? op.amap(m) * (long long)op.lda : -1;
+            rowoffA[128 + tc] = (ok && op.A2) ? op.a2map(m) * (long long)op.lda2 : -1;
         }
-        auto load_block = [&](int kb) {
-            const bool second = kb >= nkb1;
-            const float* A = second ? op.A2 : op.A;
-            const float* P = second ? nullptr : op.Apos;
-            const int K = second ? op.K2 : op.K;
-            const int k = (second ? kb - nkb1 : kb) * BK + cv * VEC;
-            const int kc = (k + VEC <= K) ? k : 0;                 // clamped (tail handled below)
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const long long off = (second ? roff2[i] : roff1[i]) + kc;
-                if (VEC == 4) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(A + off));
-                    nxa[i * 4] = t.x; nxa[i * 4 + 1] = t.y; nxa[i * 4 + 2] = t.z; nxa[i * 4 + 3] = t.w;
-                } else {
-                    const float2 t = __ldg(reinterpret_cast<const float2*>(A + off));
-                    nxa[i * 2] = t.x; nxa[i * 2 + 1] = t.y;
-                }
-            }
-            if (P) {
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    const long long off = roff1[i] + kc;
-                    if (VEC == 4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(P + off));
-                        nxp[i * 4] = t.x; nxp[i * 4 + 1] = t.y; nxp[i * 4 + 2] = t.z; nxp[i * 4 + 3] = t.w;
-                    } else {
-                        const float2 t = __ldg(reinterpret_cast<const float2*>(P + off));
-                        nxp[i * 2] = t.x; nxp[i * 2 + 1] = t.y;
-                    }
-                }
-            }
-        };
-        // validity of the block's k range for this thread: 2 = whole vector, 1 = partial tail (scalar reload), 0 = none
-        auto kstate = [&](int kb) {
-            const bool second = kb >= nkb1;
-            const int K = second ? op.K2 : op.K;
-            const int k = (second ? kb - nkb1 : kb) * BK + cv * VEC;
-            return (k + VEC <= K) ? 2 : (k < K ? 1 : 0);
-        };
-
         {   // stage the per-column epilogue vectors of this N tile once (read by every row of the tile)
             const int n = n0 + tc;
             const bool nok = n < op.N;
@@ -288,33 +249,54 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
                 rowoff[256 + tc] = (ok && op.residual) ? op.rmap(m) * (long long)op.ldr : -1;
             }
         }
-        load_block(0);
-        for (int kb = 0; kb < nkb; ++kb) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        // Global loads are issued branch-free (clamped addresses, validity applied at conversion time) and TWO K blocks
+        // ahead of the block being converted, alternating between two register buffers.
+        float buf0[NV * VEC], buf1[NV * VEC];
+        struct Src { const float* base; int K; int k0; int tab; };
+        auto source = [&](int kb) {
+            Src r;
+            if (kb < nkb1) { r.base = op.A; r.K = op.K; r.k0 = kb * BK; r.tab = 0; }
+            else if (kb < nkb1 + nkbp) { r.base = op.Apos; r.K = op.K; r.k0 = (kb - nkb1) * BK; r.tab = 0; }
+            else { r.base = op.A2; r.K = op.K2; r.k0 = (kb - nkb1 - nkbp) * BK; r.tab = 128; }
+            return r;
+        };
+        auto load_block = [&](int kb, float (&dst)[NV * VEC]) {
+            const Src sc = source(kb);
+            const int k = sc.k0 + cv * VEC;
+            const int kc = (k + VEC <= sc.K) ? k : 0;              // clamped; the K tail is re-read at conversion time
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const long long ro = rowoffA[sc.tab + r0 + i * ROW_STEP];
+                const long long off = (ro < 0 ? 0 : ro) + kc;
+                if (VEC == 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(sc.base + off));
+                    dst[i * 4] = t.x; dst[i * 4 + 1] = t.y; dst[i * 4 + 2] = t.z; dst[i * 4 + 3] = t.w;
+                } else {
+                    const float2 t = __ldg(reinterpret_cast<const float2*>(sc.base + off));
+                    dst[i * 2] = t.x; dst[i * 2 + 1] = t.y;
+                }
+            }
+        };
+        auto convert_block = [&](int kb, float (&src)[NV * VEC]) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
-            const int ks = kstate(kb);
-            const bool use_pos = has_pos && kb < nkb1;
+            const Src sc = source(kb);
+            const int k = sc.k0 + cv * VEC;
+            const int ks = (k + VEC <= sc.K) ? 2 : (k < sc.K ? 1 : 0);
+            float cur[NV * VEC];
 #pragma unroll
-            for (int i = 0; i < NV * VEC; ++i) cur[i] = use_pos ? nxa[i] + nxp[i] : nxa[i];
-            if (ks != 2) {                                          // K tail: zero / scalar reload (rare: last block only)
-                const bool second = kb >= nkb1;
-                const float* A = second ? op.A2 : op.A;
-                const float* P = second ? nullptr : op.Apos;
-                const int K = second ? op.K2 : op.K;
-                const int k = (second ? kb - nkb1 : kb) * BK + cv * VEC;
+            for (int i = 0; i < NV; ++i) {
+                const long long ro = rowoffA[sc.tab + r0 + i * ROW_STEP];
 #pragma unroll
-                for (int i = 0; i < NV; ++i)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        float v = 0.f;
-                        if (ks == 1 && k + j < K && ((rowok >> i) & 1u)) {
-                            const long long off = (second ? roff2[i] : roff1[i]) + k + j;
-                            v = A[off] + (P ? P[off] : 0.f);
-                        }
-                        cur[i * VEC + j] = v;
-                    }
+                for (int j = 0; j < VEC; ++j) {
+                    float v = src[i * VEC + j];
+                    if (ks != 2) v = (ks == 1 && k + j < sc.K && ro >= 0) ? sc.base[ro + k + j] : 0.f;   // K tail (last block only)
+                    cur[i * VEC + j] = ro >= 0 ? v : 0.f;
+                }
             }
-            if (kb + 1 < nkb) load_block(kb + 1);
+            if (kb + 2 < nkb) load_block(kb + 2, src);             // refill this buffer: two blocks stay in flight
             if (tc == 0 && kb < 8) TSTAMP(24 + kb);
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             if (tc == 0 && kb < 8) TSTAMP(32 + kb);
@@ -323,12 +305,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int row = r0 + i * ROW_STEP;
-                const float keep = ((rowok >> i) & 1u) ? 1.f : 0.f;
                 __nv_bfloat16 h[VEC], l[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) split_bf16(keep != 0.f ? cur[i * VEC + j] : 0.f, h[j], l[j]);
-                const int kel = cv * VEC;                                        // k element index inside the 64-wide row
-                const int byte = row * 128 + ((((kel >> 3) ^ (row & 7)) << 4) | ((kel & 7) << 1));
+                for (int j = 0; j < VEC; ++j) split_bf16(cur[i * VEC + j], h[j], l[j]);
+                const int byte = sw64(row, cv * VEC);
                 if (VEC == 4) {
                     uint2 ph2, pl2;
                     ph2.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
@@ -348,10 +328,16 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full_a + 8 * s);
             if (tc == 0 && kb < 8) TSTAMP(40 + kb);
+        };
+
+        load_block(0, buf0);
+        if (nkb > 1) load_block(1, buf1);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            convert_block(kb, buf0);
+            if (kb + 1 < nkb) convert_block(kb + 1, buf1);
         }
 
         // ---------------- epilogue: TMEM -> registers -> global ----------------
-        asm volatile("bar.sync 1, 256;" ::: "memory");       // vec_s written by all converter threads
         mbar_wait(bar_tmem, 0);
         tc_fence_after();
         if (tc == 0) TSTAMP(3);
@@ -507,15 +493,15 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinearOp op
 __global__ void pack_tc_kernel(const float* __restrict__ W, int row0, int nrows, int K, const float* __restrict__ gamma,
                                uint8_t* __restrict__ out, int ntiles, int nkb) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (tile row, 8-element chunk)
-    const long long total = (long long)ntiles * nkb * BN * 8;
+    const long long total = (long long)ntiles * nkb * BN * 4;
     if (idx >= total) return;
-    const int chunk = (int)(idx & 7);
-    const int nl = (int)((idx >> 3) % BN);
-    const long long tkb = (idx >> 3) / BN;
+    const int chunk = (int)(idx & 3);
+    const int nl = (int)((idx >> 2) % BN);
+    const long long tkb = (idx >> 2) / BN;
     const int kb = (int)(tkb % nkb), t = (int)(tkb / nkb);
     const int n = t * BN + nl;
     uint8_t* tile = out + ((size_t)t * nkb + kb) * (2 * W_TILE);
-    const int byte = nl * 128 + ((chunk ^ (nl & 7)) << 4);
+    const int byte = sw64(nl, chunk * 8);
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -543,7 +529,7 @@ size_t tc_packed_bytes(int nrows, int K) {
 
 cudaError_t launch_pack_tc(const float* W, int row0, int nrows, int K, const float* gamma, void* out, cudaStream_t s) {
     const int ntiles = (nrows + tc::BN - 1) / tc::BN, nkb = (K + tc::BK - 1) / tc::BK;
-    const long long total = (long long)ntiles * nkb * tc::BN * 8;
+    const long long total = (long long)ntiles * nkb * tc::BN * 4;
     tc::pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, row0, nrows, K, gamma, (uint8_t*)out, ntiles, nkb);
     g_stats.launches++;
     return cudaGetLastError();
@@ -554,7 +540,7 @@ void tc_read_times(long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_time
 #endif
 
 bool linear_tc_eligible(const LinearOp& op) {
-    if (!op.Wp || (op.A2 && !op.Wp2)) return false;
+    if (!op.Wp || (op.A2 && !op.Wp2) || op.nbatch > 1) return false;
     if (op.M < 128 || op.N < 64) return false;
     if (op.ln_g && op.N != 256) return false;
     if (op.act == ACT_SIGMOID) return false;

@@ -67,7 +67,8 @@ class Engine:
             self.ctx = self.lib.mesm_create(byref(c), self.device.index or 0)
         if not self.ctx:
             raise RuntimeError("mesm_create failed: " + self.lib.mesm_last_error(None).decode())
-        self.lib.mesm_set_chunk_pairs(self.ctx, int(chunk_pairs))
+        self.chunk_pairs = int(chunk_pairs)
+        self.lib.mesm_set_chunk_pairs(self.ctx, self.chunk_pairs)
         self._ws = None
         self._keep = []          # tensors that must outlive the asynchronous call that uses them
 
@@ -94,7 +95,8 @@ class Engine:
             self._keep.clear()
 
     def set_chunk_pairs(self, n):
-        self.lib.mesm_set_chunk_pairs(self.ctx, int(n))
+        self.chunk_pairs = int(n)
+        self.lib.mesm_set_chunk_pairs(self.ctx, self.chunk_pairs)
         self._ws = None
 
     def _workspace(self, nbytes):
@@ -133,6 +135,8 @@ class Engine:
             o.update(memory=f(B, Lv, 256), memory_global=f(B, 256), hs=f(nl, B, nq, 256))
         inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index))
         out = MesmOutputs(**{k: _ptr(v) for k, v in o.items()})
+        # a video group is never split: the internal chunk must hold the largest group
+        self.lib.mesm_set_chunk_pairs(self.ctx, max(self.chunk_pairs, max(nc)))
         with torch.cuda.device(dev):
             need = self.lib.mesm_workspace_bytes(self.ctx, B, Lv, Lt, len(nc))
             ws = self._workspace(need)
