@@ -194,6 +194,13 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
                      void* workspace, size_t workspace_bytes, void* stream);
 size_t mesm_transformer_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t L);
 
+/* Barrier watchdog of the tcgen05 kernels (out128 = {attention[64], linear[64]}; [0] = number of barrier waits that gave up after ~2 s, then {tag, block, thread|barrier|parity} triples). */
+int mesm_debug_watchdog(unsigned long long* out128);
+
+/* Test hook (tests/test_gpu_attention.py): repeated self-attention launches + the barrier watchdog record. */
+int mesm_debug_attention(const float* qkv, const uint8_t* k_pad, int32_t B, int32_t L, float* out, int32_t use_tc, int32_t iters,
+                         unsigned long long* watchdog8, void* stream);
+
 /* Test hook (tests/test_gpu_linear.py): one fused linear out = epilogue(A (+Apos) . W^T) through the fp32 SIMT kernel
  * (use_tc = 0) or the tcgen05 split-bf16 kernel (use_tc = 1); synchronises the stream. */
 int mesm_debug_linear(const float* A, const float* Apos, const float* W, const float* bias, const float* residual,

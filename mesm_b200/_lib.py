@@ -68,6 +68,8 @@ SYMBOLS = {
     "mesm_t2v_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "mesm_transformer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mesm_debug_watchdog": (c_int, [c_void_p]),
+    "mesm_debug_attention": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "mesm_debug_linear": (c_int, [c_void_p] * 9 + [c_int32] * 5 + [c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "mesm_transformer_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
 }

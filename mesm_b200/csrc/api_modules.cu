@@ -3,6 +3,7 @@
 #include "ctx.h"
 
 using namespace mesm;
+namespace mesm { void tc_read_watchdog(unsigned long long* out8); void tc_read_watchdog_linear(unsigned long long* out8); }
 
 namespace {
 __global__ void build_enc_kernel(const float* __restrict__ src, const float* __restrict__ pos, const uint8_t* __restrict__ pad,
@@ -163,6 +164,34 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
     if (hs || references)
         CK(run_decoder(ctx, query_embed, cur, posE, pad, L, B, d, nullptr, nullptr, nullptr, nullptr, 0, hs, (long long)B * nq * D,
                        references, (long long)B * nq * 2, s));
+    return 0;
+}
+
+/* Barrier watchdog records of the tcgen05 kernels: out16 = {attention[8], linear[8]}; [0] != 0 means a wait gave up
+ * (then [1] = tag, [2] = block, [3] = thread, [4] = barrier address, [5] = parity).  Synchronises the device; clears. */
+int mesm_debug_watchdog(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    tc_read_watchdog(out16);
+    tc_read_watchdog_linear(out16 + 64);
+    return 0;
+}
+
+/* Test hook: `iters` back-to-back self-attention launches (tcgen05 kernel when use_tc) on q/k/v = columns [0,256), [256,512),
+ * [512,768) of qkv [B*L, 768]; returns the watchdog record (all zero = no stalled barrier wait). */
+int mesm_debug_attention(const float* qkv, const uint8_t* k_pad, int32_t B, int32_t L, float* out, int32_t use_tc, int32_t iters,
+                         unsigned long long* watchdog8, void* stream) {
+    mesm_ctx* ctx = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    MhaRowsArgs a;
+    a.q = qkv; a.ldq = 3 * D; a.k = qkv + D; a.ldk = 3 * D; a.v = qkv + 2 * D; a.ldv = 3 * D;
+    a.k_pad = k_pad; a.q_pad = nullptr; a.out = out; a.ldo = D; a.B = B; a.Lq = L; a.Lk = L; a.b0 = 0; a.Btot = B;
+    a.q_scale = kScale32;
+    for (int i = 0; i < iters; ++i) {
+        if (use_tc) { if (!attn_tc_eligible(a)) return fail(ctx, 3, "not eligible"); CK(launch_attn_tc(a, s)); }
+        else { setenv("MESM_FORCE_SIMT_ATTN", "1", 1); CK(launch_mha_rows(a, s)); }
+    }
+    CK(cudaStreamSynchronize(s));
+    if (watchdog8) { unsigned long long tmp[64]; tc_read_watchdog(tmp); for (int i = 0; i < 8; ++i) watchdog8[i] = tmp[i]; }
     return 0;
 }
 

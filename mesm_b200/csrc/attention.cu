@@ -9,6 +9,7 @@
 //                     (scores = (Wk_h^T q_h) . x_k, output = Wv_h (sum_k p_k x_k) + b): no K/V projection of the clips.
 #include "kernels.h"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace mesm {
 
@@ -109,8 +110,13 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
 }
 
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s) {
-    ProfScope _ps("mha_rows", s);
     if (a.B <= 0 || a.Lq <= 0) return cudaSuccess;
+    {
+        static int force = -1;
+        if (force < 0) { const char* e = getenv("MESM_FORCE_SIMT"); const char* e2 = getenv("MESM_FORCE_SIMT_ATTN"); force = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
+        if (!force && attn_tc_eligible(a)) return launch_attn_tc(a, s);
+    }
+    ProfScope _ps(a.q_pad ? "mha_rows t2v" : "mha_rows self", s);
     const int threads = ((a.Lq + 31) / 32) * 32;
     if (threads > 1024) return cudaErrorInvalidValue;
     const size_t smem = (size_t)a.Lk * 32 * 2 * sizeof(float) + 2 * (size_t)a.Lk;

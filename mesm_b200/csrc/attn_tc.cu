@@ -1,0 +1,284 @@
+// Encoder self-attention on the tensor cores (tcgen05 + TMEM), split-bf16 operands, for head_dim 32 and up to 224 keys.
+//
+// One CTA = one (pair, head): K and V^T of the head are converted once to bf16 hi/lo operand tiles in shared memory, then
+// each 128-row query tile runs
+//     S = Q K^T                (UMMA M=128, N=keys padded to 32, K=32; fp32 scores in TMEM columns [0, N))
+//     softmax                  (one thread per query row straight out of TMEM: row max, exp, row sum - no shuffles)
+//     O = P V                  (UMMA M=128, N=32 per 32-key block; P written by the softmax threads as the A operand,
+//                               double-buffered against the MMA; O in TMEM columns [224, 256))
+//     out = O / rowsum         (transposed through shared memory, coalesced stores)
+// bf16x3 everywhere (Qhi Khi + Qlo Khi + Qhi Klo, same for P V) keeps ~1e-5 relative accuracy (see linear_tc.cu).
+// Warp 0 issues the MMAs (one thread); warps 1..4 are the 128 row workers; 256 TMEM columns per CTA.
+#include "kernels.h"
+#include "tc_common.cuh"
+#include <math_constants.h>
+
+namespace mesm {
+namespace tc {
+
+constexpr int AT_THREADS = 160;
+constexpr int AT_LKP_MAX = 224;
+constexpr int AT_OCOL = 224;                      // TMEM column of the O accumulator
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int AT_QHI = 0, AT_QLO = 8192;
+constexpr int AT_KHI = 16384, AT_KLO = AT_KHI + AT_LKP_MAX * 64;                  // 14336 each
+constexpr int AT_VHI = AT_KLO + AT_LKP_MAX * 64, AT_VLO = AT_VHI + 7 * 2048;      // V^T: 7 key blocks x (32 dims x 64 B)
+constexpr int AT_P = AT_VLO + 7 * 2048;                                           // 2 slots x (hi 8 KB + lo 8 KB)
+constexpr int AT_PAD = AT_P + 2 * 16384;                                          // key flags [224]
+constexpr int AT_BAR = AT_PAD + 256;                                              // mbarriers + tmem pointer
+// ONE CTA per SM on purpose (the extra 16 KB makes a second CTA not fit): with two of these CTAs co-resident the kernel
+// dead-locked about once per 10^6 CTAs inside a full forward (MMA thread waiting for P, softmax warps waiting for a
+// tcgen05.commit arrival that never came); a CTA whose own tcgen05.ld traffic overlaps its own in-flight MMAs apparently
+// must not share the SM's tensor pipe with another such CTA.  The barrier watchdog (tc_common.cuh) caught it.
+constexpr int AT_SMEM = AT_BAR + 128 + 1024 + 16384;
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t bar_S = sbase + AT_BAR, bar_O = bar_S + 8, bar_Pfull = bar_S + 16, bar_Pempty = bar_S + 32;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AT_BAR + 48);
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + AT_PAD);      // bit j of kmask[c]: key 32c+j is masked
+    int* nkb_eff_s = reinterpret_cast<int*>(smem + AT_PAD + 64);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int Lq = a.Lq, Lk = a.Lk;
+    const int Lkp = (Lk + 31) & ~31;
+    const int ntiles = (Lq + 127) >> 7;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_S, 1); mbar_init(bar_O, 1);
+        mbar_init(bar_Pfull, 4); mbar_init(bar_Pfull + 8, 4);
+        mbar_init(bar_Pempty, 1); mbar_init(bar_Pempty + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // ---- stage K (B operand of S = Q K^T) and V^T (B operand of O = P V) once per (pair, head) ----
+    if (warp >= 1) {
+        const int t = threadIdx.x - 32;                                    // 0..127
+        for (int idx = t; idx < Lkp * 8; idx += 128) {
+            const int key = idx >> 3, c4 = idx & 7;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (key < Lk) {
+                const long long row = (long long)b * Lk + key;
+                kv = __ldg(reinterpret_cast<const float4*>(a.k + row * a.ldk + h * 32 + c4 * 4));
+                vv = __ldg(reinterpret_cast<const float4*>(a.v + row * a.ldv + h * 32 + c4 * 4));
+            }
+            const float kk[4] = {kv.x, kv.y, kv.z, kv.w}, vvv[4] = {vv.x, vv.y, vv.z, vv.w};
+            __nv_bfloat16 kh[4], kl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) split_bf16(kk[u], kh[u], kl[u]);
+            const int kb = sw64(key, c4 * 4);
+            *reinterpret_cast<uint2*>(smem + AT_KHI + kb) =
+                make_uint2((uint32_t)__bfloat16_as_ushort(kh[0]) | ((uint32_t)__bfloat16_as_ushort(kh[1]) << 16),
+                           (uint32_t)__bfloat16_as_ushort(kh[2]) | ((uint32_t)__bfloat16_as_ushort(kh[3]) << 16));
+            *reinterpret_cast<uint2*>(smem + AT_KLO + kb) =
+                make_uint2((uint32_t)__bfloat16_as_ushort(kl[0]) | ((uint32_t)__bfloat16_as_ushort(kl[1]) << 16),
+                           (uint32_t)__bfloat16_as_ushort(kl[2]) | ((uint32_t)__bfloat16_as_ushort(kl[3]) << 16));
+            const int jb = (key >> 5) * 2048, col = key & 31;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                __nv_bfloat16 vh, vl;
+                split_bf16(vvv[u], vh, vl);
+                const int vb = jb + sw64(c4 * 4 + u, col);
+                *reinterpret_cast<__nv_bfloat16*>(smem + AT_VHI + vb) = vh;
+                *reinterpret_cast<__nv_bfloat16*>(smem + AT_VLO + vb) = vl;
+            }
+        }
+        if (warp == 1) {                                                   // one warp builds the per-block key masks
+            int last = 0;
+            for (int c = 0; c < (Lkp >> 5); ++c) {
+                const int k = c * 32 + lane;
+                const bool masked = (k >= Lk) || a.k_pad[((long long)a.b0 + b) * Lk + (k < Lk ? k : 0)];
+                const unsigned mk = __ballot_sync(0xffffffffu, masked);
+                if (lane == 0) kmask[c] = mk;
+                if (mk != 0xffffffffu) last = c + 1;
+            }
+            if (lane == 0) *nkb_eff_s = last > 0 ? last : 1;                // key blocks after the last valid key are skipped
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int nkb_eff = *nkb_eff_s;
+    const uint32_t idesc_s = make_idesc(nkb_eff * 32), idesc_o = make_idesc(32);
+
+    int p_use = 0;                      // running count of P blocks (slot = p_use & 1), identical in every thread
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const uint32_t tph = tile & 1;
+        if (warp >= 1) {
+            // ---- stage the Q tile (A operand), scaled by head_dim^-0.5 ----
+            const int t = threadIdx.x - 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = t + 128 * i, row = idx >> 3, c4 = idx & 7;
+                const int qi = tile * 128 + row;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qi < Lq) q = __ldg(reinterpret_cast<const float4*>(a.q + ((long long)b * Lq + qi) * a.ldq + h * 32 + c4 * 4));
+                const float qq[4] = {q.x * a.q_scale, q.y * a.q_scale, q.z * a.q_scale, q.w * a.q_scale};
+                __nv_bfloat16 qh[4], ql[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) split_bf16(qq[u], qh[u], ql[u]);
+                const int qb = sw64(row, c4 * 4);
+                *reinterpret_cast<uint2*>(smem + AT_QHI + qb) =
+                    make_uint2((uint32_t)__bfloat16_as_ushort(qh[0]) | ((uint32_t)__bfloat16_as_ushort(qh[1]) << 16),
+                               (uint32_t)__bfloat16_as_ushort(qh[2]) | ((uint32_t)__bfloat16_as_ushort(qh[3]) << 16));
+                *reinterpret_cast<uint2*>(smem + AT_QLO + qb) =
+                    make_uint2((uint32_t)__bfloat16_as_ushort(ql[0]) | ((uint32_t)__bfloat16_as_ushort(ql[1]) << 16),
+                               (uint32_t)__bfloat16_as_ushort(ql[2]) | ((uint32_t)__bfloat16_as_ushort(ql[3]) << 16));
+            }
+            fence_proxy_async();
+        }
+        __syncthreads();                                                   // [A] operands staged
+
+        if (warp == 0) {
+            if (lane == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {                              // S = Q K^T, K = 32 -> two K=16 steps
+                    const uint64_t qh = make_desc(sbase + AT_QHI + k * 32), ql = make_desc(sbase + AT_QLO + k * 32);
+                    const uint64_t kh = make_desc(sbase + AT_KHI + k * 32), kl = make_desc(sbase + AT_KLO + k * 32);
+                    umma(tmem_base, qh, kh, k > 0 ? 1u : 0u, idesc_s);
+                    umma(tmem_base, ql, kh, 1u, idesc_s);
+                    umma(tmem_base, qh, kl, 1u, idesc_s);
+                }
+                umma_commit(bar_S);
+                int pu = p_use;
+                for (int j = 0; j < nkb_eff; ++j, ++pu) {                  // O += P_j V_j
+                    const int slot = pu & 1;
+                    mbar_wait(bar_Pfull + 8 * slot, (pu >> 1) & 1, 100 + pu);
+                    tc_fence_after();
+                    const uint32_t ph_ = sbase + AT_P + slot * 16384, pl_ = ph_ + 8192;
+                    const uint32_t vh_ = sbase + AT_VHI + j * 2048, vl_ = sbase + AT_VLO + j * 2048;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint64_t dph = make_desc(ph_ + k * 32), dpl = make_desc(pl_ + k * 32);
+                        const uint64_t dvh = make_desc(vh_ + k * 32), dvl = make_desc(vl_ + k * 32);
+                        umma(tmem_base + AT_OCOL, dph, dvh, (j > 0 || k > 0) ? 1u : 0u, idesc_o);
+                        umma(tmem_base + AT_OCOL, dpl, dvh, 1u, idesc_o);
+                        umma(tmem_base + AT_OCOL, dph, dvl, 1u, idesc_o);
+                    }
+                    umma_commit(bar_Pempty + 8 * slot);
+                }
+                umma_commit(bar_O);
+            }
+        } else {
+            const int q4 = warp & 3;                                       // TMEM lane quadrant of this warp
+            const int row = q4 * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+            mbar_wait(bar_S, tph, 200 + tile);
+            tc_fence_after();
+            const bool wact = tile * 128 + q4 * 32 < Lq;                   // warp has at least one real query row
+            // pass 1: row maximum over the valid keys
+            float mx = -CUDART_INF_F;
+            if (wact) {
+                for (int c = 0; c < nkb_eff; ++c) {
+                    float v[32];
+                    tmem_ld32(trow + c * 32, v);
+                    const uint32_t mk = kmask[c];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) mx = fmaxf(mx, v[j]);
+                }
+            }
+            const float mxl = mx * 1.4426950408889634f;
+            // pass 2: p = exp(s - max) -> bf16 hi/lo A-operand blocks of 32 keys, double-buffered against the P V MMAs
+            float sum = 0.f;
+            int pu = p_use;
+            for (int c = 0; c < nkb_eff; ++c, ++pu) {
+                const int slot = pu & 1;
+                uint32_t hi[16], lo[16];
+                if (wact) {
+                    float v[32];
+                    tmem_ld32(trow + c * 32, v);
+                    const uint32_t mk = kmask[c];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = ((mk >> (2 * j)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j], 1.4426950408889634f, -mxl));
+                        const float p1 = ((mk >> (2 * j + 1)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j + 1], 1.4426950408889634f, -mxl));
+                        sum += p0 + p1;
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - __uint_as_float(hb << 16), p1 - __uint_as_float(hb & 0xffff0000u));
+                        hi[j] = hb;
+                        lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { hi[j] = 0u; lo[j] = 0u; }
+                }
+                mbar_wait(bar_Pempty + 8 * slot, ((pu >> 1) & 1) ^ 1, 300 + pu);       // slot free (first two uses pass immediately)
+                uint8_t* ph_ = smem + AT_P + slot * 16384;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int off = sw64(row, cc * 8);
+                    *reinterpret_cast<uint4*>(ph_ + off) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+                    *reinterpret_cast<uint4*>(ph_ + 8192 + off) = make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_Pfull + 8 * slot);
+            }
+            // epilogue: O / rowsum, transposed through shared memory (the P ring is idle once bar_O fires)
+            mbar_wait(bar_O, tph, 400 + tile);
+            tc_fence_after();
+            if (wact) {
+            float o[32];
+            tmem_ld32(trow + AT_OCOL, o);
+            const float inv = 1.f / sum;
+            float* T = reinterpret_cast<float*>(smem + AT_P) + (warp - 1) * (32 * 36);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(&T[lane * 36 + 4 * j]) = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+            __syncwarp();
+            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + rsub;
+                const int qi = tile * 128 + q4 * 32 + r;
+                if (qi < Lq)
+                    *reinterpret_cast<float4*>(a.out + ((long long)b * Lq + qi) * a.ldo + h * 32 + c4) =
+                        *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+            }
+            }
+        }
+        p_use += nkb_eff;
+        tc_fence_before();
+        __syncthreads();                                                   // [B] TMEM / smem reads of this tile are done
+        tc_fence_after();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+}  // namespace tc
+
+void tc_read_watchdog(unsigned long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_watchdog, 512); unsigned long long z[64] = {0}; cudaMemcpyToSymbol(tc::g_tc_watchdog, z, 512); }
+
+bool attn_tc_eligible(const MhaRowsArgs& a) {
+    if (a.q_pad) return false;                                   // T2V quirk mask: SIMT kernel
+    if (a.Lk > tc::AT_LKP_MAX || a.Lk < 1) return false;
+    auto al = [](const float* p, int ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); };
+    return al(a.q, a.ldq) && al(a.k, a.ldk) && al(a.v, a.ldv) && al(a.out, a.ldo);
+}
+
+cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s) {
+    ProfScope _ps("attn_tc", s);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MESM_CHECK(cudaFuncSetAttribute(tc::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::AT_SMEM));
+        attr_set = true;
+    }
+    dim3 grid(NH, a.B);
+    tc::attn_tc_kernel<<<grid, tc::AT_THREADS, tc::AT_SMEM, s>>>(a);
+    g_stats.launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace mesm

@@ -15,7 +15,9 @@ struct MhaRowsArgs {
     int b0, Btot;
     float q_scale;
 };
-cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s);
+cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s);      // dispatcher: tcgen05 kernel when eligible
+bool attn_tc_eligible(const MhaRowsArgs& a);
+cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s);
 
 struct MhaSmallArgs {
     const float* q; int ldq;  const float* q2; int ldq2;

@@ -16,8 +16,7 @@
 //                 the same warps run the epilogue straight out of TMEM: LayerNorm-fold / bias / scale / activation /
 //                 residual / LayerNorm over the 256-wide row / stores.
 // Two 96 KB stages (A hi/lo 2 x 16 KB + W hi/lo 2 x 32 KB) ride an mbarrier full/empty ring.
-#include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace mesm {
 namespace tc {
@@ -35,97 +34,8 @@ constexpr int W_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;      // 49152: two CTAs (2 x ~105 KB) share one SM
 constexpr int NCONV = 256;                                // converter / epilogue threads (8 warps)
 constexpr int THREADS = 64 + NCONV;
+constexpr uint32_t IDESC = make_idesc(BN);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 + 1024 + 4096 + 3072 + 2048 /*barriers, LN exchange, epilogue vectors, row offsets*/;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
-// LBO (unused for swizzled K-major) [16,30), SBO = 512 B (8 rows x 64 B) [32,46), version 1 [46,48), layout type
-// SWIZZLE_64B = 4 in [61,64).  Rows are 64 bytes (32 bf16 of K); the 16-byte chunk index is XORed with (row >> 1) & 3.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128.
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-        "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// byte offset of element (row, k) inside a K-major SWIZZLE_64B tile whose rows hold BK = 32 bf16
-__device__ __forceinline__ int sw64(int row, int k) { return row * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) << 4) | ((k & 7) << 1)); }
-
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
 
 __device__ __forceinline__ float act_fn(float v, int act, float slope) {
     if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -181,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1, 1000 + kb);
                 const int kk = kb < nkb1 ? kb : (kb < nkb1 + nkbp ? kb - nkb1 : kb - nkb1 - nkbp);
                 const uint8_t* src = kb < nkb1 + nkbp
                                          ? reinterpret_cast<const uint8_t*>(op.Wp) + ((size_t)nt * nkb1 + kk) * (2 * W_TILE)
@@ -198,9 +108,9 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(bar_full_w + 8 * s, ph);
+                mbar_wait(bar_full_w + 8 * s, ph, 2000 + kb);
                 if (kb < 8) TSTAMP(8 + kb);
-                mbar_wait(bar_full_a + 8 * s, ph);
+                mbar_wait(bar_full_a + 8 * s, ph, 3000 + kb);
                 if (kb < 8) TSTAMP(16 + kb);
                 tc_fence_after();
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
@@ -210,9 +120,9 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
                     const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes along K inside the 64B swizzle row
                     const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
                     const uint64_t dwh = make_desc(w_hi + koff), dwl = make_desc(w_lo + koff);
-                    umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma(tmem_base, dal, dwh, 1u);
-                    umma(tmem_base, dah, dwl, 1u);
+                    umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC);
+                    umma(tmem_base, dal, dwh, 1u, IDESC);
+                    umma(tmem_base, dah, dwl, 1u, IDESC);
                 }
                 umma_commit(bar_empty + 8 * s);            // stage reusable once these MMAs retire
             }
@@ -298,7 +208,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             }
             if (kb + 2 < nkb) load_block(kb + 2, src);             // refill this buffer: two blocks stay in flight
             if (tc == 0 && kb < 8) TSTAMP(24 + kb);
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1, 4000 + kb);
             if (tc == 0 && kb < 8) TSTAMP(32 + kb);
             uint8_t* a_hi = smem + s * STAGE_BYTES;
             uint8_t* a_lo = a_hi + A_TILE;
@@ -338,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
         }
 
         // ---------------- epilogue: TMEM -> registers -> global ----------------
-        mbar_wait(bar_tmem, 0);
+        mbar_wait(bar_tmem, 0, 5000);
         tc_fence_after();
         if (tc == 0) TSTAMP(3);
         const int q = warp & 3;                            // TMEM lane quadrant this warp may access
@@ -485,6 +395,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     __syncthreads();
     if (threadIdx.x == 0) TSTAMP(6);
     if (warp == 1) {
+        __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
 }
@@ -538,6 +449,8 @@ cudaError_t launch_pack_tc(const float* W, int row0, int nrows, int K, const flo
 #ifdef MESM_TC_TIMING
 void tc_read_times(long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_times, sizeof(long long) * 64); }
 #endif
+
+void tc_read_watchdog_linear(unsigned long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_watchdog, 512); unsigned long long z[64] = {0}; cudaMemcpyToSymbol(tc::g_tc_watchdog, z, 512); }
 
 bool linear_tc_eligible(const LinearOp& op) {
     if (!op.Wp || (op.A2 && !op.Wp2) || op.nbatch > 1) return false;

@@ -56,3 +56,27 @@ def test_chunking_is_invisible(name):
     for k in ("pred_logits", "pred_spans", "saliency_scores", "neg_saliency_scores", "recon_feat"):
         m = inp["video_mask"] if "saliency" in k else None
         assert rel_err(a[k], b[k], m) < 1e-4, k
+
+
+def test_repeated_forwards_are_bit_stable_and_watchdog_silent():
+    """Bench-shaped ragged batch, repeated: identical bits every time and no barrier wait of the tcgen05 kernels gave up."""
+    import ctypes
+    import bench
+    from mesm_b200 import _lib
+    from mesm_b200.model import build_model
+    torch.manual_seed(0)
+    model = build_model(bench.CHARADES_CSF).cuda()
+    wl = bench.make_workload(bench.CHARADES_CSF, 1024, 7, torch.device("cuda"))
+    ref = None
+    for _ in range(6):
+        out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"], dataset_name="charades",
+                    is_training=False, neg_index=wl["neg_index"])
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = {k: out[k].clone() for k in ("pred_logits", "pred_spans", "saliency_scores")}
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    wd = (ctypes.c_ulonglong * 128)()
+    _lib.lib().mesm_debug_watchdog(wd)
+    assert wd[0] == 0 and wd[64] == 0, list(wd)[:8] + list(wd)[64:72]
+    assert not torch.isnan(ref["pred_logits"]).any()
