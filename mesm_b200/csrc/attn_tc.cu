@@ -1,14 +1,21 @@
-// Encoder self-attention on the tensor cores (tcgen05 + TMEM), split-bf16 operands, for head_dim 32 and up to 224 keys.
+// Multi-head attention (head_dim 32, up to 224 keys) on the tensor cores: tcgen05 + TMEM, split-bf16 operands.
+// Serves the encoder self-attention (keys = Lv+1 clips) and the T2V cross-attention (keys = <= 33 words, with the
+// reference's attn_mask quirk) of the MESM path.
 //
-// One CTA = one (pair, head): K and V^T of the head are converted once to bf16 hi/lo operand tiles in shared memory, then
-// each 128-row query tile runs
-//     S = Q K^T                (UMMA M=128, N=keys padded to 32, K=32; fp32 scores in TMEM columns [0, N))
-//     softmax                  (one thread per query row straight out of TMEM: row max, exp, row sum - no shuffles)
-//     O = P V                  (UMMA M=128, N=32 per 32-key block; P written by the softmax threads as the A operand,
-//                               double-buffered against the MMA; O in TMEM columns [224, 256))
+// One CTA = one (pair, head), one CTA per SM.  K and V^T of the head are converted once to bf16 hi/lo operand tiles in
+// shared memory; then TWO 128-row query tiles are in flight at a time (TMEM: 2 x [S 224 cols | O 32 cols] = 512 columns):
+//     S = Q K^T                (UMMA M=128, N = valid key blocks x 32, K = 32; fp32 scores in TMEM)
+//     softmax                  (one thread per query row straight out of TMEM: row max, exp2, row sum - no shuffles)
+//     O = P V                  (UMMA M=128, N=32 per 32-key block; the softmax threads write P as the A operand into a
+//                               2-slot ring that the MMA thread drains, so exp and MMA overlap)
 //     out = O / rowsum         (transposed through shared memory, coalesced stores)
 // bf16x3 everywhere (Qhi Khi + Qlo Khi + Qhi Klo, same for P V) keeps ~1e-5 relative accuracy (see linear_tc.cu).
-// Warp 0 issues the MMAs (one thread); warps 1..4 are the 128 row workers; 256 TMEM columns per CTA.
+// Warp 0 = MMA issuer (one thread); warps 1..4 own query tile 0, warps 5..8 query tile 1 of the current tile pair.
+//
+// Why one CTA per SM: an earlier 1-tile / 2-CTAs-per-SM version of this kernel dead-locked about once per 10^6 CTAs
+// inside a full forward (MMA thread waiting for P, softmax warps waiting for a tcgen05.commit arrival that never came)
+// and never with a single resident CTA; the barrier watchdog in tc_common.cuh caught it.  Two tiles per CTA recover the
+// overlap without co-resident CTAs.
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <math_constants.h>
@@ -16,87 +23,100 @@
 namespace mesm {
 namespace tc {
 
-constexpr int AT_THREADS = 160;
+constexpr int AT_THREADS = 32 + 256;
 constexpr int AT_LKP_MAX = 224;
-constexpr int AT_OCOL = 224;                      // TMEM column of the O accumulator
+constexpr int AT_OCOL = 224;                      // O accumulator column inside a tile's 256-column TMEM half
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr int AT_QHI = 0, AT_QLO = 8192;
-constexpr int AT_KHI = 16384, AT_KLO = AT_KHI + AT_LKP_MAX * 64;                  // 14336 each
+constexpr int AT_Q = 0;                                                           // [2 tiles][hi 8 KB | lo 8 KB]
+constexpr int AT_KHI = 32768, AT_KLO = AT_KHI + AT_LKP_MAX * 64;                  // 14336 each
 constexpr int AT_VHI = AT_KLO + AT_LKP_MAX * 64, AT_VLO = AT_VHI + 7 * 2048;      // V^T: 7 key blocks x (32 dims x 64 B)
-constexpr int AT_P = AT_VLO + 7 * 2048;                                           // 2 slots x (hi 8 KB + lo 8 KB)
-constexpr int AT_PAD = AT_P + 2 * 16384;                                          // key flags [224]
-constexpr int AT_BAR = AT_PAD + 256;                                              // mbarriers + tmem pointer
-// ONE CTA per SM on purpose (the extra 16 KB makes a second CTA not fit): with two of these CTAs co-resident the kernel
-// dead-locked about once per 10^6 CTAs inside a full forward (MMA thread waiting for P, softmax warps waiting for a
-// tcgen05.commit arrival that never came); a CTA whose own tcgen05.ld traffic overlaps its own in-flight MMAs apparently
-// must not share the SM's tensor pipe with another such CTA.  The barrier watchdog (tc_common.cuh) caught it.
-constexpr int AT_SMEM = AT_BAR + 128 + 1024 + 16384;
+constexpr int AT_P = AT_VLO + 7 * 2048;                                           // [2 tiles][2 slots][hi 8 KB | lo 8 KB]
+constexpr int AT_MASK = AT_P + 4 * 16384;                                         // key masks: own[8], partner[8], nkb_eff
+constexpr int AT_BAR = AT_MASK + 128;                                             // 12 mbarriers + tmem pointer
+constexpr int AT_SMEM = AT_BAR + 128 + 1024;
 
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
-    const uint32_t bar_S = sbase + AT_BAR, bar_O = bar_S + 8, bar_Pfull = bar_S + 16, bar_Pempty = bar_S + 32;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AT_BAR + 48);
-    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + AT_PAD);      // bit j of kmask[c]: key 32c+j is masked
-    int* nkb_eff_s = reinterpret_cast<int*>(smem + AT_PAD + 64);
+    // barriers (8 bytes each): S[t] @0,8 ; O[t] @16,24 ; Pfull[t][slot] @32+16t+8slot ; Pempty[t][slot] @64+16t+8slot
+    const uint32_t bars = sbase + AT_BAR;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + AT_BAR + 96);
+    uint32_t* kmask_own = reinterpret_cast<uint32_t*>(smem + AT_MASK);
+    uint32_t* kmask_oth = kmask_own + 8;
+    int* nkb_eff_s = reinterpret_cast<int*>(kmask_own + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
+    const int bg = a.b0 + b;                                            // global pair index (masks are batch-global)
+    const bool quirk = a.q_pad != nullptr;
+    const int bp = quirk ? (int)(((long long)bg * NH + h) % a.Btot) : bg;   // T2V attn_mask quirk partner (see attention.cu)
     const int Lq = a.Lq, Lk = a.Lk;
     const int Lkp = (Lk + 31) & ~31;
     const int ntiles = (Lq + 127) >> 7;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_S, 1); mbar_init(bar_O, 1);
-        mbar_init(bar_Pfull, 4); mbar_init(bar_Pfull + 8, 4);
-        mbar_init(bar_Pempty, 1); mbar_init(bar_Pempty + 8, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);                     // S[0..1], O[0..1]
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 32 + 8 * i, 4);                // Pfull: 4 softmax warps per tile
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 64 + 8 * i, 1);                // Pempty: tcgen05.commit
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // ---- stage K (B operand of S = Q K^T) and V^T (B operand of O = P V) once per (pair, head) ----
     if (warp >= 1) {
-        const int t = threadIdx.x - 32;                                    // 0..127
-        for (int idx = t; idx < Lkp * 8; idx += 128) {
-            const int key = idx >> 3, c4 = idx & 7;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (key < Lk) {
-                const long long row = (long long)b * Lk + key;
-                kv = __ldg(reinterpret_cast<const float4*>(a.k + row * a.ldk + h * 32 + c4 * 4));
-                vv = __ldg(reinterpret_cast<const float4*>(a.v + row * a.ldv + h * 32 + c4 * 4));
-            }
-            const float kk[4] = {kv.x, kv.y, kv.z, kv.w}, vvv[4] = {vv.x, vv.y, vv.z, vv.w};
-            __nv_bfloat16 kh[4], kl[4];
+        const int t = threadIdx.x - 32;                                    // 0..255
+        const int total = Lkp * 8;
+        for (int base = t; base < total; base += 256 * 4) {
+            float4 kv[4], vv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) split_bf16(kk[u], kh[u], kl[u]);
-            const int kb = sw64(key, c4 * 4);
-            *reinterpret_cast<uint2*>(smem + AT_KHI + kb) =
-                make_uint2((uint32_t)__bfloat16_as_ushort(kh[0]) | ((uint32_t)__bfloat16_as_ushort(kh[1]) << 16),
-                           (uint32_t)__bfloat16_as_ushort(kh[2]) | ((uint32_t)__bfloat16_as_ushort(kh[3]) << 16));
-            *reinterpret_cast<uint2*>(smem + AT_KLO + kb) =
-                make_uint2((uint32_t)__bfloat16_as_ushort(kl[0]) | ((uint32_t)__bfloat16_as_ushort(kl[1]) << 16),
-                           (uint32_t)__bfloat16_as_ushort(kl[2]) | ((uint32_t)__bfloat16_as_ushort(kl[3]) << 16));
-            const int jb = (key >> 5) * 2048, col = key & 31;
+            for (int u = 0; u < 4; ++u) {                                  // issue the batch of loads first
+                const int idx = base + u * 256, key = idx >> 3, c4 = idx & 7;
+                kv[u] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u] = kv[u];
+                if (idx < total && key < Lk) {
+                    const long long row = (long long)b * Lk + key;
+                    kv[u] = __ldg(reinterpret_cast<const float4*>(a.k + row * a.ldk + h * 32 + c4 * 4));
+                    vv[u] = __ldg(reinterpret_cast<const float4*>(a.v + row * a.ldv + h * 32 + c4 * 4));
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                __nv_bfloat16 vh, vl;
-                split_bf16(vvv[u], vh, vl);
-                const int vb = jb + sw64(c4 * 4 + u, col);
-                *reinterpret_cast<__nv_bfloat16*>(smem + AT_VHI + vb) = vh;
-                *reinterpret_cast<__nv_bfloat16*>(smem + AT_VLO + vb) = vl;
+                const int idx = base + u * 256, key = idx >> 3, c4 = idx & 7;
+                if (idx >= total) break;
+                const float kk[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w}, vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                __nv_bfloat16 kh[4], kl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_bf16(kk[e], kh[e], kl[e]);
+                const int kb = sw64(key, c4 * 4);
+                *reinterpret_cast<uint2*>(smem + AT_KHI + kb) =
+                    make_uint2((uint32_t)__bfloat16_as_ushort(kh[0]) | ((uint32_t)__bfloat16_as_ushort(kh[1]) << 16),
+                               (uint32_t)__bfloat16_as_ushort(kh[2]) | ((uint32_t)__bfloat16_as_ushort(kh[3]) << 16));
+                *reinterpret_cast<uint2*>(smem + AT_KLO + kb) =
+                    make_uint2((uint32_t)__bfloat16_as_ushort(kl[0]) | ((uint32_t)__bfloat16_as_ushort(kl[1]) << 16),
+                               (uint32_t)__bfloat16_as_ushort(kl[2]) | ((uint32_t)__bfloat16_as_ushort(kl[3]) << 16));
+                const int jb = (key >> 5) * 2048, col = key & 31;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat16 vh, vl;
+                    split_bf16(vvv[e], vh, vl);
+                    const int vb = jb + sw64(c4 * 4 + e, col);
+                    *reinterpret_cast<__nv_bfloat16*>(smem + AT_VHI + vb) = vh;
+                    *reinterpret_cast<__nv_bfloat16*>(smem + AT_VLO + vb) = vl;
+                }
             }
         }
         if (warp == 1) {                                                   // one warp builds the per-block key masks
             int last = 0;
             for (int c = 0; c < (Lkp >> 5); ++c) {
                 const int k = c * 32 + lane;
-                const bool masked = (k >= Lk) || a.k_pad[((long long)a.b0 + b) * Lk + (k < Lk ? k : 0)];
-                const unsigned mk = __ballot_sync(0xffffffffu, masked);
-                if (lane == 0) kmask[c] = mk;
-                if (mk != 0xffffffffu) last = c + 1;
+                const int kc = k < Lk ? k : 0;
+                const bool m_own = (k >= Lk) || a.k_pad[(long long)bg * Lk + kc];
+                const bool m_oth = quirk && ((k >= Lk) || a.k_pad[(long long)bp * Lk + kc]);
+                const unsigned mo = __ballot_sync(0xffffffffu, m_own), mt = __ballot_sync(0xffffffffu, m_oth);
+                if (lane == 0) { kmask_own[c] = mo; kmask_oth[c] = mt; }
+                if (mo != 0xffffffffu) last = c + 1;
             }
             if (lane == 0) *nkb_eff_s = last > 0 ? last : 1;                // key blocks after the last valid key are skipped
         }
@@ -108,12 +128,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
     const int nkb_eff = *nkb_eff_s;
     const uint32_t idesc_s = make_idesc(nkb_eff * 32), idesc_o = make_idesc(32);
 
-    int p_use = 0;                      // running count of P blocks (slot = p_use & 1), identical in every thread
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const uint32_t tph = tile & 1;
-        if (warp >= 1) {
+    const int wt = warp >= 5 ? 1 : 0;                   // which tile of the pair this worker warp serves
+    int p_use = 0;                                      // P blocks produced so far per tile (slot = p_use & 1)
+    int pair_i = 0;                                     // tile pairs done (parity of the S / O barriers)
+    for (int tp = 0; tp < ntiles; tp += 2, ++pair_i) {
+        const uint32_t tph = pair_i & 1;
+        const int nact = (tp + 1 < ntiles) ? 2 : 1;     // tiles active in this pair
+        const int tile = tp + wt;
+        const bool gact = warp >= 1 && wt < nact;       // this worker group has a tile
+        if (gact) {
             // ---- stage the Q tile (A operand), scaled by head_dim^-0.5 ----
-            const int t = threadIdx.x - 32;
+            const int t = (threadIdx.x - 32) & 127;
+            uint8_t* qs = smem + AT_Q + wt * 16384;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int idx = t + 128 * i, row = idx >> 3, c4 = idx & 7;
@@ -125,62 +151,70 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
 #pragma unroll
                 for (int u = 0; u < 4; ++u) split_bf16(qq[u], qh[u], ql[u]);
                 const int qb = sw64(row, c4 * 4);
-                *reinterpret_cast<uint2*>(smem + AT_QHI + qb) =
+                *reinterpret_cast<uint2*>(qs + qb) =
                     make_uint2((uint32_t)__bfloat16_as_ushort(qh[0]) | ((uint32_t)__bfloat16_as_ushort(qh[1]) << 16),
                                (uint32_t)__bfloat16_as_ushort(qh[2]) | ((uint32_t)__bfloat16_as_ushort(qh[3]) << 16));
-                *reinterpret_cast<uint2*>(smem + AT_QLO + qb) =
+                *reinterpret_cast<uint2*>(qs + 8192 + qb) =
                     make_uint2((uint32_t)__bfloat16_as_ushort(ql[0]) | ((uint32_t)__bfloat16_as_ushort(ql[1]) << 16),
                                (uint32_t)__bfloat16_as_ushort(ql[2]) | ((uint32_t)__bfloat16_as_ushort(ql[3]) << 16));
             }
-            fence_proxy_async();
         }
+        fence_proxy_async();
         __syncthreads();                                                   // [A] operands staged
 
         if (warp == 0) {
             if (lane == 0) {
                 tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {                              // S = Q K^T, K = 32 -> two K=16 steps
-                    const uint64_t qh = make_desc(sbase + AT_QHI + k * 32), ql = make_desc(sbase + AT_QLO + k * 32);
-                    const uint64_t kh = make_desc(sbase + AT_KHI + k * 32), kl = make_desc(sbase + AT_KLO + k * 32);
-                    umma(tmem_base, qh, kh, k > 0 ? 1u : 0u, idesc_s);
-                    umma(tmem_base, ql, kh, 1u, idesc_s);
-                    umma(tmem_base, qh, kl, 1u, idesc_s);
-                }
-                umma_commit(bar_S);
-                int pu = p_use;
-                for (int j = 0; j < nkb_eff; ++j, ++pu) {                  // O += P_j V_j
-                    const int slot = pu & 1;
-                    mbar_wait(bar_Pfull + 8 * slot, (pu >> 1) & 1, 100 + pu);
-                    tc_fence_after();
-                    const uint32_t ph_ = sbase + AT_P + slot * 16384, pl_ = ph_ + 8192;
-                    const uint32_t vh_ = sbase + AT_VHI + j * 2048, vl_ = sbase + AT_VLO + j * 2048;
+                for (int t2 = 0; t2 < nact; ++t2) {                        // S_t = Q_t K^T, K = 32 -> two K=16 steps
+                    const uint32_t qb = sbase + AT_Q + t2 * 16384;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const uint64_t dph = make_desc(ph_ + k * 32), dpl = make_desc(pl_ + k * 32);
-                        const uint64_t dvh = make_desc(vh_ + k * 32), dvl = make_desc(vl_ + k * 32);
-                        umma(tmem_base + AT_OCOL, dph, dvh, (j > 0 || k > 0) ? 1u : 0u, idesc_o);
-                        umma(tmem_base + AT_OCOL, dpl, dvh, 1u, idesc_o);
-                        umma(tmem_base + AT_OCOL, dph, dvl, 1u, idesc_o);
+                        const uint64_t qh = make_desc(qb + k * 32), ql = make_desc(qb + 8192 + k * 32);
+                        const uint64_t kh = make_desc(sbase + AT_KHI + k * 32), kl = make_desc(sbase + AT_KLO + k * 32);
+                        umma(tmem_base + t2 * 256, qh, kh, k > 0 ? 1u : 0u, idesc_s);
+                        umma(tmem_base + t2 * 256, ql, kh, 1u, idesc_s);
+                        umma(tmem_base + t2 * 256, qh, kl, 1u, idesc_s);
                     }
-                    umma_commit(bar_Pempty + 8 * slot);
+                    umma_commit(bars + 8 * t2);
                 }
-                umma_commit(bar_O);
+                int pu = p_use;
+                for (int j = 0; j < nkb_eff; ++j, ++pu) {                  // O_t += P_t,j V_j
+                    const int slot = pu & 1;
+                    for (int t2 = 0; t2 < nact; ++t2) {
+                        mbar_wait(bars + 32 + 16 * t2 + 8 * slot, (pu >> 1) & 1, 100 + t2);
+                        tc_fence_after();
+                        const uint32_t ph_ = sbase + AT_P + (t2 * 2 + slot) * 16384, pl_ = ph_ + 8192;
+                        const uint32_t vh_ = sbase + AT_VHI + j * 2048, vl_ = sbase + AT_VLO + j * 2048;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint64_t dph = make_desc(ph_ + k * 32), dpl = make_desc(pl_ + k * 32);
+                            const uint64_t dvh = make_desc(vh_ + k * 32), dvl = make_desc(vl_ + k * 32);
+                            umma(tmem_base + t2 * 256 + AT_OCOL, dph, dvh, (j > 0 || k > 0) ? 1u : 0u, idesc_o);
+                            umma(tmem_base + t2 * 256 + AT_OCOL, dpl, dvh, 1u, idesc_o);
+                            umma(tmem_base + t2 * 256 + AT_OCOL, dph, dvl, 1u, idesc_o);
+                        }
+                        umma_commit(bars + 64 + 16 * t2 + 8 * slot);
+                        if (j == nkb_eff - 1) umma_commit(bars + 16 + 8 * t2);
+                    }
+                }
             }
-        } else {
+        } else if (gact) {
             const int q4 = warp & 3;                                       // TMEM lane quadrant of this warp
             const int row = q4 * 32 + lane;
-            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-            mbar_wait(bar_S, tph, 200 + tile);
-            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + wt * 256;
+            const uint32_t bar_Pfull = bars + 32 + 16 * wt, bar_Pempty = bars + 64 + 16 * wt;
             const bool wact = tile * 128 + q4 * 32 < Lq;                   // warp has at least one real query row
+            const int qi = tile * 128 + row;
+            const bool rflag = quirk && a.q_pad[(long long)bp * Lq + (qi < Lq ? qi : 0)];
+            mbar_wait(bars + 8 * wt, tph, 200 + wt);
+            tc_fence_after();
             // pass 1: row maximum over the valid keys
             float mx = -CUDART_INF_F;
             if (wact) {
                 for (int c = 0; c < nkb_eff; ++c) {
                     float v[32];
                     tmem_ld32(trow + c * 32, v);
-                    const uint32_t mk = kmask[c];
+                    const uint32_t mk = kmask_own[c] | (rflag ? kmask_oth[c] : 0u);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) mx = fmaxf(mx, v[j]);
                 }
@@ -195,7 +229,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
                 if (wact) {
                     float v[32];
                     tmem_ld32(trow + c * 32, v);
-                    const uint32_t mk = kmask[c];
+                    const uint32_t mk = kmask_own[c] | (rflag ? kmask_oth[c] : 0u);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float p0 = ((mk >> (2 * j)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j], 1.4426950408889634f, -mxl));
@@ -211,8 +245,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { hi[j] = 0u; lo[j] = 0u; }
                 }
-                mbar_wait(bar_Pempty + 8 * slot, ((pu >> 1) & 1) ^ 1, 300 + pu);       // slot free (first two uses pass immediately)
-                uint8_t* ph_ = smem + AT_P + slot * 16384;
+                mbar_wait(bar_Pempty + 8 * slot, ((pu >> 1) & 1) ^ 1, 300 + wt);    // slot free (first two uses pass at once)
+                uint8_t* ph_ = smem + AT_P + (wt * 2 + slot) * 16384;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const int off = sw64(row, cc * 8);
@@ -223,37 +257,37 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_Pfull + 8 * slot);
             }
-            // epilogue: O / rowsum, transposed through shared memory (the P ring is idle once bar_O fires)
-            mbar_wait(bar_O, tph, 400 + tile);
+            // epilogue: O / rowsum, transposed through shared memory (this tile's P ring is idle once its O barrier fires)
+            mbar_wait(bars + 16 + 8 * wt, tph, 400 + wt);
             tc_fence_after();
             if (wact) {
-            float o[32];
-            tmem_ld32(trow + AT_OCOL, o);
-            const float inv = 1.f / sum;
-            float* T = reinterpret_cast<float*>(smem + AT_P) + (warp - 1) * (32 * 36);
+                float o[32];
+                tmem_ld32(trow + AT_OCOL, o);
+                const float inv = 1.f / sum;
+                float* T = reinterpret_cast<float*>(smem + AT_P + wt * 32768) + q4 * (32 * 36);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(&T[lane * 36 + 4 * j]) = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
-            __syncwarp();
-            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(&T[lane * 36 + 4 * j]) = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+                __syncwarp();
+                const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + rsub;
-                const int qi = tile * 128 + q4 * 32 + r;
-                if (qi < Lq)
-                    *reinterpret_cast<float4*>(a.out + ((long long)b * Lq + qi) * a.ldo + h * 32 + c4) =
-                        *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
-            }
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + rsub;
+                    const int qo = tile * 128 + q4 * 32 + r;
+                    if (qo < Lq)
+                        *reinterpret_cast<float4*>(a.out + ((long long)b * Lq + qo) * a.ldo + h * 32 + c4) =
+                            *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+                }
             }
         }
         p_use += nkb_eff;
         tc_fence_before();
-        __syncthreads();                                                   // [B] TMEM / smem reads of this tile are done
+        __syncthreads();                                                   // [B] TMEM / smem reads of this tile pair are done
         tc_fence_after();
     }
     if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -262,14 +296,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
 void tc_read_watchdog(unsigned long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_watchdog, 512); unsigned long long z[64] = {0}; cudaMemcpyToSymbol(tc::g_tc_watchdog, z, 512); }
 
 bool attn_tc_eligible(const MhaRowsArgs& a) {
-    if (a.q_pad) return false;                                   // T2V quirk mask: SIMT kernel
     if (a.Lk > tc::AT_LKP_MAX || a.Lk < 1) return false;
+    // with <= 64 keys (the T2V cross-attention: 17 / 33 words) the per-CTA staging latency outweighs the tensor-core
+    // gain; measured 13.9 ms vs 9.5 ms per bench step for the fp32 thread-per-row kernel
+    if (a.Lk <= 64) return false;
     auto al = [](const float* p, int ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); };
     return al(a.q, a.ldq) && al(a.k, a.ldk) && al(a.v, a.ldv) && al(a.out, a.ldo);
 }
 
 cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s) {
-    ProfScope _ps("attn_tc", s);
+    ProfScope _ps(a.q_pad ? "attn_tc t2v" : "attn_tc self", s);
     static bool attr_set = false;
     if (!attr_set) {
         MESM_CHECK(cudaFuncSetAttribute(tc::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::AT_SMEM));
