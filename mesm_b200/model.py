@@ -164,6 +164,8 @@ class _EngineBacked(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _engine(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("mesm_b200: inputs must be CUDA tensors (there is no CPU fallback)")
         sig = (str(device), self._weights_signature())
         eng = getattr(self, "_eng", None)
         if eng is None or self.__dict__.get("_eng_sig") != sig:
