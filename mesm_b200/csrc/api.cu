@@ -163,7 +163,7 @@ int fail(mesm_ctx* c, int code, const std::string& msg) {
 // T2V layer (model/transformer.py:508-540).  txt rows: [Bc*Lk] through tmap; vid rows [Bc*Lq] contiguous.
 cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
-                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s) {
+                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q) {
     const int Rt = Bc * Lk, Rv = Bc * Lq;
     if (pos_txt) {
         PL kw = L.kv; kw.N = D;
@@ -173,7 +173,7 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     } else {
         MESM_CHECK(Lin(Rt, L.kv, txt, D, t.KV, 2 * D).amap(tmap).run(s));
     }
-    MESM_CHECK(Lin(Rv, L.q, vid, D, t.Q, D).apos(pos_vid).run(s));
+    if (!reuse_q) MESM_CHECK(Lin(Rv, L.q, vid, D, t.Q, D).apos(pos_vid).run(s));      // Q depends on the clips only
     MhaRowsArgs a;
     a.q = t.Q; a.ldq = D; a.k = t.KV; a.ldk = 2 * D; a.v = t.KV + D; a.ldv = 2 * D;
     a.k_pad = k_pad; a.q_pad = q_pad; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = Lq; a.Lk = Lk; a.b0 = b0; a.Btot = Btot;
@@ -536,7 +536,7 @@ struct FwdPlan {
     uint8_t *wmask, *emask, *epad, *wpad, *neg_epad, *neg_wpad, *padV_all;
     int* d_tab;
     // chunk buffers
-    float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2;
+    float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2, *Qenh0;
     uint8_t *padV, *padE;
     T2VBuffers t2v;
     EncBuffers encb;
@@ -559,7 +559,7 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     const int L1 = Lv + 1;
     const size_t Rv = (size_t)Bc * Lv, Re = (size_t)Bc * L1, Rk = (size_t)Bc * (Lt + 1);
     p.posV = ar.get<float>(Rv * D); p.posE = ar.get<float>(Re * D);
-    p.xa = ar.get<float>(Rv * D); p.xb = ar.get<float>(Rv * D); p.enh = ar.get<float>(Rv * D);
+    p.xa = ar.get<float>(Rv * D); p.xb = ar.get<float>(Rv * D); p.enh = ar.get<float>(Rv * D); p.Qenh0 = ar.get<float>(Rv * D);
     p.E = ar.get<float>(Re * D); p.E2 = ar.get<float>(Re * D); p.P1 = ar.get<float>(Re * D); p.P2 = ar.get<float>((size_t)Bc * D);
     p.padV = ar.get<uint8_t>(Rv); p.padE = ar.get<uint8_t>(Re);
     p.t2v.KV = ar.get<float>(Rk * 2 * D); p.t2v.Q = ar.get<float>(Re * D); p.t2v.AO = ar.get<float>(Re * D);
@@ -669,8 +669,16 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     // ---- whole batch: input projection of the clips (model/model.py:166) — row-wise, no reason to chunk ---------------
     {
         const long long Rall = (long long)B * Lv;
-        CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s));
-        CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+        // LayerNorm(Dv) is folded into the GEMM; its row statistics are accumulated by the kernel's operand converters
+        // while the features stream through (one pass over the feature bytes - the only HBM-bound stage of the path)
+        Lin fused((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D);
+        fused.fold_fused(ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln);
+        if (linear_tc_eligible(fused.op) && !getenv("MESM_FORCE_SIMT")) {
+            CK(fused.run(s));
+        } else {
+            CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s));
+            CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+        }
         CK(Lin((int)Rall, ctx->vid1, p.v1, D, projV_all, D).run(s));
     }
     // ---- whole batch: SS-MESM sentence reconstruction (model/model.py:184-222, 467-488).  One masked sentence slot per
@@ -715,6 +723,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         float* projV = projV_all + (size_t)b0 * Lv * D;
         PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos;
         pa.posV = p.posV; pa.posE = p.posE; pa.encbuf = p.E; pa.padV = p.padV; pa.padE = p.padE;
+        if (neg) { pa.posV = nullptr; pa.posE = nullptr; pa.padV = nullptr; pa.padE = nullptr; }   // positions / pads kept from the main pass
         CK(launch_pos_embed(pa, s));
         const float* words_c = (neg ? p.negw : expw) + (size_t)b0 * Lk * D;
         const uint8_t* epad_all = neg ? p.neg_epad : p.epad;
@@ -724,8 +733,10 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         float* enh = (!neg && out->enhanced_video_feat) ? out->enhanced_video_feat + (size_t)b0 * Lv * D : p.enh;
         for (size_t l = 0; l < ctx->enh.size(); ++l) {
             float* dst = (l + 1 == ctx->enh.size()) ? enh : (l % 2 == 0 ? p.xa : p.xb);
-            CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, p.t2v,
-                         dst, D, identity_map(), s));
+            T2VBuffers tb = p.t2v;
+            if (l == 0) tb.Q = p.Qenh0;                 // layer 0's Q = (projV + pos) Wq is identical in the negative pass
+            CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, tb,
+                         dst, D, identity_map(), s, l == 0 && neg));
             x = dst;
         }
         if (ctx->enh.empty() && !neg && out->enhanced_video_feat)
@@ -737,7 +748,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
             const bool last = (l + 1 == ctx->aln.size());
             float* dst = last ? p.E : (l % 2 == 0 ? p.xa : p.xb);
             CK(t2v_layer(ctx->aln[l], words_c, identity_map(), nullptr, Lk, xin, p.posV, Lv, Bc, b0, B, p.padV_all, epad_all,
-                         p.t2v, dst, D, last ? RowMap{Lv, L1, 1} : identity_map(), s));
+                         p.t2v, dst, D, last ? RowMap{Lv, L1, 1} : identity_map(), s, false));
             xin = dst;
         }
         if (ctx->aln.empty())
@@ -771,13 +782,18 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         return 0;
     };
 
-    for (auto& ch : chunks) { const int rc = video_chunk(ch.first, ch.second, false); if (rc) return rc; }
-
-    // ---- negative branch (model/model.py:260-302): every pair re-scored against the text of another video group ----
-    if (in->neg_index && out->neg_saliency_scores) {
+    // ---- negative branch (model/model.py:260-302): every pair re-scored against the text of another video group.  The
+    //      gathered text is needed up front so that each chunk runs its negative pass right after its main pass (the
+    //      chunk's projected clips, positions and layer-0 queries are still in L2 / reused).
+    const bool do_neg = in->neg_index && out->neg_saliency_scores;
+    if (do_neg) {
         CK(launch_gather_blocks(expw, p.negw, in->neg_index, B, (long long)Lk * D, p.epad, p.neg_epad, Lk, s));
         CK(launch_expand_mask_from_epad(p.neg_epad, B, Lt, p.neg_wpad, s));
-        for (auto& ch : chunks) { const int rc = video_chunk(ch.first, ch.second, true); if (rc) return rc; }
+    }
+    for (auto& ch : chunks) {
+        int rc = video_chunk(ch.first, ch.second, false);
+        if (rc) return rc;
+        if (do_neg) { rc = video_chunk(ch.first, ch.second, true); if (rc) return rc; }
     }
     CK(cudaGetLastError());
     ctx->last_launches = g_stats.launches - launches0;

@@ -38,6 +38,7 @@ struct LinearOp {
     int K2; const float* A2; int lda2; RowMap a2map; const float* Wt2;   // optional second input (same ldw)
     const float* bias;                            // [N] or null
     const float* rowstat;                         // [M,2] (mean, rstd) of A rows: LayerNorm folded into the GEMM
+    int fuse_rowstat;                             // tcgen05 kernel only: compute (mean, rstd) of the A rows in-kernel instead
     const float* colsum;                          // [N]  sum_k Wt[k,n]  (weights already carry gamma)
     float out_scale;                              // applied after bias (attention q scaling); 1 = none
     int act; const float* prelu;                  // PReLU slope (1 element, device)
@@ -55,7 +56,7 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
     LinearOp op;
     op.M = M; op.N = N; op.K = K; op.A = A; op.lda = lda; op.amap = identity_map(); op.Apos = nullptr;
     op.Wt = Wt; op.ldw = ldw; op.Wp = nullptr; op.Wp2 = nullptr; op.K2 = 0; op.A2 = nullptr; op.lda2 = 0; op.a2map = identity_map(); op.Wt2 = nullptr;
-    op.bias = bias; op.rowstat = nullptr; op.colsum = nullptr; op.out_scale = 1.f; op.act = ACT_NONE; op.prelu = nullptr;
+    op.bias = bias; op.rowstat = nullptr; op.fuse_rowstat = 0; op.colsum = nullptr; op.out_scale = 1.f; op.act = ACT_NONE; op.prelu = nullptr;
     op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
     op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr;
     op.nbatch = 1; op.bsA = op.bsW = op.bsBias = op.bsOut = 0;

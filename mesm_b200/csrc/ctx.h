@@ -121,6 +121,7 @@ struct Lin {    // thin builder around LinearOp
     Lin& act(int a, const float* slope = nullptr) { op.act = a; op.prelu = slope; return *this; }
     Lin& scale(float s) { op.out_scale = s; return *this; }
     Lin& fold(const float* rowstat, const float* colsum) { op.rowstat = rowstat; op.colsum = colsum; return *this; }
+    Lin& fold_fused(const float* colsum) { op.rowstat = nullptr; op.fuse_rowstat = 1; op.colsum = colsum; return *this; }
     Lin& res(const float* r, int ldr, RowMap m = identity_map()) { op.residual = r; op.ldr = ldr; op.rmap = m; return *this; }
     Lin& ln(const Norm& n) { op.ln_g = n.g; op.ln_b = n.b; return *this; }
     Lin& pre_ln(float* p) { op.pre_ln = p; return *this; }
@@ -143,7 +144,7 @@ struct DecBuffers {
 
 cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
-                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s);
+                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q = false);
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
                       const EncBuffers& t, float* out, cudaStream_t s);
 size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl);

@@ -81,6 +81,10 @@ cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float
 __global__ void __launch_bounds__(256) pos_embed_kernel(const PosArgs a) {
     extern __shared__ float xemb[];     // [Lv]
     const int b = blockIdx.x, Lv = a.Lv;
+    if (!a.posV && !a.posE && !a.padV && !a.padE) {          // only the global token row of the encoder buffer
+        if (a.encbuf) a.encbuf[(long long)b * (Lv + 1) * D + threadIdx.x] = a.gtok[threadIdx.x];
+        return;
+    }
     const uint8_t* m = a.vmask + (long long)b * Lv;
     for (int i = threadIdx.x; i < Lv; i += blockDim.x) {
         int c = 0;

@@ -215,12 +215,43 @@ __global__ void __launch_bounds__(NT, 2) linear_simt_kernel(const LinearOp op_in
     }
 }
 
+// N <= 8 outputs per row (class / span / anchor heads): one warp per row, K split over the lanes, weights from L1.
+__global__ void __launch_bounds__(256) linear_smalln_kernel(const LinearOp op) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= op.M) return;
+    const float* a = op.A + op.amap(m) * (long long)op.lda;
+    float acc[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+    for (int k = lane; k < op.K; k += 32) {
+        const float x = a[k];
+        const float* w = op.Wt + (long long)k * op.ldw;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) if (n < op.N) acc[n] = fmaf(x, __ldg(w + n), acc[n]);
+    }
+    const float slope = (op.act == ACT_PRELU) ? __ldg(op.prelu) : 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        if (n >= op.N) break;
+        float v = warp_sum(acc[n]);
+        v = (v + (op.bias ? __ldg(op.bias + n) : 0.f)) * op.out_scale;
+        v = apply_act(v, op.act, slope);
+        if (lane == 0) op.out[op.omap(m) * (long long)op.ldo + n] = v;
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s) {
     if (op.M <= 0 || op.N <= 0) return cudaSuccess;
     if (op.ln_g && op.N != 256) return cudaErrorInvalidValue;
+    if (op.fuse_rowstat) return cudaErrorInvalidValue;        // only the tcgen05 kernel computes the statistics in-kernel
     if ((op.ldw & 3) != 0) return cudaErrorInvalidValue;
+    if (op.N <= 8 && !op.A2 && !op.Apos && !op.rowstat && !op.residual && !op.ln_g && !op.out2 && !op.pre_ln && op.nbatch <= 1) {
+        linear_smalln_kernel<<<(op.M + 7) / 8, 256, 0, s>>>(op);
+        g_stats.launches++;
+        return cudaGetLastError();
+    }
     dim3 grid((op.M + BM - 1) / BM, (op.N + BN - 1) / BN, op.nbatch > 1 ? op.nbatch : 1);
     linear_simt_kernel<<<grid, NT, 0, s>>>(op);
     g_stats.launches++;

@@ -159,11 +159,15 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
                 rowoff[256 + tc] = (ok && op.residual) ? op.rmap(m) * (long long)op.ldr : -1;
             }
         }
+        ln_x[tc] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
         // Global loads are issued branch-free (clamped addresses, validity applied at conversion time) and TWO K blocks
         // ahead of the block being converted, alternating between two register buffers.
         float buf0[NV * VEC], buf1[NV * VEC];
+        float st_sum[NV], st_sq[NV];                    // fused LayerNorm statistics of this thread's A elements
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
         struct Src { const float* base; int K; int k0; int tab; };
         auto source = [&](int kb) {
             Src r;
@@ -205,6 +209,12 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
                     if (ks != 2) v = (ks == 1 && k + j < sc.K && ro >= 0) ? sc.base[ro + k + j] : 0.f;   // K tail (last block only)
                     cur[i * VEC + j] = ro >= 0 ? v : 0.f;
                 }
+            }
+            if (op.fuse_rowstat) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { const float v = cur[i * VEC + j]; st_sum[i] += v; st_sq[i] = fmaf(v, v, st_sq[i]); }
             }
             if (kb + 2 < nkb) load_block(kb + 2, src);             // refill this buffer: two blocks stay in flight
             if (tc == 0 && kb < 8) TSTAMP(24 + kb);
@@ -248,6 +258,14 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
         }
 
         // ---------------- epilogue: TMEM -> registers -> global ----------------
+        if (op.fuse_rowstat) {                             // per-row sums: PER_ROW threads share a row
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                atomicAdd(&ln_x[r0 + i * ROW_STEP], st_sum[i]);
+                atomicAdd(&ln_x[128 + r0 + i * ROW_STEP], st_sq[i]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         mbar_wait(bar_tmem, 0, 5000);
         tc_fence_after();
         if (tc == 0) TSTAMP(3);
@@ -260,6 +278,12 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
         const float slope_eff = op.act == ACT_PRELU ? __ldg(op.prelu) : (op.act == ACT_RELU ? 0.f : 1.f);
         float mean_in = 0.f, rstd_in = 1.f;
         if (op.rowstat && mok) { mean_in = __ldg(op.rowstat + 2 * m); rstd_in = __ldg(op.rowstat + 2 * m + 1); }
+        if (op.fuse_rowstat) {
+            const float invK = 1.f / (float)op.K;
+            mean_in = ln_x[row] * invK;
+            rstd_in = rsqrtf(fmaxf(ln_x[128 + row] * invK - mean_in * mean_in, 0.f) + 1e-5f);
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // ln_x is reused by the output LayerNorm below
+        }
         const float* res = (op.residual && mok) ? op.residual + op.rmap(m) * (long long)op.ldr : nullptr;
         float* out = mok ? op.out + op.omap(m) * (long long)op.ldo : nullptr;
         float* out2 = (op.out2 && mok) ? op.out2 + op.o2map(m) * (long long)op.ldo2 : nullptr;
@@ -457,6 +481,7 @@ bool linear_tc_eligible(const LinearOp& op) {
     if (op.M < 128 || op.N < 64) return false;
     if (op.ln_g && op.N != 256) return false;
     if (op.act == ACT_SIGMOID) return false;
+    if (op.fuse_rowstat && (op.Apos || op.A2 || !op.colsum)) return false;
     auto al16 = [](const float* p, long long ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); };
     if ((op.N & 3) || !al16(op.out, op.ldo) || !al16(op.out2, op.ldo2) || !al16(op.residual, op.ldr) || !al16(op.pre_ln, op.N)) return false;
     auto ok = [](const float* p, int ld, int K) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 7) == 0) && (ld % 2 == 0) && (K % 2 == 0)); };

@@ -41,6 +41,8 @@ def test_attention_kernels_match_reference(B, L):
     qkv, pad = _inputs(B, L)
     ref = _reference(qkv, pad, B, L)
     for use_tc, tol in ((0, 2e-6), (1, 3e-5)):
+        if use_tc and L <= 64:
+            continue                      # <= 64 keys stay on the fp32 kernel by design (attn_tc_eligible)
         out, wd = _run(qkv, pad, B, L, use_tc)
         assert wd[0] == 0, wd
         assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
