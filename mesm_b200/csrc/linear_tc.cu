@@ -2,7 +2,7 @@
 //
 //   out[M,N] = epilogue( (A (+Apos))[M,K] . W[N,K]^T  (+ A2[M,K2] . W2[N,K2]^T) )       fp32 in, fp32 out
 //
-// Why bf16x3: the parity bar is <= 1e-3 on the network outputs after ~50 chained GEMMs; oracle/precision_study.py shows
+// Why bf16x3: the parity bar is <= 1e-3 on the network outputs after ~50 chained GEMMs; the precision study shows
 // plain bf16 operands give 3e-3..1e-2 and tf32 1e-3..4e-3, while x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and
 // D += Ahi.Whi + Alo.Whi + Ahi.Wlo (fp32 accumulation in TMEM) gives ~1e-5.
 //
