@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--chunk-pairs", type=int, default=384)
     ap.add_argument("--cpu-sample-pairs", type=int, default=32)
     ap.add_argument("--topk", type=int, default=100)
+    ap.add_argument("--e2e-sub", type=int, default=1024, help="pairs per host->device sub-batch of the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -271,16 +272,16 @@ def main():
             "hbm_frac_whole_step": (ALGO_BYTES_PER_PAIR * B / (ms / args.steps * 1e-3)) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))}
 
     # ---- e2e: same work through the public API from pinned host memory, sub-batches double-buffered over two streams -----
-    sub = 512 if B >= 512 else B
-    nsub = B // sub
-    ncs = wl["num_clips"].tolist()
-    # sub-batches must hold whole groups: rebuild a 512-pair slice with its own grouping
+    sub = args.e2e_sub if B >= args.e2e_sub else B
+    nsub = max(1, B // sub)
+    # sub-batches must hold whole groups: rebuild a slice with its own grouping
     sb = take_groups(wl, sub)
     Bs = sb["video_feat"].shape[0]
     host = {k: sb[k].cpu().pin_memory() for k in ("video_feat", "video_mask", "words_feat", "duration", "neg_index")}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     # One context = one compute stream (a mesm_ctx is not re-entrant).  A second stream prefetches the next sub-batch from
-    # pinned host memory while the current one is being scored; events order copy -> compute -> buffer reuse.
+    # pinned host memory while the current one is being scored; events order copy -> compute -> buffer reuse.  Steps are
+    # streamed back to back (the first sub-batch of step k+1 is prefetched under the last sub-batch of step k).
     comp, copy = torch.cuda.Stream(), torch.cuda.Stream()
     dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
@@ -288,18 +289,30 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_pass():
+    def e2e_stream(total):
+        # Host order matters: a forward enqueues hundreds of launches and the launch queue is finite, so the copy of
+        # sub-batch i+1 is enqueued BEFORE the launches of sub-batch i - otherwise it would only start once they drained.
         for e in freed:
             e.record(comp)
-        for i in range(nsub):
-            d = dbuf[i % 2]
+
+        def prefetch(i):
             with torch.cuda.stream(copy):
                 copy.wait_event(freed[i % 2])                  # the compute that last read this buffer has finished
-                for k, v in host.items():
-                    d[k].copy_(v, non_blocking=True)
+                if not os.environ.get("MESM_E2E_NOCOPY"):
+                    for k, v in host.items():
+                        dbuf[i % 2][k].copy_(v, non_blocking=True)
                 ready[i % 2].record(copy)
+
+        prefetch(0)
+        for i in range(total):
+            d = dbuf[i % 2]
+            if i + 1 < total:
+                prefetch(i + 1)
             with torch.cuda.stream(comp):
                 comp.wait_event(ready[i % 2])
+                if os.environ.get("MESM_E2E_NOCOMP"):
+                    freed[i % 2].record(comp)
+                    continue
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
                           dataset_name="charades", is_training=False, neg_index=d["neg_index"])
                 w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
@@ -311,14 +324,13 @@ def main():
         copy.synchronize()
 
     d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
-    e2e_pass()
+    e2e_stream(nsub)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        e2e_pass()
+    e2e_steps = max(1, args.steps)
+    e2e_stream(nsub * e2e_steps)
     torch.cuda.synchronize()
     _v("e2e done")
     e2e_s = time.perf_counter() - t0
@@ -331,7 +343,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d * nsub, "d2h_bytes_per_step": d2h * nsub,
-                    "note": f"{nsub} sub-batches of {Bs} pairs, pinned host -> device prefetched on a copy stream, windows + keep sets back to host"},
+                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream, windows + keep sets back to host"},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

@@ -646,7 +646,11 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         return fail(ctx, 1, "mesm_forward: workspace too small: need " + std::to_string(p.total) + " bytes, got " + std::to_string(workspace_bytes));
     if (!projV_all) projV_all = p.projV;
     int* d_group = p.d_tab; int* d_slot = d_group + B; int* d_gstart = d_slot + B; int* d_glen = d_gstart + (G + 1);
-    CK(cudaMemcpyAsync(d_group, h_group, tab_ints * sizeof(int), cudaMemcpyHostToDevice, s));
+    {
+        int* h_dev = nullptr;                       // device alias of the pinned table (identical under UVA)
+        CK(cudaHostGetDevicePointer((void**)&h_dev, h_group, 0));
+        CK(launch_pull_ints(h_dev, d_group, (long long)tab_ints, s));
+    }
     CK(cudaEventRecord(ctx->tab_event, s));
     ctx->tab_event_pending = true;
     if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));

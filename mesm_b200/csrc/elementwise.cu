@@ -408,4 +408,17 @@ cudaError_t launch_fill(float* p, long long n, float v, cudaStream_t s) {
     LAUNCH_END();
 }
 
+// Pair/group tables live in pinned host memory; the device pulls them over PCIe with a kernel so that the transfer never
+// queues on the copy engine behind a caller's bulk host->device prefetch.
+__global__ void pull_ints_kernel(const int* __restrict__ host_src, int* __restrict__ dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = host_src[i];
+}
+cudaError_t launch_pull_ints(const int* host_src, int* dst, long long n, cudaStream_t s) {
+    ProfScope _ps("pull_tables", s);
+    if (n <= 0) return cudaSuccess;
+    pull_ints_kernel<<<blocks_for(n, 256), 256, 0, s>>>(host_src, dst, n);
+    LAUNCH_END();
+}
+
 }  // namespace mesm

@@ -73,5 +73,6 @@ cudaError_t launch_layernorm_rows(const float* x, long long R, const float* g, c
 cudaError_t launch_group_len(const uint8_t* vmask, int Lv, const int* group_start, int G, int* group_len, cudaStream_t s);
 cudaError_t launch_masked_mean_norm(const float* x, const uint8_t* mask, int B, int L, float* out, int ldo, int transposed, cudaStream_t s);
 cudaError_t launch_fill(float* p, long long n, float v, cudaStream_t s);
+cudaError_t launch_pull_ints(const int* pinned_host_src, int* dst, long long n, cudaStream_t s);
 
 }  // namespace mesm
