@@ -32,10 +32,18 @@ constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;                       // bytes of one bf16 plane of the A tile
 constexpr int W_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;      // 49152: two CTAs (2 x ~105 KB) share one SM
+// CTA-pair mode (cta_group::2): the pair computes a 256 x 256 tile, each CTA stages its own 128 rows of A and HALF of the
+// weight tile (128 of the 256 output columns), so the L2 -> SM weight traffic per output row halves.
+constexpr int W_HALF = W_TILE / 2;
+constexpr int STAGES_PAIR = 3;
+constexpr int STAGE_BYTES_PAIR = 2 * A_TILE + 2 * W_HALF; // 32768
+static_assert(STAGES_PAIR * STAGE_BYTES_PAIR == STAGES * STAGE_BYTES, "both modes use the same operand ring size");
 constexpr int NCONV = 256;                                // converter / epilogue threads (8 warps)
 constexpr int THREADS = 64 + NCONV;
 constexpr uint32_t IDESC = make_idesc(BN);
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 + 1024 + 4096 + 3072 + 2048 /*barriers, LN exchange, epilogue vectors, row offsets*/;
+constexpr uint32_t IDESC_PAIR = make_idesc(BN, 256);
+constexpr int BAR_BYTES = 192;                            // full_w[4] full_a[4] empty[4] peer_full[4] tmem_full tmem_ptr
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + 1024 + 4096 + 3072 + 2048 /*barriers, LN exchange, epilogue vectors, row offsets*/;
 
 __device__ __forceinline__ float act_fn(float v, int act, float slope) {
     if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -45,18 +53,21 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
 }
 
 // VEC = floats per global load of the A operand (4: 16-byte aligned rows; 2: 8-byte aligned rows such as Dv = 2818)
-template <int VEC>
+template <int VEC, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op, const int nkb1, const int nkb2) {
     // K sweeps accumulated into one tile: A.W^T, then (if present) Apos.W^T with the same weights, then A2.W2^T.
+    constexpr int NST = PAIR ? STAGES_PAIR : STAGES;
+    constexpr int STG = PAIR ? STAGE_BYTES_PAIR : STAGE_BYTES;
+    constexpr int WT = PAIR ? W_HALF : W_TILE;             // bytes of one bf16 plane of this CTA's share of the weight tile
     const int nkbp = op.Apos ? nkb1 : 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-    // barriers: full_w[s] @ +0,+8 ; full_a[s] @ +16,+24 ; empty[s] @ +32,+40 ; tmem_full @ +48 ; tmem ptr @ +56
-    const uint32_t bar_full_w = bar_base, bar_full_a = bar_base + 16, bar_empty = bar_base + 32, bar_tmem = bar_base + 48;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 56);
-    float* ln_x = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 64);      // [2][128] partial sums
+    const uint32_t bar_base = smem_base + NST * STG;
+    const uint32_t bar_full_w = bar_base, bar_full_a = bar_base + 32, bar_empty = bar_base + 64, bar_peer = bar_base + 96,
+                   bar_tmem = bar_base + 128;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + NST * STG + 136);
+    float* ln_x = reinterpret_cast<float*>(smem + NST * STG + BAR_BYTES);          // [2][128] partial sums
     float* vec_s = ln_x + 256;                                                      // [4][256]: bias, colsum, ln_g, ln_b of this N tile
     long long* rowoff = reinterpret_cast<long long*>(vec_s + 1024);                 // [3][128]: out, out2, residual row offsets (-1: no row)
     long long* rowoffA = rowoff + 3 * 128;                                          // [2][128]: A / A2 operand row offsets
@@ -65,69 +76,133 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, nt = blockIdx.y, n0 = nt * BN;
     const int nkb = nkb1 + nkbp + nkb2;
+    const uint32_t cta_rank = PAIR ? (blockIdx.x & 1u) : 0u;      // cluster (2,1,1): rank 0 issues the MMAs of the pair
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(bar_full_w + 8 * s, 1);
             mbar_init(bar_full_a + 8 * s, NCONV / 32);
             mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_peer + 8 * s, 1);
         }
         mbar_init(bar_tmem, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                  // the peer's barriers exist before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (threadIdx.x == 0) TSTAMP(1);
 
     if (warp == 0) {
-        // ===================== weight producer =====================
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+        // ===================== weight producer + L2 prefetcher of the activation rows =====================
+        // The converters keep only two K blocks per thread in flight (registers), which at HBM latency caps the operand
+        // stream far below the tensor pipe; the 32 lanes of this warp therefore pull the tile's activation rows (and the
+        // residual rows of the epilogue) from HBM into L2 PF_DIST K blocks ahead - prefetches hold no registers.
+        constexpr int PF_DIST = 8;
+        long long poff[4], poff2[4];                       // row offsets of this lane's 4 tile rows (-1: no such row)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + lane + 32 * i;
+            const bool ok = m < op.M;
+            poff[i] = ok ? op.amap(m) * (long long)op.lda : -1;
+            poff2[i] = (ok && op.A2) ? op.a2map(m) * (long long)op.lda2 : -1;
+            if (ok && op.residual && n0 < op.N) {
+                const float* r = op.residual + op.rmap(m) * (long long)op.ldr + n0;
+                const int nn = min(BN, op.N - n0);
+                for (int c = 0; c < nn; c += 32) prefetch_l2(r + c);
+            }
+        }
+        auto prefetch_block = [&](int kb) {
+            if (kb >= nkb) return;
+            const float* base; int K, k0; bool second = false;
+            if (kb < nkb1) { base = op.A; K = op.K; k0 = kb * BK; }
+            else if (kb < nkb1 + nkbp) { base = op.Apos; K = op.K; k0 = (kb - nkb1) * BK; }
+            else { base = op.A2; K = op.K2; k0 = (kb - nkb1 - nkbp) * BK; second = true; }
+            const int k1 = min(k0 + BK, K) - 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long ro = second ? poff2[i] : poff[i];
+                if (ro < 0) continue;
+                const float* r = base + ro;
+                prefetch_l2(r + k0);
+                if (((reinterpret_cast<uintptr_t>(r + k0)) & 127) != 0) prefetch_l2(r + k1);   // block straddles two lines
+            }
+        };
+        for (int kb = 0; kb < PF_DIST; ++kb) prefetch_block(kb);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % NST;
+            const uint32_t ph = (kb / NST) & 1;
+            prefetch_block(kb + PF_DIST);
+            if (lane == 0) {
                 mbar_wait(bar_empty + 8 * s, ph ^ 1, 1000 + kb);
                 const int kk = kb < nkb1 ? kb : (kb < nkb1 + nkbp ? kb - nkb1 : kb - nkb1 - nkbp);
                 const uint8_t* src = kb < nkb1 + nkbp
                                          ? reinterpret_cast<const uint8_t*>(op.Wp) + ((size_t)nt * nkb1 + kk) * (2 * W_TILE)
                                          : reinterpret_cast<const uint8_t*>(op.Wp2) + ((size_t)nt * nkb2 + kk) * (2 * W_TILE);
-                mbar_arrive_expect_tx(bar_full_w + 8 * s, 2 * W_TILE);
-                const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_TILE;
-                bulk_copy_g2s(dst, src, W_TILE, bar_full_w + 8 * s);
-                bulk_copy_g2s(dst + W_TILE, src + W_TILE, W_TILE, bar_full_w + 8 * s);
+                mbar_arrive_expect_tx(bar_full_w + 8 * s, 2 * WT);
+                const uint32_t dst = smem_base + s * STG + 2 * A_TILE;
+                // pair mode: this CTA's 128 of the 256 weight rows = one contiguous half of each packed plane
+                bulk_copy_g2s(dst, src + cta_rank * WT, WT, bar_full_w + 8 * s);
+                bulk_copy_g2s(dst + WT, src + W_TILE + cta_rank * WT, WT, bar_full_w + 8 * s);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {
+            // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(bar_full_w + 8 * s, ph, 2000 + kb);
                 if (kb < 8) TSTAMP(8 + kb);
                 mbar_wait(bar_full_a + 8 * s, ph, 3000 + kb);
+                if (PAIR) mbar_wait_cluster(bar_peer + 8 * s, ph, 3500 + kb);      // the peer's half of the stage has landed
                 if (kb < 8) TSTAMP(16 + kb);
                 tc_fence_after();
-                const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
-                const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + W_TILE;
+                const uint32_t a_hi = smem_base + s * STG, a_lo = a_hi + A_TILE;
+                const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + WT;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes along K inside the 64B swizzle row
                     const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
                     const uint64_t dwh = make_desc(w_hi + koff), dwl = make_desc(w_lo + koff);
-                    umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC);
-                    umma(tmem_base, dal, dwh, 1u, IDESC);
-                    umma(tmem_base, dah, dwl, 1u, IDESC);
+                    if (PAIR) {
+                        umma2(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC_PAIR);
+                        umma2(tmem_base, dal, dwh, 1u, IDESC_PAIR);
+                        umma2(tmem_base, dah, dwl, 1u, IDESC_PAIR);
+                    } else {
+                        umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC);
+                        umma(tmem_base, dal, dwh, 1u, IDESC);
+                        umma(tmem_base, dah, dwl, 1u, IDESC);
+                    }
                 }
-                umma_commit(bar_empty + 8 * s);            // stage reusable once these MMAs retire
+                if (PAIR) umma_commit2(bar_empty + 8 * s); // stage reusable (both CTAs) once these MMAs retire
+                else umma_commit(bar_empty + 8 * s);
             }
-            umma_commit(bar_tmem);                         // accumulator complete
+            if (PAIR) umma_commit2(bar_tmem);              // accumulator complete (both CTAs' epilogues)
+            else umma_commit(bar_tmem);
             TSTAMP(2);
+        } else if (PAIR && lane == 0) {
+            // ===================== peer CTA: forward "my half of stage s is in shared memory" to the leader =============
+            const uint32_t remote = map_to_cta(bar_peer, 0);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
+                mbar_wait(bar_full_w + 8 * s, ph, 2000 + kb);
+                mbar_wait(bar_full_a + 8 * s, ph, 3000 + kb);
+                mbar_arrive_remote(remote + 8 * s);
+            }
         }
     } else {
         // ===================== A converters, then epilogue =====================
@@ -194,8 +269,8 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             }
         };
         auto convert_block = [&](int kb, float (&src)[NV * VEC]) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
+            const int s = kb % NST;
+            const uint32_t ph = (kb / NST) & 1;
             const Src sc = source(kb);
             const int k = sc.k0 + cv * VEC;
             const int ks = (k + VEC <= sc.K) ? 2 : (k < sc.K ? 1 : 0);
@@ -220,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             if (tc == 0 && kb < 8) TSTAMP(24 + kb);
             mbar_wait(bar_empty + 8 * s, ph ^ 1, 4000 + kb);
             if (tc == 0 && kb < 8) TSTAMP(32 + kb);
-            uint8_t* a_hi = smem + s * STAGE_BYTES;
+            uint8_t* a_hi = smem + s * STG;
             uint8_t* a_lo = a_hi + A_TILE;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -417,10 +492,12 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     if (threadIdx.x == 64) TSTAMP(5);
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                  // neither CTA frees TMEM / leaves while the pair is still working
     if (threadIdx.x == 0) TSTAMP(6);
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
 }
 
@@ -489,21 +566,40 @@ bool linear_tc_eligible(const LinearOp& op) {
     return true;
 }
 
-cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s) {
+static int g_tc_pair = -1;                         // MESM_TC_PAIR=0 selects the single-CTA kernel (A/B comparisons)
+void tc_set_pair_mode(int on) { g_tc_pair = on; }
+
+template <int VEC, bool PAIR>
+static cudaError_t launch_tc_variant(const LinearOp& op, int nkb1, int nkb2, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        MESM_CHECK(cudaFuncSetAttribute(tc::linear_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        MESM_CHECK(cudaFuncSetAttribute(tc::linear_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MESM_CHECK(cudaFuncSetAttribute(tc::linear_tc_kernel<VEC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         attr_set = true;
     }
+    const unsigned mt = (unsigned)((op.M + tc::BM - 1) / tc::BM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PAIR ? ((mt + 1) & ~1u) : mt, (unsigned)((op.N + tc::BN - 1) / tc::BN), 1);
+    cfg.blockDim = dim3(tc::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<VEC, PAIR>, op, nkb1, nkb2);
+}
+
+cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s) {
+    if (g_tc_pair < 0) { const char* e = getenv("MESM_TC_PAIR"); g_tc_pair = (e && e[0] == '0') ? 0 : 1; }
     const int nkb1 = (op.K + tc::BK - 1) / tc::BK, nkb2 = op.A2 ? (op.K2 + tc::BK - 1) / tc::BK : 0;
     auto v4 = [](const float* p, int ld, int K) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0) && (K % 4 == 0)); };
     const bool vec4 = v4(op.A, op.lda, op.K) && v4(op.Apos, op.lda, op.K) && v4(op.A2, op.lda2, op.K2);
-    dim3 grid((op.M + tc::BM - 1) / tc::BM, (op.N + tc::BN - 1) / tc::BN);
-    if (vec4) tc::linear_tc_kernel<4><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(op, nkb1, nkb2);
-    else tc::linear_tc_kernel<2><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(op, nkb1, nkb2);
+    const bool pair = g_tc_pair && op.M > tc::BM;
+    cudaError_t e;
+    if (pair) e = vec4 ? launch_tc_variant<4, true>(op, nkb1, nkb2, s) : launch_tc_variant<2, true>(op, nkb1, nkb2, s);
+    else e = vec4 ? launch_tc_variant<4, false>(op, nkb1, nkb2, s) : launch_tc_variant<2, false>(op, nkb1, nkb2, s);
     g_stats.launches++;
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace mesm
