@@ -75,30 +75,66 @@ def make_workload(cfg, B, seed, device):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region.  In-process NVML queries (no nvidia-smi process per sample: spawning
+    one every 200 ms measurably slowed the step); falls back to nvidia-smi when pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
         self.rows, self.stop, self.index = [], threading.Event(), index
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            return [str(sm), str(self.max_sm)] + ["Active" if mask & bit else "Not Active" for _, bit in self.REASONS]
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        return [c.strip() for c in o.split(",")] if o else None
+
+    def run(self):
         while not self.stop.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
+                r = self.sample()
+                if r:
+                    self.rows.append(r)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05 if self.nvml is not None else 0.5)
 
     def __enter__(self):
-        self.t.start()
+        if not os.environ.get("MESM_NO_CLOCK_SAMPLER"):
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.t.is_alive():
+            self.t.join(timeout=6)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -106,10 +142,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         reasons = set()
         for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+            for (name, _), v in zip(self.REASONS, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_pairs_per_s(cfg_name, state_dict, batch, steps, warmup, threads):
@@ -155,7 +192,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="pairs per GPU per step")
-    ap.add_argument("--chunk-pairs", type=int, default=384)
+    ap.add_argument("--chunk-pairs", type=int, default=0, help="pairs per internal chunk (0 = engine default)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=32)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--e2e-sub", type=int, default=1024, help="pairs per host->device sub-batch of the e2e measurement")

@@ -210,6 +210,7 @@ int mesm_debug_linear(const float* A, const float* Apos, const float* W, const f
     CK(cudaMalloc((void**)&cs, (size_t)N * sizeof(float) + 16));
     CK(launch_transpose_pack(W, 0, N, K, Wt, ldw, Kp, s));
     CK(launch_pack_tc(W, 0, N, K, nullptr, Wp, s));
+    CK(cudaStreamSynchronize(s));      // the tcgen05 kernels fetch weights ahead of their stream predecessors (dependent launch)
     LinearOp op = make_linear(M, N, K, A, lda, Wt, ldw, bias, out, N);
     op.Apos = Apos; op.Wp = Wp; op.act = act; op.prelu = prelu; op.out_scale = out_scale;
     op.residual = residual; op.ldr = N; op.ln_g = ln_g; op.ln_b = ln_b; op.pre_ln = pre_ln;

@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     const int m0 = blockIdx.x * BM, nt = blockIdx.y, n0 = nt * BN;
     const int nkb = nkb1 + nkbp + nkb2;
     const uint32_t cta_rank = PAIR ? (blockIdx.x & 1u) : 0u;      // cluster (2,1,1): rank 0 issues the MMAs of the pair
+    // Every tile walks the K blocks in a different rotation: the CTAs of a wave start together, and without this they
+    // all ask L2 for the same weight lines at the same moment (the first weight block took ~10 k cycles to arrive).
+    const int krot = (int)((blockIdx.x >> (PAIR ? 1 : 0)) % (unsigned)nkb);
+    auto rotk = [&](int it) { const int j = it + krot; return j >= nkb ? j - nkb : j; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -103,6 +107,10 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (threadIdx.x == 0) TSTAMP(1);
+    // Programmatic dependent launch: the next kernel of the stream may start its own set-up (barriers, TMEM, first weight
+    // tiles - none of which depend on this kernel) as soon as every CTA of this grid is resident; it still waits for this
+    // grid to complete before it reads activations (griddepcontrol.wait below, on the same path in that kernel).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===================== weight producer + L2 prefetcher of the activation rows =====================
@@ -123,8 +131,9 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
                 for (int c = 0; c < nn; c += 32) prefetch_l2(r + c);
             }
         }
-        auto prefetch_block = [&](int kb) {
-            if (kb >= nkb) return;
+        auto prefetch_block = [&](int it) {
+            if (it >= nkb) return;
+            const int kb = rotk(it);
             const float* base; int K, k0; bool second = false;
             if (kb < nkb1) { base = op.A; K = op.K; k0 = kb * BK; }
             else if (kb < nkb1 + nkbp) { base = op.Apos; K = op.K; k0 = (kb - nkb1) * BK; }
@@ -146,8 +155,9 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             prefetch_block(kb + PF_DIST);
             if (lane == 0) {
                 mbar_wait(bar_empty + 8 * s, ph ^ 1, 1000 + kb);
-                const int kk = kb < nkb1 ? kb : (kb < nkb1 + nkbp ? kb - nkb1 : kb - nkb1 - nkbp);
-                const uint8_t* src = kb < nkb1 + nkbp
+                const int jb = rotk(kb);
+                const int kk = jb < nkb1 ? jb : (jb < nkb1 + nkbp ? jb - nkb1 : jb - nkb1 - nkbp);
+                const uint8_t* src = jb < nkb1 + nkbp
                                          ? reinterpret_cast<const uint8_t*>(op.Wp) + ((size_t)nt * nkb1 + kk) * (2 * W_TILE)
                                          : reinterpret_cast<const uint8_t*>(op.Wp2) + ((size_t)nt * nkb2 + kk) * (2 * W_TILE);
                 mbar_arrive_expect_tx(bar_full_w + 8 * s, 2 * WT);
@@ -236,6 +246,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
         }
         ln_x[tc] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // everything read from here on may come from the preceding kernel
 
         // Global loads are issued branch-free (clamped addresses, validity applied at conversion time) and TWO K blocks
         // ahead of the block being converted, alternating between two register buffers.
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             return r;
         };
         auto load_block = [&](int kb, float (&dst)[NV * VEC]) {
-            const Src sc = source(kb);
+            const Src sc = source(rotk(kb));
             const int k = sc.k0 + cv * VEC;
             const int kc = (k + VEC <= sc.K) ? k : 0;              // clamped; the K tail is re-read at conversion time
 #pragma unroll
@@ -271,7 +282,7 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
         auto convert_block = [&](int kb, float (&src)[NV * VEC]) {
             const int s = kb % NST;
             const uint32_t ph = (kb / NST) & 1;
-            const Src sc = source(kb);
+            const Src sc = source(rotk(kb));
             const int k = sc.k0 + cv * VEC;
             const int ks = (k + VEC <= sc.K) ? 2 : (k < sc.K ? 1 : 0);
             float cur[NV * VEC];
@@ -566,8 +577,9 @@ bool linear_tc_eligible(const LinearOp& op) {
     return true;
 }
 
-static int g_tc_pair = -1;                         // MESM_TC_PAIR=0 selects the single-CTA kernel (A/B comparisons)
-void tc_set_pair_mode(int on) { g_tc_pair = on; }
+static int g_tc_pdl = 1;         // programmatic dependent launch of the tcgen05 linear kernels (MESM_TC_PDL=0 disables)
+static int g_tc_pair = -1;       // MESM_TC_PAIR: 0 (default) = single-CTA tiles, 1 = CTA pairs, 2 = persistent CTA pairs (linear_tcp.cu)
+void tc_set_pair_mode(int mode) { g_tc_pair = mode; }
 
 template <int VEC, bool PAIR>
 static cudaError_t launch_tc_variant(const LinearOp& op, int nkb1, int nkb2, cudaStream_t s) {
@@ -582,15 +594,19 @@ static cudaError_t launch_tc_variant(const LinearOp& op, int nkb1, int nkb2, cud
     cfg.blockDim = dim3(tc::THREADS, 1, 1);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<VEC, PAIR>, op, nkb1, nkb2);
 }
 
 cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s) {
-    if (g_tc_pair < 0) { const char* e = getenv("MESM_TC_PAIR"); g_tc_pair = (e && e[0] == '0') ? 0 : 1; }
+    if (g_tc_pair < 0) { const char* pe = getenv("MESM_TC_PDL"); if (pe && pe[0] == '0') g_tc_pdl = 0; }
+    if (g_tc_pair < 0) { const char* e = getenv("MESM_TC_PAIR"); g_tc_pair = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }
+    if (g_tc_pair == 2 && linear_tcp_eligible(op)) return launch_linear_tcp(op, s);
     const int nkb1 = (op.K + tc::BK - 1) / tc::BK, nkb2 = op.A2 ? (op.K2 + tc::BK - 1) / tc::BK : 0;
     auto v4 = [](const float* p, int ld, int K) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0) && (K % 4 == 0)); };
     const bool vec4 = v4(op.A, op.lda, op.K) && v4(op.Apos, op.lda, op.K) && v4(op.A2, op.lda2, op.K2);

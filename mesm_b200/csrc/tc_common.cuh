@@ -14,6 +14,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 // Watchdog: a wait that lasts ~2 s records {tag, block, thread, barrier, parity} once and gives up,
 // so that a protocol bug surfaces as a diagnosable wrong answer instead of a hung GPU (host: mesm_debug_watchdog()).
+#ifndef MBAR_SUSPEND_NS
+#define MBAR_SUSPEND_NS 4000u      // try_wait suspend-time hint: a waiting thread sleeps in hardware instead of spinning on issue slots
+#endif
 __device__ unsigned long long g_tc_watchdog[64];      // [0] = number of records; record i at [1 + 3i]: tag, block, thread|parity
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
     uint32_t done = 0;
@@ -22,9 +25,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
         asm volatile(
             "{\n\t"
             ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P1;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
         if (!done && (spins & 255u) == 255u && clock64() - t_start > 4000000000ll) {      // ~2 s
             const unsigned long long slot = atomicAdd(&g_tc_watchdog[0], 1ull);
             if (slot < 21) {
@@ -115,9 +118,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
         asm volatile(
             "{\n\t"
             ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P1;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
         if (!done && (spins & 255u) == 255u && clock64() - t_start > 4000000000ll) {
             const unsigned long long slot = atomicAdd(&g_tc_watchdog[0], 1ull);
             if (slot < 21) {

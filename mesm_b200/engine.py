@@ -46,7 +46,7 @@ class Engine:
     num_recss_layers, n_input_proj, rec_fw, rec_ss, share_MLP, dataset_name, max_words_l, max_video_l.
     """
 
-    def __init__(self, cfg: dict, device=None, chunk_pairs: int = 256):
+    def __init__(self, cfg: dict, device=None, chunk_pairs: int = 0):
         self.lib = _lib.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("mesm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -67,7 +67,10 @@ class Engine:
             self.ctx = self.lib.mesm_create(byref(c), self.device.index or 0)
         if not self.ctx:
             raise RuntimeError("mesm_create failed: " + self.lib.mesm_last_error(None).decode())
-        self.chunk_pairs = int(chunk_pairs)
+        # Pairs per internal chunk.  Large chunks keep the GEMM grids many waves deep (the tiles of a wave drift out of
+        # phase, so one CTA's epilogue overlaps its neighbour's K loop); 0 = auto: ~800 k clip rows per chunk (~20 GB of
+        # workspace at d = 256), i.e. the whole 4096-pair Charades batch.
+        self.chunk_pairs = int(chunk_pairs) if chunk_pairs else max(64, 800_000 // max(1, int(c.max_video_l)))
         self.lib.mesm_set_chunk_pairs(self.ctx, self.chunk_pairs)
         self._ws = None
         self._keep = []          # tensors that must outlive the asynchronous call that uses them

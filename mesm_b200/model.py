@@ -170,7 +170,7 @@ class _EngineBacked(nn.Module):
         eng = getattr(self, "_eng", None)
         if eng is None or self.__dict__.get("_eng_sig") != sig:
             if eng is None or str(eng.device) != str(device):
-                eng = Engine(self._engine_cfg(), device=device, chunk_pairs=self.__dict__.get("chunk_pairs", 256))
+                eng = Engine(self._engine_cfg(), device=device, chunk_pairs=self.__dict__.get("chunk_pairs", 0))
             eng.load_state_dict({self._prefix + k: v for k, v in self.state_dict().items()})
             self.__dict__["_eng"] = eng
             self.__dict__["_eng_sig"] = (str(device), self._weights_signature())
@@ -439,7 +439,7 @@ class MESM(_EngineBacked):
                 dim_feedforward=transformer.dim_feedforward, dropout=transformer.dropout, activation=transformer.activation,
                 normalize_before=transformer.normalize_before)
         self.num_recss_layers = num_recss_layers
-        self.chunk_pairs = 256
+        self.chunk_pairs = 0          # 0 = auto (see Engine)
         self._dataset_name = None
 
     # sub-engines of the child modules are not used by the fused forward: one context holds the whole state_dict
