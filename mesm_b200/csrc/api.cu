@@ -145,6 +145,18 @@ struct Packer {
         const Tensor* b = get(ib, {3 * D});
         L.in_w = W ? W->p : nullptr; L.in_b = b ? b->p : nullptr;
         if (recon) L.vT = L.v.Wt;
+        if (!recon && D == 256 && FF == 1024) {             // fused FFN kernel: weight slots in consumption order
+            const Tensor* W1 = get(p + "linear1.weight", {FF, D});
+            const Tensor* W2 = get(p + "linear2.weight", {D, FF});
+            void *w1 = nullptr, *w2 = nullptr;
+            if (W1 && W2 && cudaMalloc(&w1, ffn_packed_bytes()) == cudaSuccess && cudaMalloc(&w2, ffn_packed_bytes()) == cudaSuccess) {
+                ctx->owned.push_back(w1); ctx->owned.push_back(w2);
+                launch_pack_ffn(W1->p, W2->p, w1, w2, s);
+                L.ffn_w1 = w1; L.ffn_w2 = w2;
+                L.ffn_maps = ffn_make_maps(w1, w2);
+                if (L.ffn_maps) ctx->owned_host.push_back(const_cast<void*>(L.ffn_maps));
+            }
+        }
         return L;
     }
 };
@@ -158,6 +170,24 @@ thread_local std::string g_create_error;
 int fail(mesm_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code ? code : 1;
+}
+
+// FFN block of a layer: out = LN2(res + W2 PReLU(W1 x + b1) + b2).  One fused tcgen05 kernel when the shape allows
+// (MESM_FFN_FUSED=0 keeps the two-GEMM path, which also serves small row counts).
+cudaError_t ffn_block(const AttnFfn& L, int R, const float* x, const float* res, float* H, float* out, int ldo, RowMap omap,
+                      cudaStream_t s) {
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("MESM_FFN_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
+    FfnArgs a;
+    a.X = x; a.ldx = D; a.R = res; a.ldr = D; a.out = out; a.ldo = ldo; a.omap = omap; a.M = R;
+    a.W1f = L.ffn_w1; a.W2f = L.ffn_w2; a.maps = L.ffn_maps; a.b1 = L.l1.bias; a.b2 = L.l2.bias; a.ln_g = L.n2.g; a.ln_b = L.n2.b; a.prelu = L.prelu;
+    if (fused && ffn_fused_eligible(a)) {
+        ProfScope _ps("ffn_fused", s, 4.0 * R * (double)D * FF, R);
+        return launch_ffn_fused(a, s);
+    }
+    MESM_CHECK(Lin(R, L.l1, x, D, H, FF).act(ACT_PRELU, L.prelu).run(s));
+    MESM_CHECK(Lin(R, L.l2, H, FF, out, ldo).omap(omap).res(res, D).ln(L.n2).run(s));
+    return cudaSuccess;
 }
 
 // T2V layer (model/transformer.py:508-540).  txt rows: [Bc*Lk] through tmap; vid rows [Bc*Lq] contiguous.
@@ -180,8 +210,7 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     a.q_scale = kScale32;
     MESM_CHECK(launch_mha_rows(a, s));
     MESM_CHECK(Lin(Rv, L.out, t.AO, D, t.Y1, D).res(vid, D).pre_ln(t.X1).ln(L.n1).run(s));
-    MESM_CHECK(Lin(Rv, L.l1, t.Y1, D, t.H, FF).act(ACT_PRELU, L.prelu).run(s));
-    MESM_CHECK(Lin(Rv, L.l2, t.H, FF, out, ldo).omap(omap).res(t.X1, D).ln(L.n2).run(s));
+    MESM_CHECK(ffn_block(L, Rv, t.Y1, t.X1, t.H, out, ldo, omap, s));
     return cudaSuccess;
 }
 
@@ -197,8 +226,7 @@ cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, cons
     a.q_scale = kScale32;
     MESM_CHECK(launch_mha_rows(a, s));
     MESM_CHECK(Lin(R, L.out, t.AO, D, t.Y1, D).res(src, D).ln(L.n1).run(s));
-    MESM_CHECK(Lin(R, L.l1, t.Y1, D, t.H, FF).act(ACT_PRELU, L.prelu).run(s));
-    MESM_CHECK(Lin(R, L.l2, t.H, FF, out, D).res(t.Y1, D).ln(L.n2).run(s));
+    MESM_CHECK(ffn_block(L, R, t.Y1, t.Y1, t.H, out, D, identity_map(), s));
     return cudaSuccess;
 }
 
@@ -387,6 +415,7 @@ void mesm_destroy(mesm_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (void* p : ctx->owned) cudaFree(p);
+    for (void* p : ctx->owned_host) free(p);
     for (auto& kv : ctx->w) cudaFree(kv.second.p);
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     if (ctx->tab_event) cudaEventDestroy(ctx->tab_event);
@@ -441,6 +470,8 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
     CK(cudaStreamSynchronize(s));                  // previous packed buffers may still be in use
     for (void* p : ctx->owned) cudaFree(p);
     ctx->owned.clear();
+    for (void* p : ctx->owned_host) free(p);
+    ctx->owned_host.clear();
     const mesm_cfg& cf = ctx->cfg;
     Packer P{ctx, s};
     // input projections: LinearLayer.0 = LN(in)->Linear->ReLU (LN folded into the GEMM), LinearLayer.1 = LN(256)->Linear

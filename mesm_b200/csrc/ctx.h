@@ -35,6 +35,9 @@ struct AttnFfn {         // T2V / recon / encoder layer
     const float* vT = nullptr;             // Wv^T packed [256,256] (recon)
     Norm n1, n2;
     const float* prelu = nullptr;
+    const void* ffn_w1 = nullptr;          // fused-FFN weight images (ffn_tc.cu); null when the shape is not 256 / 1024
+    const void* ffn_w2 = nullptr;
+    const void* ffn_maps = nullptr;        // host-side tensor maps of the two images
 };
 
 struct DecLayer {
@@ -59,6 +62,7 @@ struct mesm_ctx {
     std::string missing;               // state_dict keys absent / mis-shaped at the last finalize
     std::unordered_map<std::string, Tensor> w;
     std::vector<void*> owned;
+    std::vector<void*> owned_host;      // malloc'ed host objects (tensor maps)
     bool finalized = false;
     int chunk_pairs = 256;
     long long last_launches = 0;

@@ -72,6 +72,21 @@ cudaError_t launch_ref_update(const float* delta, int ldd, const float* ref, lon
 cudaError_t launch_layernorm_rows(const float* x, long long R, const float* g, const float* b, float* out, cudaStream_t s);
 cudaError_t launch_group_len(const uint8_t* vmask, int Lv, const int* group_start, int G, int* group_len, cudaStream_t s);
 cudaError_t launch_masked_mean_norm(const float* x, const uint8_t* mask, int B, int L, float* out, int ldo, int transposed, cudaStream_t s);
+// Fused FFN block (ffn_tc.cu): out = LN2(R + W2 . PReLU(W1 . X + b1) + b2), d_model 256, hidden 1024, CTA pairs.
+struct FfnArgs {
+    const float* X; int ldx;                 // FFN input rows [M, 256]
+    const float* R; int ldr;                 // residual rows [M, 256]
+    float* out; int ldo; RowMap omap;
+    int M;
+    const void* W1f; const void* W2f;        // launch_pack_ffn images of linear1 / linear2
+    const void* maps;                        // ffn_make_maps(W1f, W2f)
+    const float* b1; const float* b2; const float* ln_g; const float* ln_b; const float* prelu;
+};
+size_t ffn_packed_bytes();
+cudaError_t launch_pack_ffn(const float* W1, const float* W2, void* W1f, void* W2f, cudaStream_t s);
+void* ffn_make_maps(const void* W1f, const void* W2f);      // host object (free() it); null when TMA descriptors are unavailable
+bool ffn_fused_eligible(const FfnArgs& a);
+cudaError_t launch_ffn_fused(const FfnArgs& a, cudaStream_t s);
 cudaError_t launch_fill(float* p, long long n, float v, cudaStream_t s);
 cudaError_t launch_pull_ints(const int* pinned_host_src, int* dst, long long n, cudaStream_t s);
 

@@ -133,6 +133,29 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
     }
 }
 
+// Latency-critical single-thread waits (producer / MMA issuer): plain polling, no suspend-time hint.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int tag = 0, bool cluster = false) {
+    uint32_t done = 0;
+    const long long t_start = clock64();
+    for (uint32_t spins = 0; !done; ++spins) {
+        if (cluster)
+            asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && (spins & 1023u) == 1023u && clock64() - t_start > 4000000000ll) {
+            const unsigned long long slot = atomicAdd(&g_tc_watchdog[0], 1ull);
+            if (slot < 21) {
+                g_tc_watchdog[1 + 3 * slot] = (unsigned long long)tag;
+                g_tc_watchdog[2 + 3 * slot] = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
+                g_tc_watchdog[3 + 3 * slot] = ((unsigned long long)threadIdx.x << 32) | ((unsigned long long)(bar & 0xffffff) << 8) | parity;
+            }
+            return;
+        }
+    }
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     __syncwarp();                       // .sync.aligned: the whole warp must be converged
