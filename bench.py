@@ -71,7 +71,7 @@ def make_workload(cfg, B, seed, device):
     from mesm_b200.model import sample_outclass_neg
     neg = sample_outclass_neg(nct, generator=g)
     return dict(video_feat=video, video_mask=mask, words_feat=words, num_clips=nct, duration=dur.to(device),
-                neg_index=neg.to(device))
+                neg_index=neg.to(device), video_len=vlen.to(torch.int32))       # clip counts stay on the host (collate's `lengths`)
 
 
 class ClockSampler:
@@ -180,7 +180,7 @@ def take_groups(wl, n_pairs):
         k += 1
     from mesm_b200.model import sample_outclass_neg
     sub = dict(video_feat=wl["video_feat"][:tot], video_mask=wl["video_mask"][:tot], words_feat=wl["words_feat"][:tot],
-               num_clips=wl["num_clips"][:k], duration=wl["duration"][:tot])
+               num_clips=wl["num_clips"][:k], duration=wl["duration"][:tot], video_len=wl["video_len"][:tot])
     sub["neg_index"] = sample_outclass_neg(sub["num_clips"], generator=torch.Generator().manual_seed(5))
     return sub
 
@@ -249,9 +249,13 @@ def main():
     lib = _lib.lib()
     from mesm_b200.sharding import gather_topk
 
+    # host clip counts (what the collate step knows): the engine then runs on packed variable-length rows
+    vlen_host = None if os.environ.get("MESM_PADDED_ROWS") else wl["video_len"]
+    config["rows"] = "zero-padded [B, Lv]" if vlen_host is None else "packed variable-length (host clip counts passed as video_len)"
+
     def step():
         out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"],
-                    dataset_name="charades", is_training=False, neg_index=wl["neg_index"])
+                    dataset_name="charades", is_training=False, neg_index=wl["neg_index"], video_len=vlen_host)
         win, order, keep, cnt = mesm_b200.decode_nms(out["pred_logits"], out["pred_spans"], wl["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
         return out, win, order, keep, cnt
@@ -334,16 +338,20 @@ def main():
     sb = take_groups(wl, sub)
     Bs = sb["video_feat"].shape[0]
     host = {k: sb[k].cpu().pin_memory() for k in ("video_feat", "video_mask", "words_feat", "duration", "neg_index")}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    padded = bool(os.environ.get("MESM_E2E_PADDED"))            # A/B switch: plain copy of the zero-padded tensor
     # One context = one compute stream (a mesm_ctx is not re-entrant).  A second stream prefetches the next sub-batch from
     # pinned host memory while the current one is being scored; events order copy -> compute -> buffer reuse.  Steps are
     # streamed back to back (the first sub-batch of step k+1 is prefetched under the last sub-batch of step k).
+    # The host->device step is the drop-in of the reference's prepare_batch_input (dataset/base.py:358): only the valid
+    # clip rows of each pair cross PCIe, the pad rows are zero-filled on the device (mesm_upload_clips).
     comp, copy = torch.cuda.Stream(), torch.cuda.Stream()
     dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
     hkeep = [torch.empty(Bs, 10, dtype=torch.int32).pin_memory() for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
+    h2d_box = [0]
+    vl_box = [None if vlen_host is None else sb["video_len"]]
 
     def e2e_stream(total):
         # Host order matters: a forward enqueues hundreds of launches and the launch queue is finite, so the copy of
@@ -354,9 +362,14 @@ def main():
         def prefetch(i):
             with torch.cuda.stream(copy):
                 copy.wait_event(freed[i % 2])                  # the compute that last read this buffer has finished
-                if not os.environ.get("MESM_E2E_NOCOPY"):
+                if padded:
                     for k, v in host.items():
                         dbuf[i % 2][k].copy_(v, non_blocking=True)
+                    h2d_box[0] = sum(v.numel() * v.element_size() for v in host.values())
+                else:
+                    staged = mesm_b200.prepare_batch_input(dict(host), dev, non_blocking=True, out=dbuf[i % 2])
+                    h2d_box[0] = mesm_b200.prepare_batch_input.last_h2d_bytes
+                    vl_box[0] = None if vlen_host is None else staged["video_len"]
                 ready[i % 2].record(copy)
 
         prefetch(0)
@@ -366,11 +379,8 @@ def main():
                 prefetch(i + 1)
             with torch.cuda.stream(comp):
                 comp.wait_event(ready[i % 2])
-                if os.environ.get("MESM_E2E_NOCOMP"):
-                    freed[i % 2].record(comp)
-                    continue
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
-                          dataset_name="charades", is_training=False, neg_index=d["neg_index"])
+                          dataset_name="charades", is_training=False, neg_index=d["neg_index"], video_len=vl_box[0])
                 w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
                 hres[i % 2].copy_(w, non_blocking=True)
@@ -398,8 +408,8 @@ def main():
     line = {"metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
-            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d * nsub, "d2h_bytes_per_step": d2h * nsub,
-                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream, windows + keep sets back to host"},
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
+                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device'}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MESM_ABI_VERSION 1
+#define MESM_ABI_VERSION 2
 
 typedef struct mesm_ctx mesm_ctx;
 
@@ -75,6 +75,13 @@ typedef struct mesm_inputs {
     const float*   words_feat;     /* dev  [B,Lt,t_feat_dim] — `words_id` of the text_encoder=None path (model.py:160-161) */
     const int64_t* num_clips;      /* HOST [G]  (the reference calls .tolist() on it, model.py:191) */
     const int64_t* neg_index;      /* dev  [B] or NULL: NULL skips the negative branch (model.py:260-302) */
+    const int32_t* video_len;      /* HOST [B] or NULL.  Clip count of every pair, known to the host from the collate
+                                    * step (utils/data_utils.py:64: `lengths`): video_mask[b, i] must be 0 for
+                                    * i >= video_len[b], 1 <= video_len[b] <= Lv.  When given, the forward runs on
+                                    * packed variable-length rows and spends no work on the zero padding; outputs at
+                                    * valid clips are unchanged, row outputs at pad clips (saliency, projed/enhanced
+                                    * video features, memory) are 0 instead of the reference's don't-care values
+                                    * (eval.py:70-72 truncates them).  NULL: every pair is processed at Lv rows. */
 } mesm_inputs;
 
 /* Every pointer may be NULL (that output is then not materialised).  Shapes follow model/model.py:334-351. */
@@ -112,6 +119,18 @@ void mesm_profile_begin(void);
 void mesm_profile_end(double* out7);
 /* per-kernel-class text report of the last profiled region: lines "name<TAB>launches<TAB>ms" */
 const char* mesm_profile_report(void);
+
+/* ---- host -> device ingest of the collated batch ----------------------------------------------------------------- */
+/* replaces the `value.to(device, non_blocking=...)` of `video_feat` / `video_mask` in prepare_batch_input
+ * (dataset/base.py:358-363, called at eval.py:62).  host_feat [B,L,Dv] fp32 and host_mask [B,L] (1 = valid) are HOST
+ * buffers (pinned for asynchronous copies).  Only the valid rows of every pair cross PCIe: the collate function zero-pads
+ * each video to the longest of the batch (utils/data_utils.py:66-82), valid rows are a prefix, and contiguous runs
+ * are merged into one cudaMemcpyAsync each; the mask is copied whole and a kernel zero-fills the rows with mask == 0
+ * on the device, so dev_feat ends up bit-identical to a plain copy of the zero-padded tensor.  (A pair whose mask is
+ * not a prefix is copied whole; its mask == 0 rows are zeroed as well.)  Stream-ordered, no synchronisation;
+ * *bytes_copied (may be NULL) receives the host->device bytes enqueued. */
+int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv,
+                      float* dev_feat, uint8_t* dev_mask, int64_t* bytes_copied, void* stream);
 
 /* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
 /* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),

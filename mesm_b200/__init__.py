@@ -4,5 +4,6 @@ Layout: ``csrc/`` CUDA kernels + C ABI (include/mesm_b200.h) -> ``libmesm_b200.s
 ``engine`` context owner; ``model`` / ``utils`` drop-in mirrors of the reference's Python interface.
 """
 from .engine import Engine, decode_nms, temporal_nms_lists, align_scores  # noqa: F401
+from .ingest import prepare_batch_input, upload_clips  # noqa: F401
 
-__all__ = ["Engine", "decode_nms", "temporal_nms_lists", "align_scores"]
+__all__ = ["Engine", "decode_nms", "temporal_nms_lists", "align_scores", "prepare_batch_input", "upload_clips"]

@@ -193,8 +193,9 @@ cudaError_t ffn_block(const AttnFfn& L, int R, const float* x, const float* res,
 // T2V layer (model/transformer.py:508-540).  txt rows: [Bc*Lk] through tmap; vid rows [Bc*Lq] contiguous.
 cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
-                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q) {
-    const int Rt = Bc * Lk, Rv = Bc * Lq;
+                      const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q, const int* cu,
+                      int Rv_packed, int q_pad_ld) {
+    const int Rt = Bc * Lk, Rv = cu ? Rv_packed : Bc * Lq;
     if (pos_txt) {
         PL kw = L.kv; kw.N = D;
         MESM_CHECK(Lin(Rt, kw, txt, D, t.KV, 2 * D).amap(tmap).apos(pos_txt).run(s));
@@ -208,6 +209,7 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     a.q = t.Q; a.ldq = D; a.k = t.KV; a.ldk = 2 * D; a.v = t.KV + D; a.ldv = 2 * D;
     a.k_pad = k_pad; a.q_pad = q_pad; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = Lq; a.Lk = Lk; a.b0 = b0; a.Btot = Btot;
     a.q_scale = kScale32;
+    a.q_cu = cu; a.q_enc = 0; a.q_pad_ld = q_pad_ld;         // packed clips: pair b's queries are rows cu[b]-cu[0] ...
     MESM_CHECK(launch_mha_rows(a, s));
     MESM_CHECK(Lin(Rv, L.out, t.AO, D, t.Y1, D).res(vid, D).pre_ln(t.X1).ln(L.n1).run(s));
     MESM_CHECK(ffn_block(L, Rv, t.Y1, t.X1, t.H, out, ldo, omap, s));
@@ -216,14 +218,15 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
 
 // Encoder layer (model/transformer.py:637-650) on the [Bc, L1, 256] buffer (L1 = Lv + 1, global token first).
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
-                      const EncBuffers& t, float* out, cudaStream_t s) {
-    const int R = Bc * L1;
+                      const EncBuffers& t, float* out, cudaStream_t s, const int* cu, int R_packed) {
+    const int R = cu ? R_packed : Bc * L1;
     MESM_CHECK(Lin(R, L.qk, src, D, t.QKV, 3 * D).apos(pos).run(s));
     MESM_CHECK(Lin(R, L.v, src, D, t.QKV + 2 * D, 3 * D).run(s));
     MhaRowsArgs a;
     a.q = t.QKV; a.ldq = 3 * D; a.k = t.QKV + D; a.ldk = 3 * D; a.v = t.QKV + 2 * D; a.ldv = 3 * D;
     a.k_pad = pad; a.q_pad = nullptr; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = L1; a.Lk = L1; a.b0 = 0; a.Btot = Bc;
     a.q_scale = kScale32;
+    a.q_cu = cu; a.q_enc = 1; a.k_cu = cu; a.k_enc = 1;      // packed encoder rows (global token + this pair's clips)
     MESM_CHECK(launch_mha_rows(a, s));
     MESM_CHECK(Lin(R, L.out, t.AO, D, t.Y1, D).res(src, D).ln(L.n1).run(s));
     MESM_CHECK(ffn_block(L, R, t.Y1, t.Y1, t.H, out, D, identity_map(), s));
@@ -247,9 +250,9 @@ size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl) {
 cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, const float* posE, const uint8_t* padV, int Lv, int Bc,
                         const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
                         long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
-                        long long refs_layer_stride, cudaStream_t s) {
+                        long long refs_layer_stride, cudaStream_t s, const int* cu, int Re_packed) {
     const int nq = c->cfg.num_queries, nl = c->cfg.dec_layers, L1 = Lv + 1;
-    const int R = Bc * nq, Re = Bc * L1;
+    const int R = Bc * nq, Re = cu ? Re_packed : Bc * L1;
     MESM_CHECK(launch_fill(d.tgtA, (long long)R * D, 0.f, s));                         // tgt = 0 (transformer.py:201)
     MESM_CHECK(launch_dec_init_ref(qembed, Bc, nq, d.refs, s));                       // refs[0] = sigmoid(query_embed)
     float* tgt = d.tgtA;
@@ -292,7 +295,9 @@ cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, 
         MESM_CHECK(Lin(R, L.ca_sine, d.sine_s, D, d.sinep, D).run(s));
         a.q = d.qca; a.q2 = d.sinep; a.ldq2 = D; a.k = d.Kc; a.k2 = d.Kp; a.ldk2 = D; a.v = d.Vd; a.k_pad = padV;
         a.S = Lv; a.scale = kScale64; a.k_bs = L1; a.k_is = 1; a.k_off = 1;
+        a.k_cu = cu; a.k_enc = 1;                            // packed memory: pair b's clips follow its global token
         MESM_CHECK(launch_mha_small(a, s));
+        a.k_cu = nullptr; a.k_enc = 0;
         MESM_CHECK(Lin(R, L.ca_out, d.ao, D, d.t2, D).res(d.t1, D).ln(L.n2).run(s));
         MESM_CHECK(Lin(R, L.l1, d.t2, D, d.hff, FF).act(ACT_PRELU, L.prelu).run(s));
         MESM_CHECK(Lin(R, L.l2, d.hff, FF, tgt_next, D).res(d.t2, D).ln(L.n3).run(s));
@@ -566,6 +571,7 @@ struct FwdPlan {
     float *wn, *wstat, *t1, *expw, *negw, *projV, *recon;
     uint8_t *wmask, *emask, *epad, *wpad, *neg_epad, *neg_wpad, *padV_all;
     int* d_tab;
+    int *t_pad, *t_c2e, *t_g;       // packed-layout gather tables (kernels.h: launch_pack_table / launch_chunk_tables)
     // chunk buffers
     float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2, *Qenh0;
     uint8_t *padV, *padE;
@@ -585,7 +591,8 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.recon = ar.get<float>((size_t)B * D);
     p.wmask = ar.get<uint8_t>(Rt); p.emask = ar.get<uint8_t>(Rte); p.epad = ar.get<uint8_t>(Rte); p.wpad = ar.get<uint8_t>(Rt);
     p.neg_epad = ar.get<uint8_t>(Rte); p.neg_wpad = ar.get<uint8_t>(Rt); p.padV_all = ar.get<uint8_t>((size_t)B * Lv);
-    p.d_tab = ar.get<int>((size_t)2 * B + 2 * (G + 1));
+    p.d_tab = ar.get<int>((size_t)3 * B + 2 * (G + 1) + 2);
+    p.t_pad = ar.get<int>((size_t)B * Lv); p.t_c2e = ar.get<int>((size_t)Bc * Lv); p.t_g = ar.get<int>((size_t)Bc);
     p.vstat = ar.get<float>((size_t)B * Lv * 2); p.v1 = ar.get<float>((size_t)B * Lv * D);
     const int L1 = Lv + 1;
     const size_t Rv = (size_t)Bc * Lv, Re = (size_t)Bc * L1, Rk = (size_t)Bc * (Lt + 1);
@@ -635,7 +642,8 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     for (int g = 0; g < G; ++g) { if (in->num_clips[g] < 1) return fail(ctx, 1, "num_clips entries must be >= 1"); tot += in->num_clips[g]; max_nc = std::max<int>(max_nc, (int)in->num_clips[g]); }
     if (tot != B) return fail(ctx, 1, "sum(num_clips) != B");
     if (in->neg_index && G < 2) return fail(ctx, 1, "the negative branch needs >= 2 video groups (sample_outclass_neg raises in the reference)");
-    const size_t tab_ints = (size_t)2 * B + (G + 1);
+    const bool packed = in->video_len != nullptr;       // variable-length clip rows: no work on the zero padding
+    const size_t tab_ints = (size_t)3 * B + (G + 1) + 1;
     if (ctx->h_tab_cap < tab_ints) {
         if (ctx->tab_event_pending) { CK(cudaEventSynchronize(ctx->tab_event)); ctx->tab_event_pending = false; }
         if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
@@ -644,7 +652,13 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         ctx->h_tab_cap = tab_ints * 2;
     }
     if (ctx->tab_event_pending) { CK(cudaEventSynchronize(ctx->tab_event)); ctx->tab_event_pending = false; }
-    int* h_group = ctx->h_tab; int* h_slot = h_group + B; int* h_gstart = h_slot + B;
+    int* h_group = ctx->h_tab; int* h_slot = h_group + B; int* h_gstart = h_slot + B; int* h_cu = h_gstart + (G + 1);
+    h_cu[0] = 0;
+    for (int b = 0; b < B; ++b) {
+        const int n = packed ? in->video_len[b] : Lv;
+        if (n < 1 || n > Lv) return fail(ctx, 1, "mesm_forward: video_len entries must be in [1, Lv]");
+        h_cu[b + 1] = h_cu[b] + n;
+    }
     std::vector<std::pair<int, int>> chunks;
     {
         // chunks of whole video groups, greedily filled to chunk_pairs; a small tail chunk is re-balanced with its
@@ -672,11 +686,16 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     Arena ar(workspace, workspace_bytes);
     FwdPlan p;
     float* projV_all = out->projed_video_feat;
-    plan_forward(ctx, ar, p, B, Lv, Lt, G, Bc_max, projV_all == nullptr);
+    plan_forward(ctx, ar, p, B, Lv, Lt, G, Bc_max, projV_all == nullptr || packed);
     if (p.total > workspace_bytes)
         return fail(ctx, 1, "mesm_forward: workspace too small: need " + std::to_string(p.total) + " bytes, got " + std::to_string(workspace_bytes));
-    if (!projV_all) projV_all = p.projV;
-    int* d_group = p.d_tab; int* d_slot = d_group + B; int* d_gstart = d_slot + B; int* d_glen = d_gstart + (G + 1);
+    // projV_all: the projected clips in the layout the rest of the forward reads - [B, Lv, 256] zero-padded rows, or
+    // packed rows (pair b at row cu[b]) when the caller passed the clip counts
+    float* projV_padded_out = packed ? projV_all : nullptr;
+    if (!projV_all || packed) projV_all = p.projV;
+    int* d_group = p.d_tab; int* d_slot = d_group + B; int* d_gstart = d_slot + B; int* d_cu_all = d_gstart + (G + 1);
+    int* d_glen = d_cu_all + (B + 1);
+    const int* d_cu = packed ? d_cu_all : nullptr;
     {
         int* h_dev = nullptr;                       // device alias of the pinned table (identical under UVA)
         CK(cudaHostGetDevicePointer((void**)&h_dev, h_group, 0));
@@ -685,6 +704,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     CK(cudaEventRecord(ctx->tab_event, s));
     ctx->tab_event_pending = true;
     if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));
+    if (packed) CK(launch_pack_table(d_cu, B, Lv, p.t_pad, s));
 
     // ---- text side, whole batch (model/model.py:145-152, 167) --------------------------------------------------------
     const int Rt = B * Lt;
@@ -703,18 +723,24 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
 
     // ---- whole batch: input projection of the clips (model/model.py:166) — row-wise, no reason to chunk ---------------
     {
-        const long long Rall = (long long)B * Lv;
+        const long long Rall = packed ? h_cu[B] : (long long)B * Lv;
+        const RowMap inmap = packed ? table_map(p.t_pad) : identity_map();     // packed row -> row of the padded input
         // LayerNorm(Dv) is folded into the GEMM; its row statistics are accumulated by the kernel's operand converters
         // while the features stream through (one pass over the feature bytes - the only HBM-bound stage of the path)
         Lin fused((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D);
-        fused.fold_fused(ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln);
+        fused.amap(inmap).fold_fused(ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln);
         if (linear_tc_eligible(fused.op) && !getenv("MESM_FORCE_SIMT")) {
             CK(fused.run(s));
         } else {
-            CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s));
-            CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+            CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s, packed ? p.t_pad : nullptr));
+            CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).amap(inmap).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
         }
-        CK(Lin((int)Rall, ctx->vid1, p.v1, D, projV_all, D).run(s));
+        Lin second((int)Rall, ctx->vid1, p.v1, D, projV_all, D);
+        if (projV_padded_out) {           // the caller's [B, Lv, 256] output: valid rows scattered, pad rows zero
+            second.op.out2 = projV_padded_out; second.op.ldo2 = D; second.op.o2map = inmap;
+        }
+        CK(second.run(s));
+        if (projV_padded_out) CK(launch_zero_masked_rows(projV_padded_out, in->video_mask, (long long)B * Lv, D, s));
     }
     // ---- whole batch: SS-MESM sentence reconstruction (model/model.py:184-222, 467-488).  One masked sentence slot per
     //      pair -> M = B rows; the per-head back-projections are batched over blockIdx.z. ------------------------------
@@ -732,6 +758,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
             ra.x = projV_all; ra.ldx = D; ra.vmask = in->video_mask; ra.qk = p.rqk; ra.pooled = p.rpool;
             ra.pair_group = d_group; ra.pair_slot = d_slot; ra.group_start = d_gstart; ra.group_len = d_glen;
             ra.B = B; ra.Lv = Lv; ra.qvh = cf.qvh_grouping; ra.max_keys = recon_max_keys; ra.b0 = 0; ra.Btot = B;
+            ra.x_start = d_cu;
             CK(launch_recon_pool(ra, s));
             {   // attn_out[:, h*32:+32] = Wv_h pooled_h + bv_h
                 PL w; w.Wt = L.vT; w.ldw = L.v.ldw; w.K = D; w.N = HD; w.bias = L.v.bias;
@@ -753,10 +780,17 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
 
     // One chunk of whole video groups through enhance -> align -> encoder -> (decoder, heads).
     auto video_chunk = [&](int b0, int b1, bool neg) -> int {
-        const int Bc = b1 - b0, Rv = Bc * Lv, Re = Bc * L1;
+        // Row layout of the chunk: uniform ([Bc, Lv] clips, [Bc, Lv+1] encoder rows) or packed (pair b owns
+        // cu[b+1]-cu[b] clip rows; its encoder rows are those plus a leading global-token row).
+        const int Bc = b1 - b0;
+        const int Rv = packed ? h_cu[b1] - h_cu[b0] : Bc * Lv, Re = Rv + Bc;
+        const int* cu = packed ? d_cu + b0 : nullptr;
+        const long long v0 = packed ? h_cu[b0] : (long long)b0 * Lv;          // first clip row of the chunk in projV_all
+        const RowMap c2e = packed ? table_map(p.t_c2e) : RowMap{Lv, L1, 1};  // clip row -> encoder-buffer row
         const uint8_t* vmask = in->video_mask + (size_t)b0 * Lv;
-        float* projV = projV_all + (size_t)b0 * Lv * D;
-        PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos;
+        float* projV = projV_all + (size_t)v0 * D;
+        if (packed && !neg) CK(launch_chunk_tables(cu, Bc, p.t_c2e, p.t_g, s));
+        PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos; pa.cu = cu;
         pa.posV = p.posV; pa.posE = p.posE; pa.encbuf = p.E; pa.padV = p.padV; pa.padE = p.padE;
         if (neg) { pa.posV = nullptr; pa.posE = nullptr; pa.padV = nullptr; pa.padE = nullptr; }   // positions / pads kept from the main pass
         CK(launch_pos_embed(pa, s));
@@ -765,45 +799,63 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         const uint8_t* wpad_all = neg ? p.neg_wpad : p.wpad;
         // ---- FW-MESM enhance encoder (model/model.py:175-182; neg: 281-286): keys = the Lt projected words ----
         const float* x = projV;
-        float* enh = (!neg && out->enhanced_video_feat) ? out->enhanced_video_feat + (size_t)b0 * Lv * D : p.enh;
+        float* enh_out = (!neg && out->enhanced_video_feat) ? out->enhanced_video_feat + (size_t)b0 * Lv * D : nullptr;
+        float* enh = (enh_out && !packed) ? enh_out : p.enh;
         for (size_t l = 0; l < ctx->enh.size(); ++l) {
             float* dst = (l + 1 == ctx->enh.size()) ? enh : (l % 2 == 0 ? p.xa : p.xb);
             T2VBuffers tb = p.t2v;
             if (l == 0) tb.Q = p.Qenh0;                 // layer 0's Q = (projV + pos) Wq is identical in the negative pass
             CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, tb,
-                         dst, D, identity_map(), s, l == 0 && neg));
+                         dst, D, identity_map(), s, l == 0 && neg, cu, Rv, Lv));
             x = dst;
         }
-        if (ctx->enh.empty() && !neg && out->enhanced_video_feat)
+        if (ctx->enh.empty() && enh_out && !packed)
             CK(cudaMemcpyAsync(enh, projV, (size_t)Rv * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        const float* xin = ctx->enh.empty() ? projV : enh;
+        if (enh_out && packed) {            // the caller's [B, Lv, 256] output: valid rows scattered, pad rows zero
+            CK(launch_copy_rows(xin, D, identity_map(), out->enhanced_video_feat, D, table_map(p.t_pad + v0), Rv, s));
+            CK(launch_zero_masked_rows(enh_out, vmask, (long long)Bc * Lv, D, s));
+        }
         // ---- aligner (model/model.py:230-234; neg: 290-294): keys = recon token + words; last layer writes the
         //      encoder buffer [Bc, Lv+1, 256] behind the global token ----
-        const float* xin = ctx->enh.empty() ? projV : enh;
         for (size_t l = 0; l < ctx->aln.size(); ++l) {
             const bool last = (l + 1 == ctx->aln.size());
             float* dst = last ? p.E : (l % 2 == 0 ? p.xa : p.xb);
             CK(t2v_layer(ctx->aln[l], words_c, identity_map(), nullptr, Lk, xin, p.posV, Lv, Bc, b0, B, p.padV_all, epad_all,
-                         p.t2v, dst, D, last ? RowMap{Lv, L1, 1} : identity_map(), s, false));
+                         p.t2v, dst, D, last ? c2e : identity_map(), s, false, cu, Rv, Lv));
             xin = dst;
         }
         if (ctx->aln.empty())
-            CK(launch_copy_rows(xin, D, identity_map(), p.E, D, RowMap{Lv, L1, 1}, Rv, s));
+            CK(launch_copy_rows(xin, D, identity_map(), p.E, D, c2e, Rv, s));
         // ---- transformer encoder (model/transformer.py:185-197) ----
         float* Ecur = p.E; float* Enext = p.E2;
         for (size_t l = 0; l < ctx->enc.size(); ++l) {
-            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s));
+            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re));
             std::swap(Ecur, Enext);
         }
         // ---- saliency head (model/model.py:301-302) ----
         float* sal = neg ? out->neg_saliency_scores : out->saliency_scores;
         if (sal) {
             CK(Lin(Re, ctx->sal1, Ecur, D, p.P1, D).run(s));
-            CK(Lin(Bc, ctx->sal2, Ecur, L1 * D, p.P2, D).run(s));
-            CK(launch_saliency(p.P1, RowMap{Lv, L1, 1}, p.P2, Bc, Lv, sal + (size_t)b0 * Lv, s));
+            if (packed) {
+                CK(Lin(Bc, ctx->sal2, Ecur, D, p.P2, D).amap(table_map(p.t_g)).run(s));
+                CK(launch_saliency_packed(p.P1, cu, p.P2, Bc, Lv, sal + (size_t)b0 * Lv, s));
+            } else {
+                CK(Lin(Bc, ctx->sal2, Ecur, L1 * D, p.P2, D).run(s));
+                CK(launch_saliency(p.P1, c2e, p.P2, Bc, Lv, sal + (size_t)b0 * Lv, s));
+            }
         }
         if (neg) return 0;
-        if (out->memory) CK(launch_copy_rows(Ecur, D, RowMap{Lv, L1, 1}, out->memory + (size_t)b0 * Lv * D, D, identity_map(), Rv, s));
-        if (out->memory_global) CK(launch_copy_rows(Ecur, D, RowMap{1, L1, 0}, out->memory_global + (size_t)b0 * D, D, identity_map(), Bc, s));
+        if (out->memory) {
+            if (packed) {
+                CK(launch_copy_rows(Ecur, D, c2e, out->memory, D, table_map(p.t_pad + v0), Rv, s));
+                CK(launch_zero_masked_rows(out->memory + (size_t)b0 * Lv * D, vmask, (long long)Bc * Lv, D, s));
+            } else {
+                CK(launch_copy_rows(Ecur, D, c2e, out->memory + (size_t)b0 * Lv * D, D, identity_map(), Rv, s));
+            }
+        }
+        if (out->memory_global)
+            CK(launch_copy_rows(Ecur, D, packed ? table_map(p.t_g) : RowMap{1, L1, 0}, out->memory_global + (size_t)b0 * D, D, identity_map(), Bc, s));
         // ---- DAB-DETR decoder + class / span heads ----
         if (out->pred_logits || out->pred_spans || out->aux_logits || out->aux_spans || out->hs) {
             cudaError_t e = run_decoder(ctx, ctx->qembed, Ecur, p.posE, p.padV, Lv, Bc, p.dec,
@@ -811,7 +863,8 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
                                         out->pred_spans ? out->pred_spans + (size_t)b0 * nq * 2 : nullptr,
                                         out->aux_logits ? out->aux_logits + (size_t)b0 * nq * 2 : nullptr,
                                         out->aux_spans ? out->aux_spans + (size_t)b0 * nq * 2 : nullptr, (long long)B * nq * 2,
-                                        out->hs ? out->hs + (size_t)b0 * nq * D : nullptr, (long long)B * nq * D, nullptr, 0, s);
+                                        out->hs ? out->hs + (size_t)b0 * nq * D : nullptr, (long long)B * nq * D, nullptr, 0, s,
+                                        cu, Re);
             CK(e);
         }
         return 0;

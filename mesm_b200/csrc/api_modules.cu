@@ -20,6 +20,19 @@ __global__ void build_enc_kernel(const float* __restrict__ src, const float* __r
         if (c == 0) padE[(long long)b * (L + 1) + i] = pad[srow];
     }
 }
+
+// Zero the clip rows the ragged upload skipped (pad rows, mask == 0): one CTA per row, 8-byte stores when the pitch allows.
+__global__ void zero_pad_rows_kernel(float* __restrict__ feat, const uint8_t* __restrict__ mask, long long rows, int Dv) {
+    const long long r = blockIdx.x;
+    if (r >= rows || mask[r]) return;
+    float* q = feat + r * (long long)Dv;
+    if ((Dv & 1) == 0 && (reinterpret_cast<uintptr_t>(feat) & 7) == 0) {
+        float2* p = reinterpret_cast<float2*>(q);
+        for (int c = threadIdx.x; c < Dv / 2; c += blockDim.x) p[c] = make_float2(0.f, 0.f);
+    } else {
+        for (int c = threadIdx.x; c < Dv; c += blockDim.x) q[c] = 0.f;
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -46,6 +59,44 @@ int mesm_align_scores(const float* projed_video_feat, const uint8_t* clip_mask, 
     LinearOp op = make_linear(B, B, D, clipn, D, wordsT, Bp, nullptr, scores, B);
     op.out_scale = 1.f / tau;
     CK(launch_linear(op, s));
+    return 0;
+}
+
+int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, float* dev_feat,
+                      uint8_t* dev_mask, int64_t* bytes_copied, void* stream) {
+    mesm_ctx* ctx = nullptr;
+    if (!host_feat || !host_mask || !dev_feat || !dev_mask || B < 1 || L < 1 || Dv < 1) return fail(ctx, 1, "mesm_upload_clips: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t row = (size_t)Dv * sizeof(float);
+    int64_t total = (int64_t)B * L;
+    CK(cudaMemcpyAsync(dev_mask, host_mask, (size_t)B * L, cudaMemcpyHostToDevice, s));
+    // valid rows are a prefix of each pair (utils/data_utils.py:78-82); a pair whose mask is not a prefix is copied whole.
+    // Adjacent spans (a full-length pair followed by the next pair's prefix) are merged into one copy.
+    long long run_start = -1, run_rows = 0;        // in rows of the flat [B*L] row index
+    auto flush = [&]() -> cudaError_t {
+        if (run_rows <= 0) return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(dev_feat + run_start * Dv, host_feat + run_start * Dv, (size_t)run_rows * row, cudaMemcpyHostToDevice, s);
+        total += run_rows * (long long)row;
+        run_rows = 0; run_start = -1;
+        return e;
+    };
+    for (int b = 0; b < B; ++b) {
+        const uint8_t* m = host_mask + (size_t)b * L;
+        int n = 0;
+        while (n < L && m[n]) ++n;
+        for (int j = n; j < L; ++j) if (m[j]) { n = L; break; }
+        const long long first = (long long)b * L;
+        if (run_rows > 0 && run_start + run_rows != first) CK(flush());
+        if (n > 0) {
+            if (run_rows == 0) run_start = first;
+            run_rows += n;
+        }
+        if (n < L) CK(flush());
+    }
+    CK(flush());
+    zero_pad_rows_kernel<<<(unsigned)((long long)B * L), 128, 0, s>>>(dev_feat, dev_mask, (long long)B * L, Dv);
+    CK(cudaGetLastError());
+    if (bytes_copied) *bytes_copied = total;
     return 0;
 }
 

@@ -21,30 +21,33 @@ template <bool QUIRK>
 __global__ void mha_rows_kernel(const MhaRowsArgs a) {
     extern __shared__ float smem[];
     const int h = blockIdx.x, b = blockIdx.y;
-    const int Lk = a.Lk;
+    long long kbase, qbase; int Lk, Lq;
+    pair_rows(a.k_cu, a.k_enc, b, a.Lk, kbase, Lk);       // key rows of this pair (packed layouts: variable count)
+    pair_rows(a.q_cu, a.q_enc, b, a.Lq, qbase, Lq);
+    const int Lkmax = a.Lk;
     // every thread of a warp reads the SAME key row (broadcast): rows stay 16-byte aligned for LDS.128, no padding needed
     float* Ks = smem;                       // [Lk][32]
-    float* Vs = Ks + Lk * 32;               // [Lk][32]
-    uint8_t* pad_own = reinterpret_cast<uint8_t*>(Vs + Lk * 32);     // [Lk]
-    uint8_t* pad_oth = pad_own + Lk;                                  // [Lk]   k_pad of pair b'
+    float* Vs = Ks + Lkmax * 32;            // [Lk][32]
+    uint8_t* pad_own = reinterpret_cast<uint8_t*>(Vs + Lkmax * 32);  // [Lk]
+    uint8_t* pad_oth = pad_own + Lkmax;                               // [Lk]   k_pad of pair b'
     const int bg = a.b0 + b;                                           // global pair index
     const int bp = QUIRK ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
 
     for (int idx = threadIdx.x; idx < Lk * 32; idx += blockDim.x) {
         const int kk = idx >> 5, j = idx & 31;
-        const long long row = (long long)b * Lk + kk;
+        const long long row = kbase + kk;
         Ks[kk * 32 + j] = a.k[row * a.ldk + h * 32 + j];
         Vs[kk * 32 + j] = a.v[row * a.ldv + h * 32 + j];
     }
     for (int kk = threadIdx.x; kk < Lk; kk += blockDim.x) {
-        pad_own[kk] = a.k_pad[(long long)bg * Lk + kk];
-        pad_oth[kk] = QUIRK ? a.k_pad[(long long)bp * Lk + kk] : 0;
+        pad_own[kk] = a.k_pad[(a.k_cu ? kbase : (long long)bg * Lk) + kk];
+        pad_oth[kk] = QUIRK ? a.k_pad[(long long)bp * Lk + kk] : 0;      // the quirk only exists with uniform (text) keys
     }
     __syncthreads();
 
     const int i = threadIdx.x;
-    if (i >= a.Lq) return;
-    const long long qrow = (long long)b * a.Lq + i;
+    if (i >= Lq) return;
+    const long long qrow = qbase + i;
     float q[32], o[32];
     {
         const float4* qp = reinterpret_cast<const float4*>(a.q + qrow * a.ldq + h * 32);
@@ -56,7 +59,7 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = 0.f;
-    const bool qpad_oth = QUIRK ? (a.q_pad[(long long)bp * a.Lq + i] != 0) : false;
+    const bool qpad_oth = QUIRK ? (a.q_pad[(long long)bp * (a.q_pad_ld ? a.q_pad_ld : a.Lq) + i] != 0) : false;
     float m = -CUDART_INF_F, l = 0.f;
 
     for (int k0 = 0; k0 < Lk; k0 += 4) {
@@ -142,11 +145,19 @@ cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s) {
 __global__ void mha_small_kernel(const MhaSmallArgs a) {
     extern __shared__ float smem[];
     const int h = blockIdx.x, b = blockIdx.y;
-    const int L = a.L, S = a.S, hq = a.hq, hv = a.hv;
+    const int L = a.L, hq = a.hq, hv = a.hv;
+    int S = a.S;
+    long long kfirst = (long long)b * a.k_bs + a.k_off, kpad0 = (long long)b * a.S;      // first key row / first k_pad entry
+    if (a.k_cu) {                                                                        // packed keys (kernels.h)
+        const int c0 = a.k_cu[b] - a.k_cu[0];
+        S = a.k_cu[b + 1] - a.k_cu[b];
+        kfirst = (long long)c0 + (a.k_enc ? b : 0) + a.k_off;
+        kpad0 = c0;
+    }
     const int nparts = a.q2 ? 2 : 1;
     const int E = hq * nparts;
     float* Qs = smem;                 // [L][E]
-    float* Sc = Qs + L * E;           // [L][S]
+    float* Sc = Qs + L * E;           // [L][S]  (row pitch = this pair's S)
     for (int idx = threadIdx.x; idx < L * E; idx += blockDim.x) {
         const int i = idx / E, c = idx % E;
         const long long row = (long long)b * a.q_bs + (long long)i * a.q_is;
@@ -156,8 +167,8 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
     __syncthreads();
     // scores: thread per key
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
-        const bool masked = a.k_pad && a.k_pad[(long long)b * S + j];
-        const long long krow = (long long)b * a.k_bs + (long long)j * a.k_is + a.k_off;
+        const bool masked = a.k_pad && a.k_pad[kpad0 + j];
+        const long long krow = kfirst + (long long)j * a.k_is;
         for (int i0 = 0; i0 < L; i0 += 4) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (!masked) {
@@ -195,7 +206,7 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
         for (int j = lane; j < S; j += 32) {
             const float p = row[j] * inv;
             row[j] = p;
-            if (a.attn_w) atomicAdd(a.attn_w + ((long long)b * L + i) * S + j, p / a.nheads);
+            if (a.attn_w) atomicAdd(a.attn_w + ((long long)b * L + i) * a.S + j, p / a.nheads);
         }
     }
     __syncthreads();
@@ -205,7 +216,7 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
         const float* prow = Sc + i * S;
         float acc = 0.f;
         for (int j = 0; j < S; ++j) {
-            const long long vrow = (long long)b * a.k_bs + (long long)j * a.k_is + a.k_off;
+            const long long vrow = kfirst + (long long)j * a.k_is;
             acc = fmaf(prow[j], a.v[vrow * a.ldv + h * hv + c], acc);
         }
         a.out[((long long)b * a.q_bs + (long long)i * a.q_is) * a.ldo + h * hv + c] = acc;
@@ -250,11 +261,11 @@ __global__ void __launch_bounds__(256) recon_pool_kernel(const ReconPoolArgs a) 
             int n = 0;
             for (int p = a.group_start[g]; p < a.group_start[g + 1]; ++p)
                 for (int i = 0; i < Lv; ++i)
-                    if (a.vmask[(long long)p * Lv + i]) krow[n++] = (p - a.b0) * Lv + i;
+                    if (a.vmask[(long long)p * Lv + i]) krow[n++] = a.x_start ? a.x_start[p] + i : (p - a.b0) * Lv + i;
             s_nkeys = n;
         }
     } else {
-        for (int i = threadIdx.x; i < Lv; i += blockDim.x) krow[i] = a.vmask[(long long)b * Lv + i] ? bl * Lv + i : -1;
+        for (int i = threadIdx.x; i < Lv; i += blockDim.x) krow[i] = a.vmask[(long long)b * Lv + i] ? (a.x_start ? a.x_start[b] + i : bl * Lv + i) : -1;
         if (threadIdx.x == 0) s_nkeys = Lv;
     }
     __syncthreads();

@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
     const int bg = a.b0 + b;                                            // global pair index (masks are batch-global)
     const bool quirk = a.q_pad != nullptr;
     const int bp = quirk ? (int)(((long long)bg * NH + h) % a.Btot) : bg;   // T2V attn_mask quirk partner (see attention.cu)
-    const int Lq = a.Lq, Lk = a.Lk;
+    long long kbase, qbase; int Lq, Lk;                                 // rows of this pair (packed layouts: per-pair counts)
+    pair_rows(a.q_cu, a.q_enc, b, a.Lq, qbase, Lq);
+    pair_rows(a.k_cu, a.k_enc, b, a.Lk, kbase, Lk);
+    const long long kpad_own = a.k_cu ? kbase : (long long)bg * Lk;
+    const int q_pad_ld = a.q_pad_ld ? a.q_pad_ld : a.Lq;
     const int Lkp = (Lk + 31) & ~31;
     const int ntiles = (Lq + 127) >> 7;
 
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
                 const int idx = base + u * 256, key = idx >> 3, c4 = idx & 7;
                 kv[u] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u] = kv[u];
                 if (idx < total && key < Lk) {
-                    const long long row = (long long)b * Lk + key;
+                    const long long row = kbase + key;
                     kv[u] = __ldg(reinterpret_cast<const float4*>(a.k + row * a.ldk + h * 32 + c4 * 4));
                     vv[u] = __ldg(reinterpret_cast<const float4*>(a.v + row * a.ldv + h * 32 + c4 * 4));
                 }
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
             for (int c = 0; c < (Lkp >> 5); ++c) {
                 const int k = c * 32 + lane;
                 const int kc = k < Lk ? k : 0;
-                const bool m_own = (k >= Lk) || a.k_pad[(long long)bg * Lk + kc];
+                const bool m_own = (k >= Lk) || a.k_pad[kpad_own + kc];
                 const bool m_oth = quirk && ((k >= Lk) || a.k_pad[(long long)bp * Lk + kc]);
                 const unsigned mo = __ballot_sync(0xffffffffu, m_own), mt = __ballot_sync(0xffffffffu, m_oth);
                 if (lane == 0) { kmask_own[c] = mo; kmask_oth[c] = mt; }
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
                 const int idx = t + 128 * i, row = idx >> 3, c4 = idx & 7;
                 const int qi = tile * 128 + row;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (qi < Lq) q = __ldg(reinterpret_cast<const float4*>(a.q + ((long long)b * Lq + qi) * a.ldq + h * 32 + c4 * 4));
+                if (qi < Lq) q = __ldg(reinterpret_cast<const float4*>(a.q + (qbase + qi) * a.ldq + h * 32 + c4 * 4));
                 const float qq[4] = {q.x * a.q_scale, q.y * a.q_scale, q.z * a.q_scale, q.w * a.q_scale};
                 __nv_bfloat16 qh[4], ql[4];
 #pragma unroll
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
             const uint32_t bar_Pfull = bars + 32 + 16 * wt, bar_Pempty = bars + 64 + 16 * wt;
             const bool wact = tile * 128 + q4 * 32 < Lq;                   // warp has at least one real query row
             const int qi = tile * 128 + row;
-            const bool rflag = quirk && a.q_pad[(long long)bp * Lq + (qi < Lq ? qi : 0)];
+            const bool rflag = quirk && a.q_pad[(long long)bp * q_pad_ld + (qi < Lq ? qi : 0)];
             mbar_wait(bars + 8 * wt, tph, 200 + wt);
             tc_fence_after();
             // pass 1: row maximum over the valid keys
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
                     const int r = 4 * i + rsub;
                     const int qo = tile * 128 + q4 * 32 + r;
                     if (qo < Lq)
-                        *reinterpret_cast<float4*>(a.out + ((long long)b * Lq + qo) * a.ldo + h * 32 + c4) =
+                        *reinterpret_cast<float4*>(a.out + (qbase + qo) * a.ldo + h * 32 + c4) =
                             *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
                 }
             }

@@ -17,12 +17,31 @@ struct RowMap {
     int group;    // rows per group in the logical row index; 0 = identity
     int stride;   // rows between group starts in the buffer
     int offset;   // first row of the group in the buffer
+    const int* table = nullptr;   // device gather table (row r lives at buffer row table[r]); overrides the affine map.
+                                  // Used by the packed (variable-length) clip layout, where pairs have different row counts.
     __host__ __device__ inline long long operator()(int r) const {
+#ifdef __CUDA_ARCH__
+        if (table) return table[r];
+#endif
         if (group == 0) return r;
         int g = r / group;
         return (long long)g * stride + offset + (r - g * group);
     }
 };
+__host__ __device__ static inline RowMap table_map(const int* t) { RowMap m{0, 0, 0}; m.table = t; return m; }
+// Rows of pair b in a packed buffer.  cu = prefix sums of the per-pair clip counts, pointing at the first pair of the
+// chunk (cu[b + 1] - cu[b] clips for pair b); enc = 1: encoder layout, every pair carries one extra leading row (the
+// global token).  cu == nullptr: uniform layout, L rows per pair.
+__device__ __forceinline__ void pair_rows(const int* __restrict__ cu, int enc, int b, int L, long long& start, int& len) {
+    if (cu) {
+        const int c0 = cu[b];
+        start = (long long)(c0 - cu[0]) + (enc ? b : 0);
+        len = cu[b + 1] - c0 + (enc ? 1 : 0);
+    } else {
+        start = (long long)b * L;
+        len = L;
+    }
+}
 __host__ __device__ static inline RowMap identity_map() { return RowMap{0, 0, 0}; }
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_PRELU = 2, ACT_SIGMOID = 3 };

@@ -42,11 +42,12 @@ cudaError_t launch_text_prep(const float* x, int R, int Dt, float* y, uint8_t* m
 }
 
 // ---- LayerNorm statistics of raw feature rows (LinearLayer's LayerNorm(in_hsz), model/model.py:427-431) -----------
-__global__ void row_stats_kernel(const float* __restrict__ x, long long R, int Dv, int ldx, float* __restrict__ rowstat) {
+__global__ void row_stats_kernel(const float* __restrict__ x, long long R, int Dv, int ldx, float* __restrict__ rowstat,
+                                 const int* __restrict__ table) {
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
-    const float* xr = x + r * ldx;
+    const float* xr = x + (table ? (long long)table[r] : r) * ldx;      // table: statistics of gathered rows (packed layout)
     float s = 0.f;
     if ((ldx & 1) == 0 && (Dv & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
         const float2* x2 = reinterpret_cast<const float2*>(xr);
@@ -68,10 +69,10 @@ __global__ void row_stats_kernel(const float* __restrict__ x, long long R, int D
         if (lane == 0) { rowstat[2 * r] = mean; rowstat[2 * r + 1] = rsqrtf(q / Dv + 1e-5f); }
     }
 }
-cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float* rowstat, cudaStream_t s) {
+cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float* rowstat, cudaStream_t s, const int* table) {
     ProfScope _ps("row_stats", s);
     if (R <= 0) return cudaSuccess;
-    row_stats_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, R, Dv, ldx, rowstat);
+    row_stats_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, R, Dv, ldx, rowstat, table);
     LAUNCH_END();
 }
 
@@ -80,34 +81,37 @@ cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float
 // token's flag is 1: model/transformer.py:185-186); tokE row 0 of the [B,Lv+1,256] encoder buffer = global_rep_token.
 __global__ void __launch_bounds__(256) pos_embed_kernel(const PosArgs a) {
     extern __shared__ float xemb[];     // [Lv]
-    const int b = blockIdx.x, Lv = a.Lv;
+    const int b = blockIdx.x;
+    long long vrow0; int Lv;                                   // this pair's clip rows in the (possibly packed) buffers
+    pair_rows(a.cu, 0, b, a.Lv, vrow0, Lv);
+    const long long erow0 = vrow0 + b;                         // its encoder rows: global token first (uniform: b * (Lv + 1))
     if (!a.posV && !a.posE && !a.padV && !a.padE) {          // only the global token row of the encoder buffer
-        if (a.encbuf) a.encbuf[(long long)b * (Lv + 1) * D + threadIdx.x] = a.gtok[threadIdx.x];
+        if (a.encbuf) a.encbuf[erow0 * D + threadIdx.x] = a.gtok[threadIdx.x];
         return;
     }
-    const uint8_t* m = a.vmask + (long long)b * Lv;
+    const uint8_t* m = a.vmask + (long long)b * a.Lv;          // the mask itself is always the zero-padded [B, Lv] array
     for (int i = threadIdx.x; i < Lv; i += blockDim.x) {
         int c = 0;
         for (int j = 0; j <= i; ++j) c += m[j] ? 1 : 0;
         xemb[i] = (float)c;
         const uint8_t pad = m[i] ? 0 : 1;
-        if (a.padV) a.padV[(long long)b * Lv + i] = pad;
-        if (a.padE) a.padE[(long long)b * (Lv + 1) + 1 + i] = pad;
+        if (a.padV) a.padV[vrow0 + i] = pad;
+        if (a.padE) a.padE[erow0 + 1 + i] = pad;
     }
-    if (threadIdx.x == 0 && a.padE) a.padE[(long long)b * (Lv + 1)] = 1;
+    if (threadIdx.x == 0 && a.padE) a.padE[erow0] = 1;
     __syncthreads();
-    const float last = xemb[Lv - 1] + 1e-6f;
+    const float last = (Lv > 0 ? xemb[Lv - 1] : 0.f) + 1e-6f;   // packed: rows past this pair's length hold no valid clip
     const int c = threadIdx.x;          // 256 threads = 256 feature dims
     const float dim_t = powf(10000.f, (float)(2 * (c / 2)) / 256.f);
     for (int i = 0; i < Lv; ++i) {
         const float xe = xemb[i] / last * 6.283185307179586f;
         const float arg = xe / dim_t;
         const float v = (c & 1) ? cosf(arg) : sinf(arg);
-        if (a.posV) a.posV[((long long)b * Lv + i) * D + c] = v;
-        if (a.posE) a.posE[((long long)b * (Lv + 1) + 1 + i) * D + c] = v;
+        if (a.posV) a.posV[(vrow0 + i) * D + c] = v;
+        if (a.posE) a.posE[(erow0 + 1 + i) * D + c] = v;
     }
-    if (a.posE) a.posE[(long long)b * (Lv + 1) * D + c] = a.gpos[c];
-    if (a.encbuf) a.encbuf[(long long)b * (Lv + 1) * D + c] = a.gtok[c];
+    if (a.posE) a.posE[erow0 * D + c] = a.gpos[c];
+    if (a.encbuf) a.encbuf[erow0 * D + c] = a.gtok[c];
 }
 cudaError_t launch_pos_embed(const PosArgs& a, cudaStream_t s) {
     ProfScope _ps("pos_embed", s);
@@ -251,6 +255,63 @@ cudaError_t launch_saliency(const float* p1, RowMap map1, const float* p2, int B
     ProfScope _ps("saliency", s);
     if (B <= 0) return cudaSuccess;
     saliency_kernel<<<blocks_for((long long)B * Lv, 8), 256, 0, s>>>(p1, map1, p2, B, Lv, out);
+    LAUNCH_END();
+}
+
+__global__ void saliency_packed_kernel(const float* __restrict__ p1, const int* __restrict__ cu, const float* __restrict__ p2, int B,
+                                       int Lv, float* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= (long long)B * Lv) return;
+    const int b = (int)(r / Lv), i = (int)(r - (long long)b * Lv);
+    long long e0; int n;
+    pair_rows(cu, 1, b, 0, e0, n);                       // encoder rows of pair b: global token, then n - 1 clips
+    if (i >= n - 1) { if (lane == 0) out[r] = 0.f; return; }
+    const float4* x = reinterpret_cast<const float4*>(p1 + (e0 + 1 + i) * D + lane * 8);
+    const float4* y = reinterpret_cast<const float4*>(p2 + (long long)b * D + lane * 8);
+    const float4 a0 = x[0], a1 = x[1], b0 = y[0], b1 = y[1];
+    float d = a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w + a1.x * b1.x + a1.y * b1.y + a1.z * b1.z + a1.w * b1.w;
+    d = warp_sum(d);
+    if (lane == 0) out[r] = d / 16.f;
+}
+cudaError_t launch_saliency_packed(const float* p1, const int* cu, const float* p2, int B, int Lv, float* out, cudaStream_t s) {
+    ProfScope _ps("saliency", s);
+    if (B <= 0) return cudaSuccess;
+    saliency_packed_kernel<<<blocks_for((long long)B * Lv, 8), 256, 0, s>>>(p1, cu, p2, B, Lv, out);
+    LAUNCH_END();
+}
+
+// ---- packed (variable-length) clip layout: gather tables ------------------------------------------------------------
+__global__ void pack_table_kernel(const int* __restrict__ cu, int Lv, int* __restrict__ t_pad) {
+    const int b = blockIdx.x, c0 = cu[b], n = cu[b + 1] - c0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t_pad[c0 + i] = b * Lv + i;
+}
+cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s) {
+    ProfScope _ps("pack_tables", s);
+    if (B <= 0) return cudaSuccess;
+    pack_table_kernel<<<B, 128, 0, s>>>(cu, Lv, t_pad);
+    LAUNCH_END();
+}
+__global__ void chunk_tables_kernel(const int* __restrict__ cu, int* __restrict__ t_c2e, int* __restrict__ t_g) {
+    const int b = blockIdx.x, c0 = cu[b] - cu[0], n = cu[b + 1] - cu[b];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t_c2e[c0 + i] = c0 + b + 1 + i;
+    if (threadIdx.x == 0) t_g[b] = c0 + b;
+}
+cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s) {
+    ProfScope _ps("pack_tables", s);
+    if (Bc <= 0) return cudaSuccess;
+    chunk_tables_kernel<<<Bc, 128, 0, s>>>(cu, t_c2e, t_g);
+    LAUNCH_END();
+}
+__global__ void zero_masked_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ mask, long long R, int width) {
+    const long long r = (long long)blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (r >= R || mask[r]) return;
+    for (int c = threadIdx.x & 63; c < width; c += 64) x[r * width + c] = 0.f;
+}
+cudaError_t launch_zero_masked_rows(float* x, const uint8_t* mask, long long R, int width, cudaStream_t s) {
+    ProfScope _ps("zero_masked_rows", s);
+    if (R <= 0) return cudaSuccess;
+    zero_masked_rows_kernel<<<blocks_for(R, 4), 256, 0, s>>>(x, mask, R, width);
     LAUNCH_END();
 }
 

@@ -11,9 +11,14 @@ struct MhaRowsArgs {
     const uint8_t* k_pad;
     const uint8_t* q_pad;
     float* out; int ldo;
-    int B, Lq, Lk;
+    int B, Lq, Lk;             // uniform layout: Lq / Lk rows per pair; packed layout: the maxima over the pairs
     int b0, Btot;
     float q_scale;
+    // packed (variable-length) layouts, see pair_rows() in common.cuh; null = uniform.  k_pad is indexed like the key rows
+    // when k_cu is set, else [Btot, Lk] by global pair; q_pad (quirk partner) is always [Btot, q_pad_ld] by global pair.
+    const int* q_cu = nullptr; int q_enc = 0;
+    const int* k_cu = nullptr; int k_enc = 0;
+    int q_pad_ld = 0;          // 0 = Lq
 };
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s);      // dispatcher: tcgen05 kernel when eligible
 bool attn_tc_eligible(const MhaRowsArgs& a);
@@ -30,6 +35,9 @@ struct MhaSmallArgs {
     float scale;
     int q_bs, q_is;            // row of query (b,i) = b*q_bs + i*q_is  (same for out; attn_w is always [B,L,S])
     int k_bs, k_is, k_off;     // row of key/value (b,j) = b*k_bs + j*k_is + k_off
+    // packed keys: pair b owns the S_b = k_cu[b+1]-k_cu[b] key rows (k_cu[b]-k_cu[0]) + b*k_enc + k_off + j; k_pad is then
+    // indexed (k_cu[b]-k_cu[0]) + j.  S stays the maximum over the pairs (shared-memory sizing).
+    const int* k_cu = nullptr; int k_enc = 0;
 };
 cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s);
 
@@ -44,6 +52,7 @@ struct ReconPoolArgs {
     const int* group_len;
     int B, Lv, qvh, max_keys;
     int b0, Btot;
+    const int* x_start = nullptr;   // packed clip rows: pair p's clip i is row x_start[p] + i of x (null: (p - b0) * Lv + i)
 };
 cudaError_t launch_recon_pool(const ReconPoolArgs& a, cudaStream_t s);
 
@@ -51,11 +60,12 @@ struct PosArgs {
     const uint8_t* vmask; int B, Lv;
     const float* gtok; const float* gpos;
     float* posV; float* posE; float* encbuf; uint8_t* padV; uint8_t* padE;
+    const int* cu = nullptr;        // packed layout (pair_rows): clip rows at cu[b]-cu[0], encoder rows at cu[b]-cu[0]+b
 };
 cudaError_t launch_pos_embed(const PosArgs& a, cudaStream_t s);
 
 cudaError_t launch_text_prep(const float* x, int R, int Dt, float* y, uint8_t* mask, float* rowstat, cudaStream_t s);
-cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float* rowstat, cudaStream_t s);
+cudaError_t launch_row_stats(const float* x, long long R, int Dv, int ldx, float* rowstat, cudaStream_t s, const int* table = nullptr);
 cudaError_t launch_invert_mask(const uint8_t* in, uint8_t* out, long long n, cudaStream_t s);
 cudaError_t launch_expand_mask(const uint8_t* wmask, int B, int Lt, uint8_t* emask, uint8_t* epad, uint8_t* wpad, cudaStream_t s);
 cudaError_t launch_expand_mask_from_epad(const uint8_t* epad, int B, int Lt, uint8_t* wpad, cudaStream_t s);
@@ -65,6 +75,14 @@ cudaError_t launch_copy_rows(const float* src, int lds, RowMap imap, float* dst,
 cudaError_t launch_broadcast_row(const float* vec, float* dst, long long R, cudaStream_t s);
 cudaError_t launch_l2norm_rows(const float* x, long long R, float* out1, float* out2, int ld2, RowMap map2, cudaStream_t s);
 cudaError_t launch_saliency(const float* p1, RowMap map1, const float* p2, int B, int Lv, float* out, cudaStream_t s);
+// packed encoder layout: p1 row of (b, i) = cu[b]-cu[0] + b + 1 + i for i < cu[b+1]-cu[b]; out [B, Lv] (0 at the pad clips)
+cudaError_t launch_saliency_packed(const float* p1, const int* cu, const float* p2, int B, int Lv, float* out, cudaStream_t s);
+// packed-layout tables: t_pad[cu[b] + i] = b * Lv + i (packed clip row -> row of the zero-padded [B, Lv] layout)
+cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s);
+// per chunk: t_c2e[r] = encoder-buffer row of packed clip row r; t_g[b] = encoder-buffer row of pair b's global token
+cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s);
+// rows r < R of x [R, width] with mask[r] == 0 are set to zero
+cudaError_t launch_zero_masked_rows(float* x, const uint8_t* mask, long long R, int width, cudaStream_t s);
 cudaError_t launch_dec_init_ref(const float* qe, int B, int nq, float* ref, cudaStream_t s);
 cudaError_t launch_dec_sine(const float* ref, long long R, const float* pos_trans, const float* anchor, float* sine,
                             float* scaled, cudaStream_t s);

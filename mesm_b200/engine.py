@@ -108,9 +108,11 @@ class Engine:
         return self._ws
 
     # ---- forward ---------------------------------------------------------------------------------------------------
-    def forward(self, video_feat, video_mask, words_feat, num_clips, neg_index=None, want=("core",)):
+    def forward(self, video_feat, video_mask, words_feat, num_clips, neg_index=None, want=("core",), video_len=None):
         """MESM.forward in eval mode (model/model.py:154-359).  ``want``: any of "core" (logits, spans, saliency),
-        "aux", "rec" (the rec_ss extras of model.py:342-351), "taps" (memory, memory_global, hs)."""
+        "aux", "rec" (the rec_ss extras of model.py:342-351), "taps" (memory, memory_global, hs).
+        ``video_len``: optional HOST clip counts [B] (list / CPU tensor; ``video_mask[b, i]`` is False for
+        ``i >= video_len[b]``): the forward then runs on packed variable-length rows and does no work on the padding."""
         video_feat = _f32(video_feat, "video_feat")
         words_feat = _f32(words_feat, "words_feat")
         vmask = _u8(video_mask, "video_mask")
@@ -136,7 +138,17 @@ class Engine:
                      expanded_words_mask=torch.empty(B, Lt + 1, dtype=torch.uint8, device=dev))
         if "taps" in want:
             o.update(memory=f(B, Lv, 256), memory_global=f(B, 256), hs=f(nl, B, nq, 256))
-        inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index))
+        vl_arr = None
+        if video_len is not None:
+            if torch.is_tensor(video_len):
+                if video_len.is_cuda:
+                    raise RuntimeError("mesm_b200: `video_len` must live on the host (a device tensor would force a sync)")
+                video_len = video_len.tolist()
+            vl = [int(x) for x in video_len]
+            if len(vl) != B or min(vl) < 1 or max(vl) > Lv:
+                raise RuntimeError("mesm_b200: `video_len` must hold B values in [1, Lv]")
+            vl_arr = (ctypes.c_int32 * B)(*vl)
+        inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index), vl_arr)
         out = MesmOutputs(**{k: _ptr(v) for k, v in o.items()})
         # a video group is never split: the internal chunk must hold the largest group
         self.lib.mesm_set_chunk_pairs(self.ctx, max(self.chunk_pairs, max(nc)))

@@ -1,0 +1,97 @@
+"""Host -> device ingest of a collated batch: drop-in for ``prepare_batch_input`` (dataset/base.py:358-383, called at
+eval.py:62 / train.py:60).
+
+Same name, arguments and in-place semantics as the reference.  The one difference is how ``video_feat`` crosses PCIe:
+the collate function zero-pads every video to the longest of the batch (utils/data_utils.py:66-82), so on ragged
+batches a quarter or more of the padded fp32 tensor is zeros.  ``mesm_upload_clips`` (include/mesm_b200.h) copies only
+the valid prefix rows of each pair and zero-fills the pad rows on the device; the resulting device tensor is
+bit-identical to ``video_feat.to(device)``.  Everything else is a plain ``.to(device, non_blocking=...)``.  The clip
+counts the upload derives from the host mask are kept in the batch as ``video_len`` (host int32[B]); ``MESM.forward``
+picks them up from ``**kwargs`` and runs on packed variable-length rows.
+"""
+import ctypes
+from ctypes import byref, c_int64
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .engine import _ptr, _stream
+
+_SKIP = ("words_weight",)       # stays on the CPU in the reference as well (dataset/base.py:360-361)
+
+
+def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=None):
+    """Ragged upload of host ``video_feat`` f32[B,L,Dv] / ``video_mask`` bool[B,L] on the current stream.
+    Returns (dev_feat, dev_mask, bytes_copied).  Pin the host tensors for the copies to be asynchronous."""
+    if video_feat.is_cuda or video_mask.is_cuda:
+        raise RuntimeError("upload_clips takes host tensors")
+    vf = video_feat.contiguous()
+    if vf.dtype != torch.float32:
+        vf = vf.float()
+    vm = video_mask.contiguous()
+    vm8 = vm.view(torch.uint8) if vm.dtype == torch.bool else (vm != 0).view(torch.uint8)
+    B, L, Dv = vf.shape
+    if out_feat is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        out_feat = torch.empty(B, L, Dv, dtype=torch.float32, device=device)
+    if out_mask is None:
+        out_mask = torch.empty(B, L, dtype=torch.bool, device=out_feat.device)
+    if tuple(out_feat.shape) != (B, L, Dv) or tuple(out_mask.shape) != (B, L) or not out_feat.is_contiguous():
+        raise RuntimeError("upload_clips: output buffers do not match the batch shape")
+    n = c_int64(0)
+    with torch.cuda.device(out_feat.device):
+        check(_lib.lib().mesm_upload_clips(ctypes.c_void_p(vf.data_ptr()), ctypes.c_void_p(vm8.data_ptr()), B, L, Dv,
+                                           _ptr(out_feat), _ptr(out_mask.view(torch.uint8)), byref(n), _stream()))
+    return out_feat, out_mask, int(n.value)
+
+
+def clip_counts(video_mask):
+    """Host clip counts int32[B] of a host mask bool[B, L]: index of the last valid clip + 1 (>= 1), i.e. the `lengths`
+    of the collate step (utils/data_utils.py:64) - what ``Engine.forward(video_len=...)`` expects."""
+    m = video_mask.bool()
+    L = m.shape[1]
+    last = L - torch.flip(m, dims=[1]).to(torch.int8).argmax(dim=1)         # first True from the right
+    last = torch.where(m.any(dim=1), last, torch.ones_like(last))
+    return last.to(torch.int32)
+
+
+def prepare_batch_input(batched_data, device, non_blocking=False, out=None):
+    """dataset/base.py:358-383.  ``out`` (optional): dict of preallocated device tensors to copy into (double buffering);
+    keys missing from it are allocated.  ``prepare_batch_input.last_h2d_bytes`` = host->device bytes this call enqueued."""
+    from .utils import span_xx_to_cxw
+    device = torch.device(device)
+    out = out or {}
+    total = 0
+    ragged = ("video_feat" in batched_data and "video_mask" in batched_data and torch.is_tensor(batched_data["video_feat"])
+              and not batched_data["video_feat"].is_cuda and batched_data["video_feat"].dim() == 3
+              and torch.is_tensor(batched_data["video_mask"]) and not batched_data["video_mask"].is_cuda)
+    if ragged:
+        host_mask = batched_data["video_mask"]
+        f, m, n = upload_clips(batched_data["video_feat"], batched_data["video_mask"], device, out.get("video_feat"),
+                               out.get("video_mask"))
+        batched_data["video_feat"], batched_data["video_mask"] = f, m
+        total += n
+    for key, value in batched_data.items():
+        if key in _SKIP or (ragged and key in ("video_feat", "video_mask")):
+            continue
+        if isinstance(value, torch.Tensor):
+            if not value.is_cuda:
+                total += value.numel() * value.element_size()
+            if key in out:
+                out[key].copy_(value, non_blocking=non_blocking)
+                batched_data[key] = out[key]
+            else:
+                batched_data[key] = value.to(device, non_blocking=non_blocking)
+        if key == "norm_moment":
+            batched_data[key] = [dict(moments=e["moments"].to(device, non_blocking=non_blocking)) for e in value]
+        if key == "norm_span":
+            batched_data[key] = [dict(spans=e["spans"].to(device, non_blocking=non_blocking)) for e in value]
+    if ragged and "video_len" not in batched_data:
+        batched_data["video_len"] = clip_counts(host_mask)        # stays on the host; MESM.forward reads it from **kwargs
+    if "moment" in batched_data and "norm_span" not in batched_data:
+        moment, duration = batched_data["moment"], batched_data["duration"]
+        batched_data["norm_moment"] = moment / duration.unsqueeze(1)
+        batched_data["norm_span"] = span_xx_to_cxw(batched_data["norm_moment"])
+    prepare_batch_input.last_h2d_bytes = total
+    return batched_data

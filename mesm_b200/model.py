@@ -479,7 +479,10 @@ class MESM(_EngineBacked):
         if neg_index is None:
             neg_index = sample_outclass_neg(num_clips)
         want = ("core", "rec", "aux") if self.aux_loss else ("core", "rec")
-        o = eng.forward(video_feat, video_mask, words_feat, num_clips, neg_index=neg_index, want=want)
+        # `video_len` (host clip counts, added to the batch by mesm_b200.prepare_batch_input) switches the engine to packed
+        # variable-length rows; it reaches this forward through **kwargs exactly like the reference's extra batch keys
+        o = eng.forward(video_feat, video_mask, words_feat, num_clips, neg_index=neg_index, want=want,
+                        video_len=kwargs.get("video_len"))
         out = {"pred_logits": o["pred_logits"], "pred_spans": o["pred_spans"], "saliency_scores": o["saliency_scores"],
                "neg_saliency_scores": o["neg_saliency_scores"]}
         if self.aux_loss:

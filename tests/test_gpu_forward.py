@@ -9,21 +9,25 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north star: <= 1e-3 relative (max|a-b| / max|ref|) on logits, spans, saliency
 
 
-def _run(name, chunk_pairs=256):
+def _run(name, chunk_pairs=256, packed=False):
     import mesm_b200
+    from mesm_b200.ingest import clip_counts
     cfg, sd, inp, neg, gold, meta = load_case(name)
     eng = mesm_b200.Engine(engine_cfg(cfg), chunk_pairs=chunk_pairs)
     eng.load_state_dict(sd)
     dev = eng.device
     out = eng.forward(inp["video_feat"].to(dev), inp["video_mask"].to(dev), inp["words_feat"].to(dev), inp["num_clips"],
-                      neg_index=neg.to(dev), want=("core", "aux", "rec", "taps"))
+                      neg_index=neg.to(dev), want=("core", "aux", "rec", "taps"),
+                      video_len=clip_counts(inp["video_mask"]) if packed else None)
     torch.cuda.synchronize()
     return cfg, inp, gold, out
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["padded", "packed"])
 @pytest.mark.parametrize("name", sorted(golden_cases()))
-def test_forward_matches_reference_golden(name):
-    cfg, inp, gold, out = _run(name)
+def test_forward_matches_reference_golden(name, packed):
+    """packed = the host passes the clip counts (video_len) and the forward runs on variable-length rows."""
+    cfg, inp, gold, out = _run(name, packed=packed)
     vm = inp["video_mask"]
     errs = {
         "pred_logits": rel_err(out["pred_logits"], gold["pred_logits"]),
@@ -45,6 +49,24 @@ def test_forward_matches_reference_golden(name):
     sal_h = out["saliency_scores"].half().float().cpu()
     ref_h = torch.from_numpy(gold["saliency_scores"]).half().float()
     assert rel_err(sal_h, ref_h, vm) <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "charades_csf_ragged", "tiny_qvh_groups", "tacos_l96"])
+@pytest.mark.parametrize("chunk_pairs", [256, 3])
+def test_packed_rows_match_padded_rows(name, chunk_pairs):
+    """Variable-length (packed) rows vs zero-padded rows: same numbers at every valid clip, zeros at the pad clips."""
+    _, inp, gold, a = _run(name, chunk_pairs=256, packed=False)
+    _, _, _, b = _run(name, chunk_pairs=chunk_pairs, packed=True)
+    vm = inp["video_mask"]
+    for k in ("pred_logits", "pred_spans", "aux_logits", "aux_spans", "recon_feat", "projed_recon_feat", "memory_global", "hs",
+              "expanded_words_feat"):
+        assert rel_err(b[k], a[k]) < 1e-4, k
+    for k in ("saliency_scores", "neg_saliency_scores"):
+        assert rel_err(b[k], a[k], vm) < 1e-4, k
+        assert float(b[k].cpu()[~vm].abs().max() if (~vm).any() else 0.0) == 0.0, k
+    for k in ("projed_video_feat", "enhanced_video_feat", "memory"):
+        assert rel_err(b[k], a[k], vm[..., None]) < 1e-4, k
+        assert float(b[k].cpu()[~vm].abs().max() if (~vm).any() else 0.0) == 0.0, k
 
 
 @pytest.mark.parametrize("name", ["tiny_ragged", "charades_csf_ragged"])
@@ -70,7 +92,7 @@ def test_repeated_forwards_are_bit_stable_and_watchdog_silent():
     ref = None
     for _ in range(6):
         out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"], dataset_name="charades",
-                    is_training=False, neg_index=wl["neg_index"])
+                    is_training=False, neg_index=wl["neg_index"], video_len=wl["video_len"])
         torch.cuda.synchronize()
         if ref is None:
             ref = {k: out[k].clone() for k in ("pred_logits", "pred_spans", "saliency_scores")}

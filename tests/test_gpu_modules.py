@@ -37,6 +37,12 @@ def test_mesm_module_is_a_drop_in(name):
     out2 = m(inp["video_feat"].cuda(), inp["video_mask"].cuda(), inp["words_feat"].cuda(), None, None, inp["num_clips"],
              dataset_name=cfg.dataset_name, is_training=False)
     assert torch.equal(out2["pred_logits"], out["pred_logits"])                 # independent of the negative draw
+    # host clip counts in the batch (mesm_b200.prepare_batch_input adds them) -> packed rows, same results
+    from mesm_b200.ingest import clip_counts
+    out3 = m(inp["video_feat"].cuda(), inp["video_mask"].cuda(), inp["words_feat"].cuda(), None, None, inp["num_clips"],
+             dataset_name=cfg.dataset_name, is_training=False, neg_index=neg.cuda(), video_len=clip_counts(inp["video_mask"]))
+    assert rel_err(out3["pred_logits"], out["pred_logits"]) < 1e-4 and rel_err(out3["pred_spans"], out["pred_spans"]) < 1e-4
+    assert rel_err(out3["saliency_scores"], out["saliency_scores"], vm) < 1e-4
     with pytest.raises(NotImplementedError):
         m(inp["video_feat"].cuda(), inp["video_mask"].cuda(), inp["words_feat"].cuda(), None, None, inp["num_clips"],
           dataset_name=cfg.dataset_name, is_training=True)
