@@ -313,11 +313,12 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f)["ffn_pair_kernel"]["dram_bytes_per_row"] * B * Lv      # ncu DRAM bytes per row x rows of one launch
+            traffic = json.load(f)["ffn_pair_kernel"]["dram_bytes_per_row"] * (B * Lv if vlen_host is None else int(wl["video_len"].sum()))   # ncu DRAM bytes per row x rows of one launch
     except Exception:
         pass
     if ffn_n:
-        ffn_flops = 4.0 * 256 * 1024 * (8.0 * B * Lv + 4.0 * B * (Lv + 1)) * (ffn_n / 12.0)
+        clip_rows = float(B * Lv) if vlen_host is None else float(wl["video_len"].sum())      # rows the kernels actually process
+        ffn_flops = 4.0 * 256 * 1024 * (8.0 * clip_rows + 4.0 * (clip_rows + B)) * (ffn_n / 12.0)
         ach = ffn_flops / (ffn_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "ffn_pair_kernel (fused FFN block, tcgen05 CTA pairs; bf16x3 = 3 MMAs per algorithmic MAC)",
                 "achieved": ach, "peak": peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback B200_PROFILING.md",
@@ -344,7 +345,10 @@ def main():
     # streamed back to back (the first sub-batch of step k+1 is prefetched under the last sub-batch of step k).
     # The host->device step is the drop-in of the reference's prepare_batch_input (dataset/base.py:358): only the valid
     # clip rows of each pair cross PCIe, the pad rows are zero-filled on the device (mesm_upload_clips).
-    comp, copy = torch.cuda.Stream(), torch.cuda.Stream()
+    # (the copy stream has the higher priority: its one small kernel - the pad-row zero fill - must not queue behind the
+    # compute stream's grids, or the copy engine idles until it has run)
+    comp, copy = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+    shared = not padded and vlen_host is not None and not os.environ.get("MESM_E2E_NO_SHARED")
     dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
     hkeep = [torch.empty(Bs, 10, dtype=torch.int32).pin_memory() for _ in range(2)]
@@ -367,7 +371,8 @@ def main():
                         dbuf[i % 2][k].copy_(v, non_blocking=True)
                     h2d_box[0] = sum(v.numel() * v.element_size() for v in host.values())
                 else:
-                    staged = mesm_b200.prepare_batch_input(dict(host), dev, non_blocking=True, out=dbuf[i % 2])
+                    staged = mesm_b200.prepare_batch_input(dict(host, num_clips=sb["num_clips"]), dev, non_blocking=True, out=dbuf[i % 2],
+                                                           shared_group_video=shared)
                     h2d_box[0] = mesm_b200.prepare_batch_input.last_h2d_bytes
                     vl_box[0] = None if vlen_host is None else staged["video_len"]
                 ready[i % 2].record(copy)
@@ -380,7 +385,8 @@ def main():
             with torch.cuda.stream(comp):
                 comp.wait_event(ready[i % 2])
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
-                          dataset_name="charades", is_training=False, neg_index=d["neg_index"], video_len=vl_box[0])
+                          dataset_name="charades", is_training=False, neg_index=d["neg_index"], video_len=vl_box[0],
+                          shared_group_video=shared)
                 w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
                 hres[i % 2].copy_(w, non_blocking=True)
@@ -409,7 +415,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
-                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device'}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
+                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

@@ -82,6 +82,9 @@ typedef struct mesm_inputs {
                                     * valid clips are unchanged, row outputs at pad clips (saliency, projed/enhanced
                                     * video features, memory) are 0 instead of the reference's don't-care values
                                     * (eval.py:70-72 truncates them).  NULL: every pair is processed at Lv rows. */
+    int32_t shared_group_video;    /* 1: the clips of pair b are read from the FIRST pair of its video group (the
+                                    * charades / tacos collate replicates the video per query, dataset/base.py:307-309;
+                                    * see mesm_upload_clips).  Needs video_len; must be 0 for qvhighlights grouping. */
 } mesm_inputs;
 
 /* Every pointer may be NULL (that output is then not materialised).  Shapes follow model/model.py:334-351. */
@@ -124,13 +127,17 @@ const char* mesm_profile_report(void);
 /* replaces the `value.to(device, non_blocking=...)` of `video_feat` / `video_mask` in prepare_batch_input
  * (dataset/base.py:358-363, called at eval.py:62).  host_feat [B,L,Dv] fp32 and host_mask [B,L] (1 = valid) are HOST
  * buffers (pinned for asynchronous copies).  Only the valid rows of every pair cross PCIe: the collate function zero-pads
- * each video to the longest of the batch (utils/data_utils.py:66-82), valid rows are a prefix, and contiguous runs
- * are merged into one cudaMemcpyAsync each; the mask is copied whole and a kernel zero-fills the rows with mask == 0
- * on the device, so dev_feat ends up bit-identical to a plain copy of the zero-padded tensor.  (A pair whose mask is
- * not a prefix is copied whole; its mask == 0 rows are zeroed as well.)  Stream-ordered, no synchronisation;
- * *bytes_copied (may be NULL) receives the host->device bytes enqueued. */
+ * each video to the longest of the batch (utils/data_utils.py:66-82), so the rows after a pair's last valid clip are
+ * zeros; contiguous runs are merged into one cudaMemcpyAsync each, the mask is copied whole and a kernel zero-fills
+ * the rows with mask == 0 on the device: dev_feat ends up bit-identical to a plain copy of the zero-padded tensor.
+ * num_clips (HOST [G], may be NULL): the charades / tacos collate replicates one video for every query of its group
+ * (dataset/base.py:307-309).  When given, only the FIRST pair of each group is copied; the rows of the other pairs of
+ * the group are left untouched, which is what mesm_forward reads with mesm_inputs.shared_group_video = 1.  Do not pass
+ * it for qvhighlights batches (a group there holds different segments).
+ * Stream-ordered, no synchronisation; *bytes_copied (may be NULL) receives the host->device bytes enqueued. */
 int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv,
-                      float* dev_feat, uint8_t* dev_mask, int64_t* bytes_copied, void* stream);
+                      float* dev_feat, uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied,
+                      void* stream);
 
 /* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
 /* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),

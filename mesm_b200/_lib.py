@@ -21,7 +21,8 @@ class MesmCfg(Structure):
 class MesmInputs(Structure):
     _fields_ = [("B", c_int32), ("Lv", c_int32), ("Lt", c_int32), ("G", c_int32),
                 ("video_feat", c_void_p), ("video_mask", c_void_p), ("words_feat", c_void_p),
-                ("num_clips", POINTER(c_int64)), ("neg_index", c_void_p), ("video_len", POINTER(c_int32))]
+                ("num_clips", POINTER(c_int64)), ("neg_index", c_void_p), ("video_len", POINTER(c_int32)),
+                ("shared_group_video", c_int32)]
 
 
 class MesmOutputs(Structure):
@@ -51,7 +52,8 @@ SYMBOLS = {
     "mesm_profile_begin": (None, []),
     "mesm_profile_end": (None, [POINTER(c_double)]),
     "mesm_profile_report": (c_char_p, []),
-    "mesm_upload_clips": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
+    "mesm_upload_clips": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_int32,
+                                  POINTER(c_int64), c_void_p]),
     "mesm_decode_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(MesmDecodeParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mesm_temporal_nms": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),

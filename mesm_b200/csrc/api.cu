@@ -571,7 +571,7 @@ struct FwdPlan {
     float *wn, *wstat, *t1, *expw, *negw, *projV, *recon;
     uint8_t *wmask, *emask, *epad, *wpad, *neg_epad, *neg_wpad, *padV_all;
     int* d_tab;
-    int *t_pad, *t_c2e, *t_g;       // packed-layout gather tables (kernels.h: launch_pack_table / launch_chunk_tables)
+    int *t_pad, *t_in, *t_c2e, *t_g;   // packed-layout gather tables (kernels.h: launch_pack_table / launch_chunk_tables)
     // chunk buffers
     float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2, *Qenh0;
     uint8_t *padV, *padE;
@@ -592,7 +592,7 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.wmask = ar.get<uint8_t>(Rt); p.emask = ar.get<uint8_t>(Rte); p.epad = ar.get<uint8_t>(Rte); p.wpad = ar.get<uint8_t>(Rt);
     p.neg_epad = ar.get<uint8_t>(Rte); p.neg_wpad = ar.get<uint8_t>(Rt); p.padV_all = ar.get<uint8_t>((size_t)B * Lv);
     p.d_tab = ar.get<int>((size_t)3 * B + 2 * (G + 1) + 2);
-    p.t_pad = ar.get<int>((size_t)B * Lv); p.t_c2e = ar.get<int>((size_t)Bc * Lv); p.t_g = ar.get<int>((size_t)Bc);
+    p.t_pad = ar.get<int>((size_t)B * Lv); p.t_in = ar.get<int>((size_t)B * Lv); p.t_c2e = ar.get<int>((size_t)Bc * Lv); p.t_g = ar.get<int>((size_t)Bc);
     p.vstat = ar.get<float>((size_t)B * Lv * 2); p.v1 = ar.get<float>((size_t)B * Lv * D);
     const int L1 = Lv + 1;
     const size_t Rv = (size_t)Bc * Lv, Re = (size_t)Bc * L1, Rk = (size_t)Bc * (Lt + 1);
@@ -704,7 +704,14 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     CK(cudaEventRecord(ctx->tab_event, s));
     ctx->tab_event_pending = true;
     if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));
+    // t_pad: packed clip row -> this pair's row in the zero-padded [B, Lv] layout (outputs); t_in: the row its features are
+    // read from (the same, or the group's first pair when the collate-replicated video was uploaded once per group)
+    const bool shared_video = in->shared_group_video != 0;
+    if (shared_video && (!packed || cf.qvh_grouping))
+        return fail(ctx, 1, "mesm_forward: shared_group_video needs video_len and the charades / tacos grouping");
+    const int* t_in = shared_video ? p.t_in : p.t_pad;
     if (packed) CK(launch_pack_table(d_cu, B, Lv, p.t_pad, s));
+    if (shared_video) CK(launch_pack_table(d_cu, B, Lv, p.t_in, s, d_group, d_gstart));
 
     // ---- text side, whole batch (model/model.py:145-152, 167) --------------------------------------------------------
     const int Rt = B * Lt;
@@ -724,7 +731,8 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     // ---- whole batch: input projection of the clips (model/model.py:166) — row-wise, no reason to chunk ---------------
     {
         const long long Rall = packed ? h_cu[B] : (long long)B * Lv;
-        const RowMap inmap = packed ? table_map(p.t_pad) : identity_map();     // packed row -> row of the padded input
+        const RowMap inmap = packed ? table_map(t_in) : identity_map();        // packed row -> row of the padded input
+        const RowMap outmap = packed ? table_map(p.t_pad) : identity_map();    // packed row -> row of a padded output
         // LayerNorm(Dv) is folded into the GEMM; its row statistics are accumulated by the kernel's operand converters
         // while the features stream through (one pass over the feature bytes - the only HBM-bound stage of the path)
         Lin fused((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D);
@@ -732,12 +740,12 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         if (linear_tc_eligible(fused.op) && !getenv("MESM_FORCE_SIMT")) {
             CK(fused.run(s));
         } else {
-            CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s, packed ? p.t_pad : nullptr));
+            CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s, packed ? t_in : nullptr));
             CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).amap(inmap).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
         }
         Lin second((int)Rall, ctx->vid1, p.v1, D, projV_all, D);
         if (projV_padded_out) {           // the caller's [B, Lv, 256] output: valid rows scattered, pad rows zero
-            second.op.out2 = projV_padded_out; second.op.ldo2 = D; second.op.o2map = inmap;
+            second.op.out2 = projV_padded_out; second.op.ldo2 = D; second.op.o2map = outmap;
         }
         CK(second.run(s));
         if (projV_padded_out) CK(launch_zero_masked_rows(projV_padded_out, in->video_mask, (long long)B * Lv, D, s));

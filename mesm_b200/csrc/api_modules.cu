@@ -63,15 +63,20 @@ int mesm_align_scores(const float* projed_video_feat, const uint8_t* clip_mask, 
 }
 
 int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, float* dev_feat,
-                      uint8_t* dev_mask, int64_t* bytes_copied, void* stream) {
+                      uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied, void* stream) {
     mesm_ctx* ctx = nullptr;
     if (!host_feat || !host_mask || !dev_feat || !dev_mask || B < 1 || L < 1 || Dv < 1) return fail(ctx, 1, "mesm_upload_clips: bad argument");
+    if (num_clips) {
+        long long tot = 0;
+        for (int g = 0; g < G; ++g) { if (num_clips[g] < 1) return fail(ctx, 1, "mesm_upload_clips: num_clips entries must be >= 1"); tot += num_clips[g]; }
+        if (tot != B) return fail(ctx, 1, "mesm_upload_clips: sum(num_clips) != B");
+    }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t row = (size_t)Dv * sizeof(float);
     int64_t total = (int64_t)B * L;
     CK(cudaMemcpyAsync(dev_mask, host_mask, (size_t)B * L, cudaMemcpyHostToDevice, s));
-    // valid rows are a prefix of each pair (utils/data_utils.py:78-82); a pair whose mask is not a prefix is copied whole.
-    // Adjacent spans (a full-length pair followed by the next pair's prefix) are merged into one copy.
+    // valid rows are a prefix of each pair (utils/data_utils.py:78-82); a pair whose mask is not a prefix is copied up to its
+    // last valid row.  Adjacent spans (a full-length pair followed by the next pair's prefix) are merged into one copy.
     long long run_start = -1, run_rows = 0;        // in rows of the flat [B*L] row index
     auto flush = [&]() -> cudaError_t {
         if (run_rows <= 0) return cudaSuccess;
@@ -80,11 +85,15 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
         run_rows = 0; run_start = -1;
         return e;
     };
+    int g = 0; long long g_first = 0;               // current video group and its first pair
     for (int b = 0; b < B; ++b) {
+        if (num_clips) {
+            while (b >= g_first + num_clips[g]) { g_first += num_clips[g]; ++g; }
+            if (b != g_first) continue;             // shared video: only the group's first pair crosses the bus
+        }
         const uint8_t* m = host_mask + (size_t)b * L;
-        int n = 0;
-        while (n < L && m[n]) ++n;
-        for (int j = n; j < L; ++j) if (m[j]) { n = L; break; }
+        int n = L;
+        while (n > 0 && !m[n - 1]) --n;            // rows up to the last valid one
         const long long first = (long long)b * L;
         if (run_rows > 0 && run_start + run_rows != first) CK(flush());
         if (n > 0) {

@@ -282,14 +282,16 @@ cudaError_t launch_saliency_packed(const float* p1, const int* cu, const float* 
 }
 
 // ---- packed (variable-length) clip layout: gather tables ------------------------------------------------------------
-__global__ void pack_table_kernel(const int* __restrict__ cu, int Lv, int* __restrict__ t_pad) {
+__global__ void pack_table_kernel(const int* __restrict__ cu, int Lv, int* __restrict__ t_pad, const int* __restrict__ pair_group,
+                                  const int* __restrict__ group_start) {
     const int b = blockIdx.x, c0 = cu[b], n = cu[b + 1] - c0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) t_pad[c0 + i] = b * Lv + i;
+    const int src = pair_group ? group_start[pair_group[b]] : b;      // shared group video: read the group's first pair
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t_pad[c0 + i] = src * Lv + i;
 }
-cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s) {
+cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s, const int* pair_group, const int* group_start) {
     ProfScope _ps("pack_tables", s);
     if (B <= 0) return cudaSuccess;
-    pack_table_kernel<<<B, 128, 0, s>>>(cu, Lv, t_pad);
+    pack_table_kernel<<<B, 128, 0, s>>>(cu, Lv, t_pad, pair_group, group_start);
     LAUNCH_END();
 }
 __global__ void chunk_tables_kernel(const int* __restrict__ cu, int* __restrict__ t_c2e, int* __restrict__ t_g) {

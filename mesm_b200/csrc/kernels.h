@@ -77,8 +77,10 @@ cudaError_t launch_l2norm_rows(const float* x, long long R, float* out1, float* 
 cudaError_t launch_saliency(const float* p1, RowMap map1, const float* p2, int B, int Lv, float* out, cudaStream_t s);
 // packed encoder layout: p1 row of (b, i) = cu[b]-cu[0] + b + 1 + i for i < cu[b+1]-cu[b]; out [B, Lv] (0 at the pad clips)
 cudaError_t launch_saliency_packed(const float* p1, const int* cu, const float* p2, int B, int Lv, float* out, cudaStream_t s);
-// packed-layout tables: t_pad[cu[b] + i] = b * Lv + i (packed clip row -> row of the zero-padded [B, Lv] layout)
-cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s);
+// packed-layout tables: t_pad[cu[b] + i] = src(b) * Lv + i (packed clip row -> row of the zero-padded [B, Lv] layout);
+// src(b) = b, or the first pair of b's video group when pair_group / group_start are given
+cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s, const int* pair_group = nullptr,
+                              const int* group_start = nullptr);
 // per chunk: t_c2e[r] = encoder-buffer row of packed clip row r; t_g[b] = encoder-buffer row of pair b's global token
 cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s);
 // rows r < R of x [R, width] with mask[r] == 0 are set to zero

@@ -108,11 +108,14 @@ class Engine:
         return self._ws
 
     # ---- forward ---------------------------------------------------------------------------------------------------
-    def forward(self, video_feat, video_mask, words_feat, num_clips, neg_index=None, want=("core",), video_len=None):
+    def forward(self, video_feat, video_mask, words_feat, num_clips, neg_index=None, want=("core",), video_len=None,
+                shared_group_video=False):
         """MESM.forward in eval mode (model/model.py:154-359).  ``want``: any of "core" (logits, spans, saliency),
         "aux", "rec" (the rec_ss extras of model.py:342-351), "taps" (memory, memory_global, hs).
         ``video_len``: optional HOST clip counts [B] (list / CPU tensor; ``video_mask[b, i]`` is False for
-        ``i >= video_len[b]``): the forward then runs on packed variable-length rows and does no work on the padding."""
+        ``i >= video_len[b]``): the forward then runs on packed variable-length rows and does no work on the padding.
+        ``shared_group_video``: the clips of a pair are read from the first pair of its video group (what
+        ``prepare_batch_input(..., shared_group_video=True)`` uploads for charades / tacos batches); needs ``video_len``."""
         video_feat = _f32(video_feat, "video_feat")
         words_feat = _f32(words_feat, "words_feat")
         vmask = _u8(video_mask, "video_mask")
@@ -148,7 +151,8 @@ class Engine:
             if len(vl) != B or min(vl) < 1 or max(vl) > Lv:
                 raise RuntimeError("mesm_b200: `video_len` must hold B values in [1, Lv]")
             vl_arr = (ctypes.c_int32 * B)(*vl)
-        inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index), vl_arr)
+        inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index), vl_arr,
+                         int(bool(shared_group_video)))
         out = MesmOutputs(**{k: _ptr(v) for k, v in o.items()})
         # a video group is never split: the internal chunk must hold the largest group
         self.lib.mesm_set_chunk_pairs(self.ctx, max(self.chunk_pairs, max(nc)))

@@ -21,9 +21,12 @@ from .engine import _ptr, _stream
 _SKIP = ("words_weight",)       # stays on the CPU in the reference as well (dataset/base.py:360-361)
 
 
-def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=None):
+def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=None, num_clips=None):
     """Ragged upload of host ``video_feat`` f32[B,L,Dv] / ``video_mask`` bool[B,L] on the current stream.
-    Returns (dev_feat, dev_mask, bytes_copied).  Pin the host tensors for the copies to be asynchronous."""
+    Returns (dev_feat, dev_mask, bytes_copied).  Pin the host tensors for the copies to be asynchronous.
+    ``num_clips`` (optional, charades / tacos batches only): the collate step replicates a group's video for each of
+    its queries (dataset/base.py:307-309); only the first pair of every group is then uploaded and the rows of the
+    other pairs are left untouched - to be consumed with ``shared_group_video=True``."""
     if video_feat.is_cuda or video_mask.is_cuda:
         raise RuntimeError("upload_clips takes host tensors")
     vf = video_feat.contiguous()
@@ -40,9 +43,20 @@ def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=No
     if tuple(out_feat.shape) != (B, L, Dv) or tuple(out_mask.shape) != (B, L) or not out_feat.is_contiguous():
         raise RuntimeError("upload_clips: output buffers do not match the batch shape")
     n = c_int64(0)
+    nc_arr, G = None, 0
+    if num_clips is not None:
+        nc = [int(x) for x in (num_clips.tolist() if torch.is_tensor(num_clips) else num_clips)]
+        # cheap guard of the contract: (a slice of) the first and last valid clip of every replicated pair equals its group's first pair
+        first = torch.repeat_interleave(torch.cumsum(torch.tensor([0] + nc[:-1]), 0), torch.tensor(nc))
+        lastrow = (clip_counts(vm) - 1).long()
+        ar = torch.arange(B)
+        if sum(nc) != B or not (torch.equal(vf[ar, 0, :64], vf[first, 0, :64]) and torch.equal(vf[ar, lastrow, -64:], vf[first, lastrow, -64:])
+                                and torch.equal(vm, vm[first])):
+            raise ValueError("upload_clips(num_clips=...): the pairs of a video group do not share one video")
+        nc_arr, G = (c_int64 * len(nc))(*nc), len(nc)
     with torch.cuda.device(out_feat.device):
         check(_lib.lib().mesm_upload_clips(ctypes.c_void_p(vf.data_ptr()), ctypes.c_void_p(vm8.data_ptr()), B, L, Dv,
-                                           _ptr(out_feat), _ptr(out_mask.view(torch.uint8)), byref(n), _stream()))
+                                           _ptr(out_feat), _ptr(out_mask.view(torch.uint8)), nc_arr, G, byref(n), _stream()))
     return out_feat, out_mask, int(n.value)
 
 
@@ -56,9 +70,11 @@ def clip_counts(video_mask):
     return last.to(torch.int32)
 
 
-def prepare_batch_input(batched_data, device, non_blocking=False, out=None):
+def prepare_batch_input(batched_data, device, non_blocking=False, out=None, shared_group_video=False):
     """dataset/base.py:358-383.  ``out`` (optional): dict of preallocated device tensors to copy into (double buffering);
-    keys missing from it are allocated.  ``prepare_batch_input.last_h2d_bytes`` = host->device bytes this call enqueued."""
+    keys missing from it are allocated.  ``shared_group_video=True`` (charades / tacos batches, whose collate replicates
+    the video of a group for each of its queries): every video crosses PCIe once; the batch gets
+    ``shared_group_video=True`` so that ``MESM.forward`` reads the clips of a pair from its group's first pair.  ``prepare_batch_input.last_h2d_bytes`` = host->device bytes this call enqueued."""
     from .utils import span_xx_to_cxw
     device = torch.device(device)
     out = out or {}
@@ -68,8 +84,11 @@ def prepare_batch_input(batched_data, device, non_blocking=False, out=None):
               and torch.is_tensor(batched_data["video_mask"]) and not batched_data["video_mask"].is_cuda)
     if ragged:
         host_mask = batched_data["video_mask"]
+        shared = bool(shared_group_video) and "num_clips" in batched_data
         f, m, n = upload_clips(batched_data["video_feat"], batched_data["video_mask"], device, out.get("video_feat"),
-                               out.get("video_mask"))
+                               out.get("video_mask"), batched_data["num_clips"] if shared else None)
+        if shared:
+            batched_data["shared_group_video"] = True
         batched_data["video_feat"], batched_data["video_mask"] = f, m
         total += n
     for key, value in batched_data.items():

@@ -482,7 +482,7 @@ class MESM(_EngineBacked):
         # `video_len` (host clip counts, added to the batch by mesm_b200.prepare_batch_input) switches the engine to packed
         # variable-length rows; it reaches this forward through **kwargs exactly like the reference's extra batch keys
         o = eng.forward(video_feat, video_mask, words_feat, num_clips, neg_index=neg_index, want=want,
-                        video_len=kwargs.get("video_len"))
+                        video_len=kwargs.get("video_len"), shared_group_video=bool(kwargs.get("shared_group_video", False)))
         out = {"pred_logits": o["pred_logits"], "pred_spans": o["pred_spans"], "saliency_scores": o["saliency_scores"],
                "neg_saliency_scores": o["neg_saliency_scores"]}
         if self.aux_loss:

@@ -69,3 +69,63 @@ def test_prepare_batch_input_is_a_drop_in():
     assert torch.allclose(out["norm_span"].cpu(), cxw, atol=1e-7)
     assert mesm_b200.prepare_batch_input.last_h2d_bytes < sum(v.numel() * v.element_size() for k, v in ref.items()
                                                               if torch.is_tensor(v) and k != "words_weight")
+
+
+def test_upload_clips_shared_group_video():
+    """charades / tacos collate replicates the group's video (dataset/base.py:307-309): with num_clips only the first pair
+    of every group crosses the bus; the other pairs' rows are left untouched."""
+    import mesm_b200
+    nc = [2, 1, 3, 1]
+    B, L, Dv = sum(nc), 9, 18
+    glen = [9, 4, 6, 9]
+    vids = [torch.randn(n, Dv) for n in glen]
+    vf, mask = torch.zeros(B, L, Dv), torch.zeros(B, L, dtype=torch.bool)
+    b, firsts = 0, []
+    for g, n in enumerate(nc):
+        firsts.append(b)
+        for _ in range(n):
+            vf[b, :glen[g]] = vids[g]; mask[b, :glen[g]] = True; b += 1
+    out_f = torch.full((B, L, Dv), 7.0, device="cuda")
+    f, mm, nbytes = mesm_b200.upload_clips(vf.pin_memory(), mask.pin_memory(), out_feat=out_f, num_clips=torch.tensor(nc))
+    torch.cuda.synchronize()
+    fc = f.cpu()
+    assert torch.equal(mm.cpu(), mask)
+    for b in range(B):
+        if b in firsts:
+            assert torch.equal(fc[b], vf[b])
+        else:                                        # untouched valid rows, zero-filled pad rows
+            assert torch.equal(fc[b][mask[b]], torch.full_like(vf[b][mask[b]], 7.0)) and float(fc[b][~mask[b]].abs().sum()) == 0.0
+    assert nbytes == sum(glen) * Dv * 4 + B * L
+    bad = vf.clone(); bad[1, 0, 0] += 1.0            # pair 1 no longer shares pair 0's video
+    with pytest.raises(ValueError):
+        mesm_b200.upload_clips(bad, mask, num_clips=nc)
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "charades_csf_ragged", "tacos_l96", "tiny_twomlp"])
+def test_eval_loop_drop_in_with_shared_upload(name):
+    """eval.py:62-63 with the two drop-ins: prepare_batch_input(batch, device, non_blocking) then model(**batch, ...); the
+    video of a query group is uploaded once, the forward runs on packed rows - results = the reference's golden outputs."""
+    import mesm_b200
+    from mesm_b200.model import build_model
+    from tests.helpers import engine_cfg, load_case, rel_err
+    cfg, sd, inp, neg, gold, meta = load_case(name)
+    model = build_model(engine_cfg(cfg))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    B, L, Dv = inp["video_feat"].shape
+    batch = dict(video_feat=inp["video_feat"].pin_memory(), video_mask=inp["video_mask"].pin_memory(), words_id=inp["words_feat"],
+                 words_mask=None, words_weight=torch.ones(B, inp["words_feat"].shape[1]), num_clips=inp["num_clips"],
+                 duration=inp["duration"], qid=list(range(B)))
+    stale = {"video_feat": torch.full((B, L, Dv), float("nan"), device="cuda")}       # a reused staging buffer
+    mesm_b200.prepare_batch_input(batch, "cuda", non_blocking=True, out=stale, shared_group_video=True)
+    assert batch["shared_group_video"] is True and not batch["video_len"].is_cuda
+    out = model(**batch, dataset_name=cfg.dataset_name, is_training=False, neg_index=neg.cuda())
+    torch.cuda.synchronize()
+    vm = inp["video_mask"]
+    assert rel_err(out["pred_logits"], gold["pred_logits"]) <= 1e-3
+    assert rel_err(out["pred_spans"], gold["pred_spans"]) <= 1e-3
+    assert rel_err(out["saliency_scores"], gold["saliency_scores"], vm) <= 1e-3
+    assert rel_err(out["neg_saliency_scores"], gold["neg_saliency_scores"], vm) <= 1e-3
+    assert rel_err(out["recon_feat"], gold["recon_feat"]) <= 1e-3
+    assert rel_err(out["projed_video_feat"][:, 0], gold["projed_video_row0"]) <= 1e-3
+    assert not torch.isnan(out["projed_video_feat"]).any() and not torch.isnan(out["enhanced_video_feat"]).any()
