@@ -80,9 +80,10 @@ class ClockSampler:
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.rows, self.stop, self.index, self.query_s = [], threading.Event(), index, []
         self.t = threading.Thread(target=self.run, daemon=True)
         self.nvml = None
+        self.interval = float(os.environ.get("MESM_CLOCK_SAMPLE_S", "0.1"))     # every NVML query briefly stalls kernel submission
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -104,11 +105,13 @@ class ClockSampler:
     def sample(self):
         if self.nvml is not None:
             n = self.nvml
+            t0 = time.perf_counter()
             sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
             try:
                 mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
                 mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.query_s.append(time.perf_counter() - t0)
             return [str(sm), str(self.max_sm)] + ["Active" if mask & bit else "Not Active" for _, bit in self.REASONS]
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -124,7 +127,7 @@ class ClockSampler:
                     self.rows.append(r)
             except Exception:
                 pass
-            self.stop.wait(0.05 if self.nvml is not None else 0.5)
+            self.stop.wait(self.interval if self.nvml is not None else 0.5)
 
     def __enter__(self):
         if not os.environ.get("MESM_NO_CLOCK_SAMPLER"):
@@ -145,8 +148,11 @@ class ClockSampler:
             for (name, _), v in zip(self.REASONS, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons), "samples": len(sm),
+               "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+        if self.query_s:
+            out["query_ms_mean"] = 1e3 * sum(self.query_s) / len(self.query_s)
+        return out
 
 
 def cpu_reference_pairs_per_s(cfg_name, state_dict, batch, steps, warmup, threads):
@@ -195,7 +201,7 @@ def main():
     ap.add_argument("--chunk-pairs", type=int, default=0, help="pairs per internal chunk (0 = engine default)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=32)
     ap.add_argument("--topk", type=int, default=100)
-    ap.add_argument("--e2e-sub", type=int, default=1024, help="pairs per host->device sub-batch of the e2e measurement")
+    ap.add_argument("--e2e-sub", type=int, default=2048, help="pairs per host->device sub-batch of the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -262,7 +268,9 @@ def main():
 
     _v = lambda m: print(f"[bench] {m}", file=sys.stderr, flush=True) if os.environ.get("MESM_BENCH_VERBOSE") else None
     for _ in range(args.warmup):
-        step()
+        o_w = step()
+    gather_topk(o_w[1], wl["num_clips"], args.topk, rank, world, B)     # first use of the sort kernels / NCCL communicator
+    del o_w
     torch.cuda.synchronize()
     _v("warmup done")
     if dist:
@@ -272,9 +280,12 @@ def main():
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
         ev0.record()
+        step_ev = [ev0]
         for _ in range(args.steps):
             out, win, order, keep, cnt = step()
             launches += model._eng.last_launch_count + 1
+            step_ev.append(torch.cuda.Event(enable_timing=True))
+            step_ev[-1].record()
         top = gather_topk(win, wl["num_clips"], args.topk, rank, world, B)      # one NCCL all_gather of top-k spans
         ev1.record()
         torch.cuda.synchronize()
@@ -282,6 +293,7 @@ def main():
         dist.barrier()
     _v("timed region done")
     ms = ev0.elapsed_time(ev1)
+    each_ms = [round(a.elapsed_time(b), 2) for a, b in zip(step_ev[:-1], step_ev[1:])]
     t = torch.tensor([ms], device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,10 +301,15 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- roofline of the dominant kernel (fused linear): one extra step with CUDA events around each launch ----------
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib.mesm_profile_begin()
+    pe0.record()
     step()
+    pe1.record()
     prof = (ctypes.c_double * 7)()
     lib.mesm_profile_end(prof)
+    torch.cuda.synchronize()
+    profile_step_ms = pe0.elapsed_time(pe1)
     _v("profile step done")
     if os.environ.get("MESM_PROFILE_REPORT"):
         rep = sorted((l.split("\t") for l in lib.mesm_profile_report().decode().strip().split("\n")), key=lambda r: -float(r[2]))
@@ -330,6 +347,8 @@ def main():
     roof["all_gemm_launches"] = {"achieved": lin_flops / (lin_ms * 1e-3) / 1e12 if lin_ms else None,
                                  "frac": (lin_flops / (lin_ms * 1e-3) / 1e12 / peak_tf) if lin_ms else None,
                                  "launches_per_step": int(prof[3]), "kernel_ms_per_step": lin_ms, "share_of_step": lin_ms / step_ms}
+    roof["profiled_step_ms"] = profile_step_ms
+    roof["profiled_kernels_ms"] = sum(v[1] for v in rep_rows.values())
     roof["hbm_frac_whole_step"] = (ALGO_BYTES_PER_PAIR * B / (step_ms * 1e-3)) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))
 
     # ---- e2e: same work through the public API from pinned host memory, sub-batches double-buffered over two streams -----
@@ -377,11 +396,15 @@ def main():
                     vl_box[0] = None if vlen_host is None else staged["video_len"]
                 ready[i % 2].record(copy)
 
+        trace = [] if os.environ.get("MESM_E2E_TRACE") else None
+        t_host0 = time.perf_counter()
         prefetch(0)
         for i in range(total):
             d = dbuf[i % 2]
+            th = time.perf_counter()
             if i + 1 < total:
                 prefetch(i + 1)
+            th1 = time.perf_counter()
             with torch.cuda.stream(comp):
                 comp.wait_event(ready[i % 2])
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
@@ -392,8 +415,15 @@ def main():
                 hres[i % 2].copy_(w, non_blocking=True)
                 hkeep[i % 2].copy_(kp, non_blocking=True)
                 freed[i % 2].record(comp)
+                if trace is not None:
+                    e = torch.cuda.Event(enable_timing=True); e.record(comp)
+                    trace.append((e, th - t_host0, th1 - th, time.perf_counter() - th1))
         comp.synchronize()
         copy.synchronize()
+        if trace:
+            for j in range(1, len(trace)):
+                print(f"[e2e] sub {j}: gpu period {trace[j - 1][0].elapsed_time(trace[j][0]):7.2f} ms  host: t={trace[j][1] * 1e3:7.1f} "
+                      f"prefetch {trace[j][2] * 1e3:6.2f} ms forward {trace[j][3] * 1e3:6.2f} ms", file=sys.stderr)
 
     d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
     e2e_stream(nsub)
@@ -412,7 +442,7 @@ def main():
     e2e_val = world * Bs * nsub * e2e_steps / float(t)
 
     line = {"metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
                     "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},

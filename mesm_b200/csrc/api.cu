@@ -194,7 +194,7 @@ cudaError_t ffn_block(const AttnFfn& L, int R, const float* x, const float* res,
 cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
                       const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q, const int* cu,
-                      int Rv_packed, int q_pad_ld) {
+                      int Rv_packed, int q_pad_ld, const float* posW, const int* t_pos) {
     const int Rt = Bc * Lk, Rv = cu ? Rv_packed : Bc * Lq;
     if (pos_txt) {
         PL kw = L.kv; kw.N = D;
@@ -204,7 +204,11 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     } else {
         MESM_CHECK(Lin(Rt, L.kv, txt, D, t.KV, 2 * D).amap(tmap).run(s));
     }
-    if (!reuse_q) MESM_CHECK(Lin(Rv, L.q, vid, D, t.Q, D).apos(pos_vid).run(s));      // Q depends on the clips only
+    if (!reuse_q) {                                                                     // Q depends on the clips only
+        Lin q(Rv, L.q, vid, D, t.Q, D);
+        if (posW) q.res(posW, D, table_map(t_pos)); else q.apos(pos_vid);             // (x + pos) Wq = x Wq + (pos Wq)[table]
+        MESM_CHECK(q.run(s));
+    }
     MhaRowsArgs a;
     a.q = t.Q; a.ldq = D; a.k = t.KV; a.ldk = 2 * D; a.v = t.KV + D; a.ldv = 2 * D;
     a.k_pad = k_pad; a.q_pad = q_pad; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = Lq; a.Lk = Lk; a.b0 = b0; a.Btot = Btot;
@@ -218,9 +222,14 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
 
 // Encoder layer (model/transformer.py:637-650) on the [Bc, L1, 256] buffer (L1 = Lv + 1, global token first).
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
-                      const EncBuffers& t, float* out, cudaStream_t s, const int* cu, int R_packed) {
+                      const EncBuffers& t, float* out, cudaStream_t s, const int* cu, int R_packed, const float* posW,
+                      const int* t_pos) {
     const int R = cu ? R_packed : Bc * L1;
-    MESM_CHECK(Lin(R, L.qk, src, D, t.QKV, 3 * D).apos(pos).run(s));
+    {
+        Lin qk(R, L.qk, src, D, t.QKV, 3 * D);
+        if (posW) qk.res(posW, 2 * D, table_map(t_pos)); else qk.apos(pos);
+        MESM_CHECK(qk.run(s));
+    }
     MESM_CHECK(Lin(R, L.v, src, D, t.QKV + 2 * D, 3 * D).run(s));
     MhaRowsArgs a;
     a.q = t.QKV; a.ldq = 3 * D; a.k = t.QKV + D; a.ldk = 3 * D; a.v = t.QKV + 2 * D; a.ldv = 3 * D;
@@ -250,7 +259,8 @@ size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl) {
 cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, const float* posE, const uint8_t* padV, int Lv, int Bc,
                         const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
                         long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
-                        long long refs_layer_stride, cudaStream_t s, const int* cu, int Re_packed) {
+                        long long refs_layer_stride, cudaStream_t s, const int* cu, int Re_packed, const float* const* posWkp,
+                        const int* t_posE) {
     const int nq = c->cfg.num_queries, nl = c->cfg.dec_layers, L1 = Lv + 1;
     const int R = Bc * nq, Re = cu ? Re_packed : Bc * L1;
     MESM_CHECK(launch_fill(d.tgtA, (long long)R * D, 0.f, s));                         // tgt = 0 (transformer.py:201)
@@ -285,19 +295,21 @@ cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, 
         // cross-attention into the encoder memory
         if (lid == 0) {
             MESM_CHECK(Lin(R, L.ca_qc, d.t1, D, d.qca, D).second(d.qpos, D, L.ca_qp).bias(L.ca_q_bias0).run(s));
-            MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).second(posE, D, L.ca_kp).bias(L.ca_k_bias0).run(s));
+            if (posWkp) MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).res(posWkp[0], D, table_map(t_posE)).run(s));   // k_content + k_pos
+            else MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).second(posE, D, L.ca_kp).bias(L.ca_k_bias0).run(s));
         } else {
             MESM_CHECK(Lin(R, L.ca_qc, d.t1, D, d.qca, D).run(s));
             MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).run(s));
         }
-        MESM_CHECK(Lin(Re, L.ca_kp, posE, D, d.Kp, D).run(s));
+        if (!posWkp) MESM_CHECK(Lin(Re, L.ca_kp, posE, D, d.Kp, D).run(s));          // else: rows of the position table product
         MESM_CHECK(Lin(Re, L.ca_v, E, D, d.Vd, D).run(s));
         MESM_CHECK(Lin(R, L.ca_sine, d.sine_s, D, d.sinep, D).run(s));
-        a.q = d.qca; a.q2 = d.sinep; a.ldq2 = D; a.k = d.Kc; a.k2 = d.Kp; a.ldk2 = D; a.v = d.Vd; a.k_pad = padV;
+        a.q = d.qca; a.q2 = d.sinep; a.ldq2 = D; a.k = d.Kc; a.k2 = posWkp ? posWkp[lid] : d.Kp; a.ldk2 = D; a.v = d.Vd; a.k_pad = padV;
+        a.k2_table = posWkp ? t_posE : nullptr;
         a.S = Lv; a.scale = kScale64; a.k_bs = L1; a.k_is = 1; a.k_off = 1;
         a.k_cu = cu; a.k_enc = 1;                            // packed memory: pair b's clips follow its global token
         MESM_CHECK(launch_mha_small(a, s));
-        a.k_cu = nullptr; a.k_enc = 0;
+        a.k_cu = nullptr; a.k_enc = 0; a.k2_table = nullptr;
         MESM_CHECK(Lin(R, L.ca_out, d.ao, D, d.t2, D).res(d.t1, D).ln(L.n2).run(s));
         MESM_CHECK(Lin(R, L.l1, d.t2, D, d.hff, FF).act(ACT_PRELU, L.prelu).run(s));
         MESM_CHECK(Lin(R, L.l2, d.hff, FF, tgt_next, D).res(d.t2, D).ln(L.n3).run(s));
@@ -412,7 +424,7 @@ mesm_ctx* mesm_create(const mesm_cfg* cfg, int device) {
     mesm_ctx* c = new mesm_ctx();
     c->cfg = *cfg;
     c->device = device;
-    cudaEventCreateWithFlags(&c->tab_event, cudaEventDisableTiming);
+    for (int i = 0; i < mesm_ctx::kTabSlots; ++i) cudaEventCreateWithFlags(&c->tab_event[i], cudaEventDisableTiming);
     return c;
 }
 
@@ -422,8 +434,10 @@ void mesm_destroy(mesm_ctx* ctx) {
     for (void* p : ctx->owned) cudaFree(p);
     for (void* p : ctx->owned_host) free(p);
     for (auto& kv : ctx->w) cudaFree(kv.second.p);
-    if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
-    if (ctx->tab_event) cudaEventDestroy(ctx->tab_event);
+    for (int i = 0; i < mesm_ctx::kTabSlots; ++i) {
+        if (ctx->h_tab[i]) cudaFreeHost(ctx->h_tab[i]);
+        if (ctx->tab_event[i]) cudaEventDestroy(ctx->tab_event[i]);
+    }
     delete ctx;
 }
 
@@ -571,7 +585,7 @@ struct FwdPlan {
     float *wn, *wstat, *t1, *expw, *negw, *projV, *recon;
     uint8_t *wmask, *emask, *epad, *wpad, *neg_epad, *neg_wpad, *padV_all;
     int* d_tab;
-    int *t_pad, *t_in, *t_c2e, *t_g;   // packed-layout gather tables (kernels.h: launch_pack_table / launch_chunk_tables)
+    int *t_pad, *t_in, *t_c2e, *t_g, *t_posV, *t_posE;   // packed-layout gather tables (kernels.h: launch_pack_table / launch_chunk_tables)
     // chunk buffers
     float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2, *Qenh0;
     uint8_t *padV, *padE;
@@ -579,6 +593,7 @@ struct FwdPlan {
     EncBuffers encb;
     DecBuffers dec;
     float *rS, *rS2, *rq, *rqk, *rpool, *rao, *rX1, *rY1, *rH, *rtmp;
+    float *PT, *PWq, *PWqk, *PWkp;
     size_t total = 0;
 };
 
@@ -591,7 +606,15 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.recon = ar.get<float>((size_t)B * D);
     p.wmask = ar.get<uint8_t>(Rt); p.emask = ar.get<uint8_t>(Rte); p.epad = ar.get<uint8_t>(Rte); p.wpad = ar.get<uint8_t>(Rt);
     p.neg_epad = ar.get<uint8_t>(Rte); p.neg_wpad = ar.get<uint8_t>(Rt); p.padV_all = ar.get<uint8_t>((size_t)B * Lv);
-    p.d_tab = ar.get<int>((size_t)3 * B + 2 * (G + 1) + 2);
+    p.d_tab = ar.get<int>((size_t)3 * B + 2 * (G + 1) + 2 + 3 * (size_t)Lv + 2);
+    p.t_posV = ar.get<int>((size_t)Bc * Lv); p.t_posE = ar.get<int>((size_t)Bc * (Lv + 1));
+    {   // position table and its products with every projection that consumes positions (packed layout only)
+        const size_t nPT = 1 + std::min<size_t>((size_t)Lv * (Lv + 1) / 2, (size_t)B * Lv);
+        p.PT = ar.get<float>(nPT * D);
+        p.PWq = ar.get<float>(nPT * D * (c->enh.size() + c->aln.size() + 1));
+        p.PWqk = ar.get<float>(nPT * 2 * D * (c->enc.size() + 1));
+        p.PWkp = ar.get<float>(nPT * D * (c->dec.size() + 1));
+    }
     p.t_pad = ar.get<int>((size_t)B * Lv); p.t_in = ar.get<int>((size_t)B * Lv); p.t_c2e = ar.get<int>((size_t)Bc * Lv); p.t_g = ar.get<int>((size_t)Bc);
     p.vstat = ar.get<float>((size_t)B * Lv * 2); p.v1 = ar.get<float>((size_t)B * Lv * D);
     const int L1 = Lv + 1;
@@ -643,22 +666,33 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     if (tot != B) return fail(ctx, 1, "sum(num_clips) != B");
     if (in->neg_index && G < 2) return fail(ctx, 1, "the negative branch needs >= 2 video groups (sample_outclass_neg raises in the reference)");
     const bool packed = in->video_len != nullptr;       // variable-length clip rows: no work on the zero padding
-    const size_t tab_ints = (size_t)3 * B + (G + 1) + 1;
-    if (ctx->h_tab_cap < tab_ints) {
-        if (ctx->tab_event_pending) { CK(cudaEventSynchronize(ctx->tab_event)); ctx->tab_event_pending = false; }
-        if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
-        ctx->h_tab = nullptr; ctx->h_tab_cap = 0;
-        CK(cudaMallocHost((void**)&ctx->h_tab, tab_ints * 2 * sizeof(int)));
-        ctx->h_tab_cap = tab_ints * 2;
+    const size_t tab_ints = (size_t)3 * B + (G + 1) + 1 + 3 * (size_t)Lv + 1;
+    const int ts = ctx->tab_turn;                    // this forward's slot of the pinned-table ring
+    ctx->tab_turn = (ts + 1) % mesm_ctx::kTabSlots;
+    if (ctx->tab_event_pending[ts]) { CK(cudaEventSynchronize(ctx->tab_event[ts])); ctx->tab_event_pending[ts] = false; }   // its last reader has run
+    if (ctx->h_tab_cap[ts] < tab_ints) {
+        if (ctx->h_tab[ts]) cudaFreeHost(ctx->h_tab[ts]);
+        ctx->h_tab[ts] = nullptr; ctx->h_tab_cap[ts] = 0;
+        CK(cudaMallocHost((void**)&ctx->h_tab[ts], tab_ints * 2 * sizeof(int)));
+        ctx->h_tab_cap[ts] = tab_ints * 2;
     }
-    if (ctx->tab_event_pending) { CK(cudaEventSynchronize(ctx->tab_event)); ctx->tab_event_pending = false; }
-    int* h_group = ctx->h_tab; int* h_slot = h_group + B; int* h_gstart = h_slot + B; int* h_cu = h_gstart + (G + 1);
+    int* h_group = ctx->h_tab[ts]; int* h_slot = h_group + B; int* h_gstart = h_slot + B; int* h_cu = h_gstart + (G + 1);
     h_cu[0] = 0;
     for (int b = 0; b < B; ++b) {
         const int n = packed ? in->video_len[b] : Lv;
         if (n < 1 || n > Lv) return fail(ctx, 1, "mesm_forward: video_len entries must be in [1, Lv]");
         h_cu[b + 1] = h_cu[b] + n;
     }
+    // distinct clip counts -> rows of the position table (row 0 = the global token's position)
+    int* h_lenoff = h_cu + (B + 1); int* h_dllen = h_lenoff + (Lv + 1); int* h_dloff = h_dllen + Lv;
+    int nd = 0, nPT = 1;
+    for (int n = 0; n <= Lv; ++n) h_lenoff[n] = -1;
+    if (packed)
+        for (int b = 0; b < B; ++b) {
+            const int n = in->video_len[b];
+            if (h_lenoff[n] < 0) { h_lenoff[n] = nPT; h_dllen[nd] = n; h_dloff[nd] = nPT; nPT += n; ++nd; }
+        }
+    for (int j = nd; j < Lv; ++j) { h_dllen[j] = 0; h_dloff[j] = 0; }
     std::vector<std::pair<int, int>> chunks;
     {
         // chunks of whole video groups, greedily filled to chunk_pairs; a small tail chunk is re-balanced with its
@@ -694,15 +728,16 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     float* projV_padded_out = packed ? projV_all : nullptr;
     if (!projV_all || packed) projV_all = p.projV;
     int* d_group = p.d_tab; int* d_slot = d_group + B; int* d_gstart = d_slot + B; int* d_cu_all = d_gstart + (G + 1);
-    int* d_glen = d_cu_all + (B + 1);
+    int* d_lenoff = d_cu_all + (B + 1); int* d_dllen = d_lenoff + (Lv + 1); int* d_dloff = d_dllen + Lv;
+    int* d_glen = d_dloff + Lv;
     const int* d_cu = packed ? d_cu_all : nullptr;
     {
         int* h_dev = nullptr;                       // device alias of the pinned table (identical under UVA)
         CK(cudaHostGetDevicePointer((void**)&h_dev, h_group, 0));
         CK(launch_pull_ints(h_dev, d_group, (long long)tab_ints, s));
     }
-    CK(cudaEventRecord(ctx->tab_event, s));
-    ctx->tab_event_pending = true;
+    CK(cudaEventRecord(ctx->tab_event[ts], s));
+    ctx->tab_event_pending[ts] = true;
     if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));
     // t_pad: packed clip row -> this pair's row in the zero-padded [B, Lv] layout (outputs); t_in: the row its features are
     // read from (the same, or the group's first pair when the collate-replicated video was uploaded once per group)
@@ -712,6 +747,28 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     const int* t_in = shared_video ? p.t_in : p.t_pad;
     if (packed) CK(launch_pack_table(d_cu, B, Lv, p.t_pad, s));
     if (shared_video) CK(launch_pack_table(d_cu, B, Lv, p.t_in, s, d_group, d_gstart));
+    // Position terms (packed layout).  PositionEmbeddingSine of a clip depends only on (clip count, clip index): build the
+    // table once per distinct clip count of the batch and push it through every projection that adds positions to its
+    // input - (x + pos) W = x W + (pos W)[row] - so those GEMMs lose their second K-sweep and the decoder's k_pos GEMMs
+    // shrink from B*(Lv+1) rows to the table's rows.
+    static int pos_tables_on = -1;
+    if (pos_tables_on < 0) { const char* e = getenv("MESM_POS_TABLES"); pos_tables_on = (e && e[0] == '0') ? 0 : 1; }
+    const bool ptab = packed && pos_tables_on;
+    std::vector<const float*> PWq_enh(ctx->enh.size(), nullptr), PWq_aln(ctx->aln.size(), nullptr), PWqk(ctx->enc.size(), nullptr),
+        PWkp(ctx->dec.size(), nullptr);
+    if (ptab) {
+        CK(launch_pos_table(d_dllen, d_dloff, nd, ctx->gpos, p.PT, s));
+        size_t slot = 0;
+        auto project = [&](const PL& w0, bool keep_bias, float* dst, int N) -> cudaError_t {
+            PL w = w0;
+            if (!keep_bias) w.bias = nullptr;
+            return Lin(nPT, w, p.PT, D, dst, N).run(s);
+        };
+        for (size_t l = 0; l < ctx->enh.size(); ++l, ++slot) { float* d = p.PWq + slot * (size_t)nPT * D; CK(project(ctx->enh[l].q, false, d, D)); PWq_enh[l] = d; }
+        for (size_t l = 0; l < ctx->aln.size(); ++l, ++slot) { float* d = p.PWq + slot * (size_t)nPT * D; CK(project(ctx->aln[l].q, false, d, D)); PWq_aln[l] = d; }
+        for (size_t l = 0; l < ctx->enc.size(); ++l) { float* d = p.PWqk + l * (size_t)nPT * 2 * D; CK(project(ctx->enc[l].qk, false, d, 2 * D)); PWqk[l] = d; }
+        for (size_t l = 0; l < ctx->dec.size(); ++l) { float* d = p.PWkp + l * (size_t)nPT * D; CK(project(ctx->dec[l].ca_kp, true, d, D)); PWkp[l] = d; }
+    }
 
     // ---- text side, whole batch (model/model.py:145-152, 167) --------------------------------------------------------
     const int Rt = B * Lt;
@@ -797,9 +854,10 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         const RowMap c2e = packed ? table_map(p.t_c2e) : RowMap{Lv, L1, 1};  // clip row -> encoder-buffer row
         const uint8_t* vmask = in->video_mask + (size_t)b0 * Lv;
         float* projV = projV_all + (size_t)v0 * D;
-        if (packed && !neg) CK(launch_chunk_tables(cu, Bc, p.t_c2e, p.t_g, s));
+        if (packed && !neg) CK(launch_chunk_tables(cu, Bc, p.t_c2e, p.t_g, s, ptab ? d_lenoff : nullptr, p.t_posV, p.t_posE));
         PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos; pa.cu = cu;
         pa.posV = p.posV; pa.posE = p.posE; pa.encbuf = p.E; pa.padV = p.padV; pa.padE = p.padE;
+        if (ptab) { pa.posV = nullptr; pa.posE = nullptr; }                                        // positions come from the table
         if (neg) { pa.posV = nullptr; pa.posE = nullptr; pa.padV = nullptr; pa.padE = nullptr; }   // positions / pads kept from the main pass
         CK(launch_pos_embed(pa, s));
         const float* words_c = (neg ? p.negw : expw) + (size_t)b0 * Lk * D;
@@ -814,7 +872,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
             T2VBuffers tb = p.t2v;
             if (l == 0) tb.Q = p.Qenh0;                 // layer 0's Q = (projV + pos) Wq is identical in the negative pass
             CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, tb,
-                         dst, D, identity_map(), s, l == 0 && neg, cu, Rv, Lv));
+                         dst, D, identity_map(), s, l == 0 && neg, cu, Rv, Lv, PWq_enh[l], p.t_posV));
             x = dst;
         }
         if (ctx->enh.empty() && enh_out && !packed)
@@ -830,7 +888,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
             const bool last = (l + 1 == ctx->aln.size());
             float* dst = last ? p.E : (l % 2 == 0 ? p.xa : p.xb);
             CK(t2v_layer(ctx->aln[l], words_c, identity_map(), nullptr, Lk, xin, p.posV, Lv, Bc, b0, B, p.padV_all, epad_all,
-                         p.t2v, dst, D, last ? c2e : identity_map(), s, false, cu, Rv, Lv));
+                         p.t2v, dst, D, last ? c2e : identity_map(), s, false, cu, Rv, Lv, PWq_aln[l], p.t_posV));
             xin = dst;
         }
         if (ctx->aln.empty())
@@ -838,7 +896,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         // ---- transformer encoder (model/transformer.py:185-197) ----
         float* Ecur = p.E; float* Enext = p.E2;
         for (size_t l = 0; l < ctx->enc.size(); ++l) {
-            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re));
+            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re, PWqk[l], p.t_posE));
             std::swap(Ecur, Enext);
         }
         // ---- saliency head (model/model.py:301-302) ----
@@ -872,7 +930,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
                                         out->aux_logits ? out->aux_logits + (size_t)b0 * nq * 2 : nullptr,
                                         out->aux_spans ? out->aux_spans + (size_t)b0 * nq * 2 : nullptr, (long long)B * nq * 2,
                                         out->hs ? out->hs + (size_t)b0 * nq * D : nullptr, (long long)B * nq * D, nullptr, 0, s,
-                                        cu, Re);
+                                        cu, Re, ptab ? PWkp.data() : nullptr, p.t_posE);
             CK(e);
         }
         return 0;

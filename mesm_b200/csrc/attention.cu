@@ -173,7 +173,8 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (!masked) {
                 for (int part = 0; part < nparts; ++part) {
-                    const float* kp = part == 0 ? a.k + krow * a.ldk + h * hq : a.k2 + krow * a.ldk2 + h * hq;
+                    const float* kp = part == 0 ? a.k + krow * a.ldk + h * hq
+                                                : a.k2 + (a.k2_table ? (long long)a.k2_table[krow] : krow) * a.ldk2 + h * hq;
                     for (int c = 0; c < hq; c += 4) {
                         const float4 kv = *reinterpret_cast<const float4*>(kp + c);
 #pragma unroll

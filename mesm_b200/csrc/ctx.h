@@ -77,10 +77,15 @@ struct mesm_ctx {
     Norm osp0_ln, osp1_ln;
     const float *gtok = nullptr, *gpos = nullptr, *msent = nullptr, *qembed = nullptr;
 
-    int* h_tab = nullptr;
-    size_t h_tab_cap = 0;
-    cudaEvent_t tab_event = nullptr;
-    bool tab_event_pending = false;
+    // pinned host tables of a forward (pulled by a kernel at its start).  A small ring of them lets the host enqueue a few
+    // forwards ahead of the device: with a single table every forward had to wait for the previous one to START on the GPU,
+    // so any host hiccup longer than one forward's GPU time stalled the device.
+    static constexpr int kTabSlots = 3;
+    int* h_tab[kTabSlots] = {nullptr, nullptr, nullptr};
+    size_t h_tab_cap[kTabSlots] = {0, 0, 0};
+    cudaEvent_t tab_event[kTabSlots] = {nullptr, nullptr, nullptr};
+    bool tab_event_pending[kTabSlots] = {false, false, false};
+    int tab_turn = 0;
 };
 
 
@@ -149,16 +154,21 @@ struct DecBuffers {
 cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
                       const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q = false,
-                      const int* cu = nullptr, int Rv_packed = 0, int q_pad_ld = 0);
+                      const int* cu = nullptr, int Rv_packed = 0, int q_pad_ld = 0, const float* posW = nullptr,
+                      const int* t_pos = nullptr);
+// posW / t_pos: the position term of a projection as a gathered residual - row r of the GEMM adds posW[t_pos[r]], where
+// posW = (position table) . W^T was computed once per distinct (clip count, clip index); replaces the (x + pos) K-sweep
 // cu != nullptr (device, first pair of the chunk): packed variable-length rows, see pair_rows() in common.cuh
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
-                      const EncBuffers& t, float* out, cudaStream_t s, const int* cu = nullptr, int R_packed = 0);
+                      const EncBuffers& t, float* out, cudaStream_t s, const int* cu = nullptr, int R_packed = 0,
+                      const float* posW = nullptr, const int* t_pos = nullptr);
 size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl);
 cudaError_t launch_colsum(const float* Wt, int Kp, int ldw, int N, float* out, cudaStream_t s);
 cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, float* Wt, int ldw, int Kp, cudaStream_t s);
 cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, const float* posE, const uint8_t* padV, int Lv, int Bc,
                         const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
                         long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
-                        long long refs_layer_stride, cudaStream_t s, const int* cu = nullptr, int Re_packed = 0);
+                        long long refs_layer_stride, cudaStream_t s, const int* cu = nullptr, int Re_packed = 0,
+                        const float* const* posWkp = nullptr, const int* t_posE = nullptr);
 
 }  // namespace mesm

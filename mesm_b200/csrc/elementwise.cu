@@ -90,15 +90,18 @@ __global__ void __launch_bounds__(256) pos_embed_kernel(const PosArgs a) {
         return;
     }
     const uint8_t* m = a.vmask + (long long)b * a.Lv;          // the mask itself is always the zero-padded [B, Lv] array
+    const bool need_pos = a.posV || a.posE;
     for (int i = threadIdx.x; i < Lv; i += blockDim.x) {
         int c = 0;
-        for (int j = 0; j <= i; ++j) c += m[j] ? 1 : 0;
+        if (need_pos) for (int j = 0; j <= i; ++j) c += m[j] ? 1 : 0;
         xemb[i] = (float)c;
         const uint8_t pad = m[i] ? 0 : 1;
         if (a.padV) a.padV[vrow0 + i] = pad;
         if (a.padE) a.padE[erow0 + 1 + i] = pad;
     }
     if (threadIdx.x == 0 && a.padE) a.padE[erow0] = 1;
+    if (threadIdx.x < D && a.encbuf && !a.posV && !a.posE) a.encbuf[erow0 * D + threadIdx.x] = a.gtok[threadIdx.x];
+    if (!need_pos) return;                                     // pads (+ global token) only: positions come from the table
     __syncthreads();
     const float last = (Lv > 0 ? xemb[Lv - 1] : 0.f) + 1e-6f;   // packed: rows past this pair's length hold no valid clip
     const int c = threadIdx.x;          // 256 threads = 256 feature dims
@@ -294,15 +297,41 @@ cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStre
     pack_table_kernel<<<B, 128, 0, s>>>(cu, Lv, t_pad, pair_group, group_start);
     LAUNCH_END();
 }
-__global__ void chunk_tables_kernel(const int* __restrict__ cu, int* __restrict__ t_c2e, int* __restrict__ t_g) {
+__global__ void chunk_tables_kernel(const int* __restrict__ cu, int* __restrict__ t_c2e, int* __restrict__ t_g,
+                                    const int* __restrict__ len_off, int* __restrict__ t_posV, int* __restrict__ t_posE) {
     const int b = blockIdx.x, c0 = cu[b] - cu[0], n = cu[b + 1] - cu[b];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) t_c2e[c0 + i] = c0 + b + 1 + i;
-    if (threadIdx.x == 0) t_g[b] = c0 + b;
+    const int po = len_off ? len_off[n] : 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        t_c2e[c0 + i] = c0 + b + 1 + i;
+        if (len_off) { t_posV[c0 + i] = po + i; t_posE[c0 + b + 1 + i] = po + i; }
+    }
+    if (threadIdx.x == 0) { t_g[b] = c0 + b; if (len_off) t_posE[c0 + b] = 0; }
 }
-cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s) {
+cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s, const int* len_off, int* t_posV,
+                                int* t_posE) {
     ProfScope _ps("pack_tables", s);
     if (Bc <= 0) return cudaSuccess;
-    chunk_tables_kernel<<<Bc, 128, 0, s>>>(cu, t_c2e, t_g);
+    chunk_tables_kernel<<<Bc, 128, 0, s>>>(cu, t_c2e, t_g, len_off, t_posV, t_posE);
+    LAUNCH_END();
+}
+// same arithmetic as pos_embed_kernel for a prefix mask of n valid clips: x_embed = (i + 1) / (n + 1e-6) * 2 pi
+__global__ void __launch_bounds__(256) pos_table_kernel(const int* __restrict__ dl_len, const int* __restrict__ dl_off,
+                                                        const float* __restrict__ gpos, float* __restrict__ PT) {
+    const int c = threadIdx.x;
+    if (blockIdx.x == 0) { PT[c] = gpos[c]; return; }
+    const int n = dl_len[blockIdx.x - 1];
+    float* out = PT + (long long)dl_off[blockIdx.x - 1] * D;
+    const float last = (float)n + 1e-6f;
+    const float dim_t = powf(10000.f, (float)(2 * (c / 2)) / 256.f);
+    for (int i = 0; i < n; ++i) {
+        const float xe = (float)(i + 1) / last * 6.283185307179586f;
+        const float arg = xe / dim_t;
+        out[(long long)i * D + c] = (c & 1) ? cosf(arg) : sinf(arg);
+    }
+}
+cudaError_t launch_pos_table(const int* dl_len, const int* dl_off, int nd, const float* gpos, float* PT, cudaStream_t s) {
+    ProfScope _ps("pos_table", s);
+    pos_table_kernel<<<nd + 1, 256, 0, s>>>(dl_len, dl_off, gpos, PT);
     LAUNCH_END();
 }
 __global__ void zero_masked_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ mask, long long R, int width) {

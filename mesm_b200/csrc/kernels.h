@@ -38,6 +38,7 @@ struct MhaSmallArgs {
     // packed keys: pair b owns the S_b = k_cu[b+1]-k_cu[b] key rows (k_cu[b]-k_cu[0]) + b*k_enc + k_off + j; k_pad is then
     // indexed (k_cu[b]-k_cu[0]) + j.  S stays the maximum over the pairs (shared-memory sizing).
     const int* k_cu = nullptr; int k_enc = 0;
+    const int* k2_table = nullptr;   // k2 row of key row r is k2_table[r] (position-term table) instead of r
 };
 cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s);
 
@@ -82,7 +83,12 @@ cudaError_t launch_saliency_packed(const float* p1, const int* cu, const float* 
 cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s, const int* pair_group = nullptr,
                               const int* group_start = nullptr);
 // per chunk: t_c2e[r] = encoder-buffer row of packed clip row r; t_g[b] = encoder-buffer row of pair b's global token
-cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s);
+cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s, const int* len_off = nullptr,
+                                int* t_posV = nullptr, int* t_posE = nullptr);
+// Position table (packed layout): PositionEmbeddingSine depends only on (clip count n, clip index i), so the batch needs
+// one row per distinct (n, i): row 0 = global_rep_pos, rows dl_off[j] + i (i < dl_len[j]) = the sine embedding of clip i
+// in a video of dl_len[j] clips.  chunk tables t_posV / t_posE (len_off[n] = first row of length n) index it per row.
+cudaError_t launch_pos_table(const int* dl_len, const int* dl_off, int nd, const float* gpos, float* PT, cudaStream_t s);
 // rows r < R of x [R, width] with mask[r] == 0 are set to zero
 cudaError_t launch_zero_masked_rows(float* x, const uint8_t* mask, long long R, int width, cudaStream_t s);
 cudaError_t launch_dec_init_ref(const float* qe, int B, int nq, float* ref, cudaStream_t s);
