@@ -258,6 +258,7 @@ def main():
     # host clip counts (what the collate step knows): the engine then runs on packed variable-length rows
     vlen_host = None if os.environ.get("MESM_PADDED_ROWS") else wl["video_len"]
     config["rows"] = "zero-padded [B, Lv]" if vlen_host is None else "packed variable-length (host clip counts passed as video_len)"
+    config["clip_rows_per_gpu"] = int(B * Lv if vlen_host is None else wl["video_len"].sum())
 
     def step():
         out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"],

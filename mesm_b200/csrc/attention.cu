@@ -17,13 +17,18 @@ namespace mesm {
 // mha_rows_kernel
 // ---------------------------------------------------------------------------------------------------------------
 
+// 128 query rows per CTA (blockIdx.z tiles a pair's rows): with ~96 registers per thread that is 5 CTAs = 20 warps per SM,
+// against 2 CTAs = 14 warps for one 224-thread CTA per (pair, head) (ncu: registers were the occupancy limiter, 16 % warps
+// active), and short pairs of a packed batch launch no idle warps beyond their last tile.
+constexpr int MR_ROWS = 128;
 template <bool QUIRK>
-__global__ void mha_rows_kernel(const MhaRowsArgs a) {
+__global__ void __launch_bounds__(MR_ROWS, 5) mha_rows_kernel(const MhaRowsArgs a) {
     extern __shared__ float smem[];
     const int h = blockIdx.x, b = blockIdx.y;
     long long kbase, qbase; int Lk, Lq;
     pair_rows(a.k_cu, a.k_enc, b, a.Lk, kbase, Lk);       // key rows of this pair (packed layouts: variable count)
     pair_rows(a.q_cu, a.q_enc, b, a.Lq, qbase, Lq);
+    if ((int)blockIdx.z * MR_ROWS >= Lq) return;            // packed batch: this pair has no rows in this tile
     const int Lkmax = a.Lk;
     // every thread of a warp reads the SAME key row (broadcast): rows stay 16-byte aligned for LDS.128, no padding needed
     float* Ks = smem;                       // [Lk][32]
@@ -45,7 +50,7 @@ __global__ void mha_rows_kernel(const MhaRowsArgs a) {
     }
     __syncthreads();
 
-    const int i = threadIdx.x;
+    const int i = blockIdx.z * MR_ROWS + threadIdx.x;
     if (i >= Lq) return;
     const long long qrow = qbase + i;
     float q[32], o[32];
@@ -120,11 +125,10 @@ cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s) {
         if (!force && attn_tc_eligible(a)) return launch_attn_tc(a, s);
     }
     ProfScope _ps(a.q_pad ? "mha_rows t2v" : "mha_rows self", s);
-    const int threads = ((a.Lq + 31) / 32) * 32;
-    if (threads > 1024) return cudaErrorInvalidValue;
+    const int threads = MR_ROWS;
     const size_t smem = (size_t)a.Lk * 32 * 2 * sizeof(float) + 2 * (size_t)a.Lk;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
-    dim3 grid(NH, a.B);
+    dim3 grid(NH, a.B, (a.Lq + MR_ROWS - 1) / MR_ROWS);
     if (a.q_pad) {
         if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(mha_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mha_rows_kernel<true><<<grid, threads, smem, s>>>(a);
