@@ -228,9 +228,123 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Decoder cross-attention (model/transformer.py:770-790): LQ queries x S memory keys, per-head operands
+// [content ; sine] (2 x 32) and 32-wide values.  One CTA per pair, one WARP per head; keys in blocks of 32 with the lane
+// as the key for the scores (its 2 x 128-byte key segments live in registers for all LQ queries - every key byte is read
+// once) and the lane as the output dimension for P V (value rows read coalesced, straight from global memory).  Online
+// softmax per query; no block-wide barrier after the query tile is staged.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LQ>
+__global__ void __launch_bounds__(256) dec_cross_kernel(const MhaSmallArgs a) {
+    extern __shared__ float smem[];
+    float* Qs = smem;                                  // [LQ][2][256]  scaled content / sine queries
+    float* Ps = Qs + LQ * 512;                         // [8 warps][LQ][32]  probabilities of the current key block
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int S = a.S;
+    long long kfirst = (long long)b * a.k_bs + a.k_off, kpad0 = (long long)b * a.S;
+    if (a.k_cu) {
+        const int c0 = a.k_cu[b] - a.k_cu[0];
+        S = a.k_cu[b + 1] - a.k_cu[b];
+        kfirst = (long long)c0 + (a.k_enc ? b : 0) + a.k_off;
+        kpad0 = c0;
+    }
+    for (int idx = threadIdx.x; idx < LQ * 128; idx += 256) {
+        const int i = idx >> 7, part = (idx >> 6) & 1, c4 = (idx & 63) * 4;
+        const long long row = (long long)b * a.q_bs + (long long)i * a.q_is;
+        float4 v = *reinterpret_cast<const float4*>((part ? a.q2 + row * a.ldq2 : a.q + row * a.ldq) + c4);
+        v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;
+        *reinterpret_cast<float4*>(Qs + i * 512 + part * 256 + c4) = v;
+    }
+    __syncthreads();
+    float* P = Ps + h * (LQ * 32);
+    float m[LQ], l[LQ], acc[LQ];
+#pragma unroll
+    for (int i = 0; i < LQ; ++i) { m[i] = -CUDART_INF_F; l[i] = 0.f; acc[i] = 0.f; }
+
+    for (int k0 = 0; k0 < S; k0 += 32) {
+        const int key = k0 + lane;
+        const bool valid = key < S && !(a.k_pad && a.k_pad[kpad0 + key]);
+        float s[LQ];
+#pragma unroll
+        for (int i = 0; i < LQ; ++i) s[i] = 0.f;
+        if (valid) {
+            const long long krow = kfirst + (long long)key * a.k_is;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const float* kp = part == 0 ? a.k + krow * a.ldk + h * 32
+                                            : a.k2 + (a.k2_table ? (long long)a.k2_table[krow] : krow) * a.ldk2 + h * 32;
+                float kr[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = *reinterpret_cast<const float4*>(kp + 4 * j);
+                    kr[4 * j] = t.x; kr[4 * j + 1] = t.y; kr[4 * j + 2] = t.z; kr[4 * j + 3] = t.w;
+                }
+#pragma unroll
+                for (int i = 0; i < LQ; ++i) {
+                    const float4* q4 = reinterpret_cast<const float4*>(Qs + i * 512 + part * 256 + h * 32);   // broadcast reads
+                    float d = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = q4[j];
+                        d = fmaf(t.x, kr[4 * j], d); d = fmaf(t.y, kr[4 * j + 1], d);
+                        d = fmaf(t.z, kr[4 * j + 2], d); d = fmaf(t.w, kr[4 * j + 3], d);
+                    }
+                    s[i] += d;
+                }
+            }
+        }
+        __syncwarp();                                  // the previous block's P has been consumed
+#pragma unroll
+        for (int i = 0; i < LQ; ++i) {
+            const float sv = valid ? s[i] : -CUDART_INF_F;
+            const float mn = fmaxf(m[i], warp_max(sv));
+            float corr = 1.f, p = 0.f;
+            if (mn != -CUDART_INF_F) { corr = __expf(m[i] - mn); p = valid ? __expf(sv - mn) : 0.f; }   // m = -inf -> corr 0
+            l[i] = l[i] * corr + warp_sum(p);
+            acc[i] *= corr;
+            m[i] = mn;
+            P[i * 32 + lane] = p;
+        }
+        __syncwarp();
+        const int nk = min(32, S - k0);
+        for (int j0 = 0; j0 < nk; j0 += 4) {           // lane = output dim; 4 keys per step, P read as broadcast float4
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jj = j0 + u;
+                v[u] = jj < nk ? a.v[(kfirst + (long long)(k0 + jj) * a.k_is) * a.ldv + h * 32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < LQ; ++i) {
+                const float4 p4 = *reinterpret_cast<const float4*>(P + i * 32 + j0);
+                acc[i] = fmaf(p4.x, v[0], fmaf(p4.y, v[1], fmaf(p4.z, v[2], fmaf(p4.w, v[3], acc[i]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LQ; ++i)
+        a.out[((long long)b * a.q_bs + (long long)i * a.q_is) * a.ldo + h * 32 + lane] = acc[i] / l[i];   // l == 0 -> NaN like the reference
+}
+
+static bool dec_cross_eligible(const MhaSmallArgs& a) {
+    auto al16 = [](const float* p, int ld) { return p && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); };
+    return a.L == 10 && a.nheads == NH && a.hq == HD && a.hv == HD && a.q2 && a.k2 && !a.attn_w && al16(a.q, a.ldq) &&
+           al16(a.q2, a.ldq2) && al16(a.k, a.ldk) && al16(a.k2, a.ldk2) && a.S >= 1;
+}
+
 cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s) {
-    ProfScope _ps("mha_small", s);
     if (a.B <= 0 || a.L <= 0) return cudaSuccess;
+    static int cross_on = -1;
+    if (cross_on < 0) { const char* e = getenv("MESM_DEC_CROSS"); cross_on = (e && e[0] == '0') ? 0 : 1; }
+    if (cross_on && dec_cross_eligible(a)) {
+        ProfScope _ps("dec_cross", s);
+        const size_t smem = (size_t)(10 * 512 + 8 * 10 * 32) * sizeof(float);
+        dec_cross_kernel<10><<<a.B, 256, smem, s>>>(a);
+        g_stats.launches++;
+        return cudaGetLastError();
+    }
+    ProfScope _ps("mha_small", s);
     const int E = a.hq * (a.q2 ? 2 : 1);
     const size_t smem = ((size_t)a.L * E + (size_t)a.L * a.S) * sizeof(float);
     if (smem > 220 * 1024 || (a.hq & 3)) return cudaErrorInvalidValue;
