@@ -248,7 +248,7 @@ int mesm_debug_attention(const float* qkv, const uint8_t* k_pad, int32_t B, int3
     a.q_scale = kScale32;
     for (int i = 0; i < iters; ++i) {
         if (use_tc) { if (!attn_tc_eligible(a)) return fail(ctx, 3, "not eligible"); CK(launch_attn_tc(a, s)); }
-        else { setenv("MESM_FORCE_SIMT_ATTN", "1", 1); CK(launch_mha_rows(a, s)); }
+        else { CK(launch_mha_rows(a, s, true)); }
     }
     CK(cudaStreamSynchronize(s));
     if (watchdog8) { unsigned long long tmp[64]; tc_read_watchdog(tmp); for (int i = 0; i < 8; ++i) watchdog8[i] = tmp[i]; }

@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(MR_ROWS, 5) mha_rows_kernel(const MhaRowsArgs 
     for (int j = 0; j < 8; ++j) op[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
 }
 
-cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s) {
+cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_simt) {
     if (a.B <= 0 || a.Lq <= 0) return cudaSuccess;
     {
         static int force = -1;
         if (force < 0) { const char* e = getenv("MESM_FORCE_SIMT"); const char* e2 = getenv("MESM_FORCE_SIMT_ATTN"); force = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
-        if (!force && attn_tc_eligible(a)) return launch_attn_tc(a, s);
+        if (!force && !force_simt && attn_tc_eligible(a)) return launch_attn_tc(a, s);
     }
     ProfScope _ps(a.q_pad ? "mha_rows t2v" : "mha_rows self", s);
     const int threads = MR_ROWS;

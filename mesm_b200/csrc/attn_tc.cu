@@ -295,6 +295,322 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
     }
 }
 
+
+// =====================================================================================================================
+// Pipelined variant: one CTA per PAIR walks its 8 heads; four loader warps stage the next head's operands while the current
+// head is in its softmax, and the S MMAs of the next head run under the current head's epilogue.
+//
+//   loader warps (9..12)   head i+1:  wait "S MMAs of head i retired"  -> K (hi/lo), Q tiles, key masks -> KQ barrier
+//                                     wait "P V MMAs of head i retired" -> V^T (hi/lo)                   -> V barrier
+//   MMA thread (warp 0)    head i:    wait KQ -> S = Q K^T (both tiles) ; per key block: wait P (and V once) -> O += P V
+//                          (S of head i+1 is issued right after the last P block of head i arrived: every softmax thread has
+//                           finished reading S by then; its O columns are free once the same warps' epilogue of head i ran,
+//                           which precedes their first P of head i+1 in program order)
+//   softmax warps (1..8)   head i:    wait S -> max, exp, P blocks -> wait O -> O / rowsum -> global (private transpose scratch)
+// TMEM is allocated once per CTA, barriers flip once per head (parity = head & 1).  The one-CTA-per-(pair, head) kernel above
+// spent its ~14 us per CTA in strictly serial phases (tensor pipe 7 % active, ncu profiles/r1_final_kernels_ncu.md).
+// =====================================================================================================================
+constexpr int ATP_THREADS = 32 + 256 + 128;
+constexpr int ATP_MASK = AT_P + 4 * 16384;                  // 2 x {own[8], partner[8], nkb_eff, pad} u32 (128 B per buffer)
+constexpr int ATP_T = ATP_MASK + 256;                       // epilogue transpose scratch: 8 warps x 32 rows x 36 floats
+constexpr int ATP_BAR = ATP_T + 8 * 32 * 36 * 4;            // S[2] 0,8 | O[2] 16,24 | Pfull[2][2] 32.. | Pempty[2][2] 64.. | KQ 96 | V 104 | tmem 112
+constexpr int ATP_SMEM = ATP_BAR + 128 + 1024;
+
+__global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t bars = sbase + ATP_BAR;
+    const uint32_t bar_kq = bars + 96, bar_v = bars + 104;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + ATP_BAR + 112);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(smem + ATP_MASK);       // buffer (head & 1) at masks + 32 * (head & 1)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    const int bg = a.b0 + b;
+    const bool quirk = a.q_pad != nullptr;
+    long long kbase, qbase; int Lq, Lk;
+    pair_rows(a.q_cu, a.q_enc, b, a.Lq, qbase, Lq);
+    pair_rows(a.k_cu, a.k_enc, b, a.Lk, kbase, Lk);
+    const long long kpad_own = a.k_cu ? kbase : (long long)bg * Lk;
+    const int q_pad_ld = a.q_pad_ld ? a.q_pad_ld : a.Lq;
+    const int Lkp = (Lk + 31) & ~31;
+    const int nact = Lq > 128 ? 2 : 1;                      // query tiles of this pair (Lq <= 256)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);                     // S[0..1], O[0..1]: tcgen05.commit
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 32 + 8 * i, 4);                // Pfull: 4 softmax warps per tile
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 64 + 8 * i, 1);                // Pempty: tcgen05.commit
+        mbar_init(bar_kq, 4);                                                       // 4 loader warps
+        mbar_init(bar_v, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp >= 9) {
+        // ================================ loaders ================================
+        const int t = threadIdx.x - 288;                                            // 0..127
+        for (int h = 0; h < NH; ++h) {
+            const int bp = quirk ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
+            if (h > 0) mbar_wait(bars + 8 * (nact - 1), (h - 1) & 1, 600 + h);      // S MMAs of the previous head retired: K / Q free
+            {   // K -> bf16 hi/lo, K-major SWIZZLE_64B rows of 32
+                const int total = Lkp * 8;
+                for (int base = t; base < total; base += 128 * 4) {
+                    float4 kv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
+                        kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (idx < total && key < Lk) kv[u] = __ldg(reinterpret_cast<const float4*>(a.k + (kbase + key) * a.ldk + h * 32 + c4 * 4));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
+                        if (idx >= total) break;
+                        const float kk[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
+                        __nv_bfloat16 kh[4], kl[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_bf16(kk[e], kh[e], kl[e]);
+                        const int kb = sw64(key, c4 * 4);
+                        *reinterpret_cast<uint2*>(smem + AT_KHI + kb) =
+                            make_uint2((uint32_t)__bfloat16_as_ushort(kh[0]) | ((uint32_t)__bfloat16_as_ushort(kh[1]) << 16),
+                                       (uint32_t)__bfloat16_as_ushort(kh[2]) | ((uint32_t)__bfloat16_as_ushort(kh[3]) << 16));
+                        *reinterpret_cast<uint2*>(smem + AT_KLO + kb) =
+                            make_uint2((uint32_t)__bfloat16_as_ushort(kl[0]) | ((uint32_t)__bfloat16_as_ushort(kl[1]) << 16),
+                                       (uint32_t)__bfloat16_as_ushort(kl[2]) | ((uint32_t)__bfloat16_as_ushort(kl[3]) << 16));
+                    }
+                }
+            }
+            for (int tile = 0; tile < nact; ++tile) {       // Q tiles (A operand), scaled by head_dim^-0.5
+                uint8_t* qs = smem + AT_Q + tile * 16384;
+                float4 qv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int idx = t + 128 * i, row = idx >> 3, c4 = idx & 7;
+                    const int qi = tile * 128 + row;
+                    qv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (qi < Lq) qv[i] = __ldg(reinterpret_cast<const float4*>(a.q + (qbase + qi) * a.ldq + h * 32 + c4 * 4));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int idx = t + 128 * i, row = idx >> 3, c4 = idx & 7;
+                    const float qq[4] = {qv[i].x * a.q_scale, qv[i].y * a.q_scale, qv[i].z * a.q_scale, qv[i].w * a.q_scale};
+                    __nv_bfloat16 qh[4], ql[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) split_bf16(qq[u], qh[u], ql[u]);
+                    const int qb = sw64(row, c4 * 4);
+                    *reinterpret_cast<uint2*>(qs + qb) =
+                        make_uint2((uint32_t)__bfloat16_as_ushort(qh[0]) | ((uint32_t)__bfloat16_as_ushort(qh[1]) << 16),
+                                   (uint32_t)__bfloat16_as_ushort(qh[2]) | ((uint32_t)__bfloat16_as_ushort(qh[3]) << 16));
+                    *reinterpret_cast<uint2*>(qs + 8192 + qb) =
+                        make_uint2((uint32_t)__bfloat16_as_ushort(ql[0]) | ((uint32_t)__bfloat16_as_ushort(ql[1]) << 16),
+                                   (uint32_t)__bfloat16_as_ushort(ql[2]) | ((uint32_t)__bfloat16_as_ushort(ql[3]) << 16));
+                }
+            }
+            if (warp == 9) {                                                   // per-block key masks of this head
+                uint32_t* mk = masks + 32 * (h & 1);
+                int last = 0;
+                for (int c = 0; c < (Lkp >> 5); ++c) {
+                    const int k = c * 32 + lane;
+                    const int kc = k < Lk ? k : 0;
+                    const bool m_own = (k >= Lk) || a.k_pad[kpad_own + kc];
+                    const bool m_oth = quirk && ((k >= Lk) || a.k_pad[(long long)bp * Lk + kc]);
+                    const unsigned mo = __ballot_sync(0xffffffffu, m_own), mt = __ballot_sync(0xffffffffu, m_oth);
+                    if (lane == 0) { mk[c] = mo; mk[8 + c] = mt; }
+                    if (mo != 0xffffffffu) last = c + 1;
+                }
+                if (lane == 0) mk[16] = (uint32_t)(last > 0 ? last : 1);        // key blocks after the last valid key are skipped
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_kq);
+            if (h > 0) mbar_wait(bars + 16 + 8 * (nact - 1), (h - 1) & 1, 620 + h);  // P V MMAs of the previous head retired: V free
+            {   // V^T -> bf16 hi/lo: per 32-key block a [32 dims][32 keys] K-major tile
+                const int total = Lkp * 8;
+                for (int base = t; base < total; base += 128 * 4) {
+                    float4 vv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
+                        vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (idx < total && key < Lk) vv[u] = __ldg(reinterpret_cast<const float4*>(a.v + (kbase + key) * a.ldv + h * 32 + c4 * 4));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
+                        if (idx >= total) break;
+                        const float vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                        const int jb = (key >> 5) * 2048, col = key & 31;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat16 vh, vl;
+                            split_bf16(vvv[e], vh, vl);
+                            const int vb = jb + sw64(c4 * 4 + e, col);
+                            *reinterpret_cast<__nv_bfloat16*>(smem + AT_VHI + vb) = vh;
+                            *reinterpret_cast<__nv_bfloat16*>(smem + AT_VLO + vb) = vl;
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_v);
+        }
+    } else if (warp == 0) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc_o = make_idesc(32);
+            int pu = 0;
+            for (int h = 0; h < NH; ++h) {
+                mbar_wait(bar_kq, h & 1, 700 + h);
+                tc_fence_after();
+                const int nkb_eff = (int)masks[32 * (h & 1) + 16];
+                const uint32_t idesc_s = make_idesc(nkb_eff * 32);
+                for (int t2 = 0; t2 < nact; ++t2) {                        // S_t = Q_t K^T, K = 32 -> two K=16 steps
+                    const uint32_t qb = sbase + AT_Q + t2 * 16384;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint64_t qh = make_desc(qb + k * 32), ql = make_desc(qb + 8192 + k * 32);
+                        const uint64_t kh = make_desc(sbase + AT_KHI + k * 32), kl = make_desc(sbase + AT_KLO + k * 32);
+                        umma(tmem_base + t2 * 256, qh, kh, k > 0 ? 1u : 0u, idesc_s);
+                        umma(tmem_base + t2 * 256, ql, kh, 1u, idesc_s);
+                        umma(tmem_base + t2 * 256, qh, kl, 1u, idesc_s);
+                    }
+                    umma_commit(bars + 8 * t2);
+                }
+                for (int j = 0; j < nkb_eff; ++j, ++pu) {                  // O_t += P_t,j V_j
+                    const int slot = pu & 1;
+                    for (int t2 = 0; t2 < nact; ++t2) {
+                        mbar_wait(bars + 32 + 16 * t2 + 8 * slot, (pu >> 1) & 1, 100 + t2);
+                        if (j == 0 && t2 == 0) mbar_wait(bar_v, h & 1, 720 + h);
+                        tc_fence_after();
+                        const uint32_t ph_ = sbase + AT_P + (t2 * 2 + slot) * 16384, pl_ = ph_ + 8192;
+                        const uint32_t vh_ = sbase + AT_VHI + j * 2048, vl_ = sbase + AT_VLO + j * 2048;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint64_t dph = make_desc(ph_ + k * 32), dpl = make_desc(pl_ + k * 32);
+                            const uint64_t dvh = make_desc(vh_ + k * 32), dvl = make_desc(vl_ + k * 32);
+                            umma(tmem_base + t2 * 256 + AT_OCOL, dph, dvh, (j > 0 || k > 0) ? 1u : 0u, idesc_o);
+                            umma(tmem_base + t2 * 256 + AT_OCOL, dpl, dvh, 1u, idesc_o);
+                            umma(tmem_base + t2 * 256 + AT_OCOL, dph, dvl, 1u, idesc_o);
+                        }
+                        umma_commit(bars + 64 + 16 * t2 + 8 * slot);
+                        if (j == nkb_eff - 1) umma_commit(bars + 16 + 8 * t2);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ softmax / epilogue warps ================================
+        const int wt = warp >= 5 ? 1 : 0;
+        if (wt < nact) {
+            const int q4 = warp & 3;                                       // TMEM lane quadrant of this warp
+            const int row = q4 * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + wt * 256;
+            const uint32_t bar_Pfull = bars + 32 + 16 * wt, bar_Pempty = bars + 64 + 16 * wt;
+            const bool wact = wt * 128 + q4 * 32 < Lq;                     // warp has at least one real query row
+            const int qi = wt * 128 + row;
+            float* T = reinterpret_cast<float*>(smem + ATP_T) + (warp - 1) * (32 * 36);
+            int pu = 0;
+            for (int h = 0; h < NH; ++h) {
+                const uint32_t hp = h & 1;
+                const int bp = quirk ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
+                const bool rflag = quirk && a.q_pad[(long long)bp * q_pad_ld + (qi < Lq ? qi : 0)];
+                mbar_wait(bars + 8 * wt, hp, 200 + wt);
+                tc_fence_after();
+                const uint32_t* kmask_own = masks + 32 * hp;
+                const uint32_t* kmask_oth = kmask_own + 8;
+                const int nkb_eff = (int)kmask_own[16];
+                // pass 1: row maximum over the valid keys
+                float mx = -CUDART_INF_F;
+                if (wact) {
+                    for (int c = 0; c < nkb_eff; ++c) {
+                        float v[32];
+                        tmem_ld32(trow + c * 32, v);
+                        const uint32_t mk = kmask_own[c] | (rflag ? kmask_oth[c] : 0u);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) mx = fmaxf(mx, v[j]);
+                    }
+                }
+                const float mxl = mx * 1.4426950408889634f;
+                // pass 2: p = exp(s - max) -> bf16 hi/lo A-operand blocks of 32 keys, double-buffered against the P V MMAs
+                float sum = 0.f;
+                for (int c = 0; c < nkb_eff; ++c, ++pu) {
+                    const int slot = pu & 1;
+                    uint32_t hi[16], lo[16];
+                    if (wact) {
+                        float v[32];
+                        tmem_ld32(trow + c * 32, v);
+                        const uint32_t mk = kmask_own[c] | (rflag ? kmask_oth[c] : 0u);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float p0 = ((mk >> (2 * j)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j], 1.4426950408889634f, -mxl));
+                            const float p1 = ((mk >> (2 * j + 1)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j + 1], 1.4426950408889634f, -mxl));
+                            sum += p0 + p1;
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - __uint_as_float(hb << 16), p1 - __uint_as_float(hb & 0xffff0000u));
+                            hi[j] = hb;
+                            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { hi[j] = 0u; lo[j] = 0u; }
+                    }
+                    mbar_wait(bar_Pempty + 8 * slot, ((pu >> 1) & 1) ^ 1, 300 + wt);    // slot free (first two uses pass at once)
+                    uint8_t* ph_ = smem + AT_P + (wt * 2 + slot) * 16384;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int off = sw64(row, cc * 8);
+                        *reinterpret_cast<uint4*>(ph_ + off) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+                        *reinterpret_cast<uint4*>(ph_ + 8192 + off) = make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();               // this warp's TMEM reads (S, and O of the previous head) precede the arrival
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_Pfull + 8 * slot);
+                }
+                // epilogue: O / rowsum, transposed through this warp's private scratch
+                mbar_wait(bars + 16 + 8 * wt, hp, 400 + wt);
+                tc_fence_after();
+                if (wact) {
+                    float o[32];
+                    tmem_ld32(trow + AT_OCOL, o);
+                    const float inv = 1.f / sum;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(&T[lane * 36 + 4 * j]) = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+                    __syncwarp();
+                    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + rsub;
+                        const int qo = wt * 128 + q4 * 32 + r;
+                        if (qo < Lq)
+                            *reinterpret_cast<float4*>(a.out + (qbase + qo) * a.ldo + h * 32 + c4) =
+                                *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+                    }
+                    __syncwarp();                    // scratch is rewritten by the next head's epilogue
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 }  // namespace tc
 
 void tc_read_watchdog(unsigned long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_watchdog, 512); unsigned long long z[64] = {0}; cudaMemcpyToSymbol(tc::g_tc_watchdog, z, 512); }
@@ -310,6 +626,18 @@ bool attn_tc_eligible(const MhaRowsArgs& a) {
 
 cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s) {
     ProfScope _ps(a.q_pad ? "attn_tc t2v" : "attn_tc self", s);
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("MESM_ATTN_PIPE"); pipe = (e && e[0] == '0') ? 0 : 1; }
+    if (pipe && a.Lq <= 256) {                    // one CTA per pair, heads pipelined (attn_tcp_kernel)
+        static bool attr_set_p = false;
+        if (!attr_set_p) {
+            MESM_CHECK(cudaFuncSetAttribute(tc::attn_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ATP_SMEM));
+            attr_set_p = true;
+        }
+        tc::attn_tcp_kernel<<<a.B, tc::ATP_THREADS, tc::ATP_SMEM, s>>>(a);
+        g_stats.launches++;
+        return cudaGetLastError();
+    }
     static bool attr_set = false;
     if (!attr_set) {
         MESM_CHECK(cudaFuncSetAttribute(tc::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::AT_SMEM));

@@ -20,7 +20,7 @@ struct MhaRowsArgs {
     const int* k_cu = nullptr; int k_enc = 0;
     int q_pad_ld = 0;          // 0 = Lq
 };
-cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s);      // dispatcher: tcgen05 kernel when eligible
+cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_simt = false);      // dispatcher: tcgen05 kernel when eligible
 bool attn_tc_eligible(const MhaRowsArgs& a);
 cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s);
 
