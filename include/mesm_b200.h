@@ -223,6 +223,10 @@ size_t mesm_transformer_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t 
 /* Barrier watchdog of the tcgen05 kernels (out128 = {attention[64], linear[64]}; [0] = number of barrier waits that gave up after ~2 s, then {tag, block, thread|barrier|parity} triples). */
 int mesm_debug_watchdog(unsigned long long* out128);
 
+/* In-kernel timeline of the pipelined self-attention kernel (library built with -DMESM_ATP_TRACE, tools/attn_trace.py): clock64
+ * stamps of CTA 0, [head][event]; returns the number of values written (0 in a normal build). */
+int mesm_debug_attn_trace(long long* out128);
+
 /* Test hook (tests/test_gpu_attention.py): repeated self-attention launches + the barrier watchdog record. */
 int mesm_debug_attention(const float* qkv, const uint8_t* k_pad, int32_t B, int32_t L, float* out, int32_t use_tc, int32_t iters,
                          unsigned long long* watchdog8, void* stream);

@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmesm_b200.so")
+LIB_PATH = os.environ.get("MESM_B200_LIB") or os.path.join(_HERE, "libmesm_b200.so")     # override: A/B builds of the library
 
 
 class MesmCfg(Structure):
@@ -72,6 +72,7 @@ SYMBOLS = {
     "mesm_transformer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mesm_debug_watchdog": (c_int, [c_void_p]),
+    "mesm_debug_attn_trace": (c_int, [c_void_p]),
     "mesm_debug_attention": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "mesm_debug_linear": (c_int, [c_void_p] * 9 + [c_int32] * 5 + [c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "mesm_transformer_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),

@@ -3,7 +3,7 @@
 #include "ctx.h"
 
 using namespace mesm;
-namespace mesm { void tc_read_watchdog(unsigned long long* out8); void tc_read_watchdog_linear(unsigned long long* out8); }
+namespace mesm { void tc_read_watchdog(unsigned long long* out8); void tc_read_watchdog_linear(unsigned long long* out8); int tc_read_attn_trace(long long* out128); }
 
 namespace {
 __global__ void build_enc_kernel(const float* __restrict__ src, const float* __restrict__ pos, const uint8_t* __restrict__ pad,
@@ -229,6 +229,8 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
 
 /* Barrier watchdog records of the tcgen05 kernels: out16 = {attention[8], linear[8]}; [0] != 0 means a wait gave up
  * (then [1] = tag, [2] = block, [3] = thread, [4] = barrier address, [5] = parity).  Synchronises the device; clears. */
+int mesm_debug_attn_trace(long long* out128) { return tc_read_attn_trace(out128); }
+
 int mesm_debug_watchdog(unsigned long long* out16) {
     cudaDeviceSynchronize();
     tc_read_watchdog(out16);

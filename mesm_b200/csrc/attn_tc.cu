@@ -310,6 +310,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
 // TMEM is allocated once per CTA, barriers flip once per head (parity = head & 1).  The one-CTA-per-(pair, head) kernel above
 // spent its ~14 us per CTA in strictly serial phases (tensor pipe 7 % active, ncu profiles/r1_final_kernels_ncu.md).
 // =====================================================================================================================
+// In-kernel timeline of CTA 0 (compile with -DMESM_ATP_TRACE; read back with mesm_debug_trace): slot [head][event] = clock64.
+#ifdef MESM_ATP_TRACE
+__device__ long long g_atp_trace[8 * 16];
+#define ATRACE(h, ev) do { if (blockIdx.x == 0) g_atp_trace[(h) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define ATRACE(h, ev) do { } while (0)
+#endif
 constexpr int ATP_THREADS = 32 + 256 + 128;
 constexpr int ATP_MASK = AT_P + 4 * 16384;                  // 2 x {own[8], partner[8], nkb_eff, pad} u32 (128 B per buffer)
 constexpr int ATP_T = ATP_MASK + 256;                       // epilogue transpose scratch: 8 warps x 32 rows x 36 floats
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
         for (int h = 0; h < NH; ++h) {
             const int bp = quirk ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
             if (h > 0) mbar_wait(bars + 8 * (nact - 1), (h - 1) & 1, 600 + h);      // S MMAs of the previous head retired: K / Q free
+            if (t == 0) ATRACE(h, 0);
             {   // K -> bf16 hi/lo, K-major SWIZZLE_64B rows of 32
                 const int total = Lkp * 8;
                 for (int base = t; base < total; base += 128 * 4) {
@@ -431,7 +439,9 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_kq);
+            if (t == 0) ATRACE(h, 1);
             if (h > 0) mbar_wait(bars + 16 + 8 * (nact - 1), (h - 1) & 1, 620 + h);  // P V MMAs of the previous head retired: V free
+            if (t == 0) ATRACE(h, 2);
             {   // V^T -> bf16 hi/lo: per 32-key block a [32 dims][32 keys] K-major tile
                 const int total = Lkp * 8;
                 for (int base = t; base < total; base += 128 * 4) {
@@ -462,6 +472,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_v);
+            if (t == 0) ATRACE(h, 3);
         }
     } else if (warp == 0) {
         // ================================ MMA issuer ================================
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
             int pu = 0;
             for (int h = 0; h < NH; ++h) {
                 mbar_wait(bar_kq, h & 1, 700 + h);
+                ATRACE(h, 4);
                 tc_fence_after();
                 const int nkb_eff = (int)masks[32 * (h & 1) + 16];
                 const uint32_t idesc_s = make_idesc(nkb_eff * 32);
@@ -485,11 +497,12 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     }
                     umma_commit(bars + 8 * t2);
                 }
+                ATRACE(h, 5);
                 for (int j = 0; j < nkb_eff; ++j, ++pu) {                  // O_t += P_t,j V_j
                     const int slot = pu & 1;
                     for (int t2 = 0; t2 < nact; ++t2) {
                         mbar_wait(bars + 32 + 16 * t2 + 8 * slot, (pu >> 1) & 1, 100 + t2);
-                        if (j == 0 && t2 == 0) mbar_wait(bar_v, h & 1, 720 + h);
+                        if (j == 0 && t2 == 0) { ATRACE(h, 6); mbar_wait(bar_v, h & 1, 720 + h); ATRACE(h, 7); }
                         tc_fence_after();
                         const uint32_t ph_ = sbase + AT_P + (t2 * 2 + slot) * 16384, pl_ = ph_ + 8192;
                         const uint32_t vh_ = sbase + AT_VHI + j * 2048, vl_ = sbase + AT_VLO + j * 2048;
@@ -505,6 +518,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                         if (j == nkb_eff - 1) umma_commit(bars + 16 + 8 * t2);
                     }
                 }
+                ATRACE(h, 8);
             }
         }
     } else {
@@ -524,6 +538,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                 const int bp = quirk ? (int)(((long long)bg * NH + h) % a.Btot) : bg;
                 const bool rflag = quirk && a.q_pad[(long long)bp * q_pad_ld + (qi < Lq ? qi : 0)];
                 mbar_wait(bars + 8 * wt, hp, 200 + wt);
+                if (threadIdx.x == 32) ATRACE(h, 9);
                 tc_fence_after();
                 const uint32_t* kmask_own = masks + 32 * hp;
                 const uint32_t* kmask_oth = kmask_own + 8;
@@ -540,6 +555,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     }
                 }
                 const float mxl = mx * 1.4426950408889634f;
+                if (threadIdx.x == 32) ATRACE(h, 10);
                 // pass 2: p = exp(s - max) -> bf16 hi/lo A-operand blocks of 32 keys, double-buffered against the P V MMAs
                 float sum = 0.f;
                 for (int c = 0; c < nkb_eff; ++c, ++pu) {
@@ -578,7 +594,9 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     if (lane == 0) mbar_arrive(bar_Pfull + 8 * slot);
                 }
                 // epilogue: O / rowsum, transposed through this warp's private scratch
+                if (threadIdx.x == 32) ATRACE(h, 11);
                 mbar_wait(bars + 16 + 8 * wt, hp, 400 + wt);
+                if (threadIdx.x == 32) ATRACE(h, 12);
                 tc_fence_after();
                 if (wact) {
                     float o[32];
@@ -599,6 +617,7 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     }
                     __syncwarp();                    // scratch is rewritten by the next head's epilogue
                 }
+                if (threadIdx.x == 32) ATRACE(h, 13);
             }
         }
     }
@@ -612,6 +631,15 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
 }
 
 }  // namespace tc
+
+int tc_read_attn_trace(long long* out128) {
+#ifdef MESM_ATP_TRACE
+    return cudaMemcpyFromSymbol(out128, tc::g_atp_trace, sizeof(long long) * 128) == cudaSuccess ? 128 : 0;
+#else
+    (void)out128;
+    return 0;
+#endif
+}
 
 void tc_read_watchdog(unsigned long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_watchdog, 512); unsigned long long z[64] = {0}; cudaMemcpyToSymbol(tc::g_tc_watchdog, z, 512); }
 
