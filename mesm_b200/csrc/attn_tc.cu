@@ -89,25 +89,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
             for (int u = 0; u < 4; ++u) {
                 const int idx = base + u * 256, key = idx >> 3, c4 = idx & 7;
                 if (idx >= total) break;
-                const float kk[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w}, vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
-                __nv_bfloat16 kh[4], kl[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split_bf16(kk[e], kh[e], kl[e]);
+                const float vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                uint2 kh2, kl2;
+                split_bf16x2(kv[u].x, kv[u].y, kh2.x, kl2.x);
+                split_bf16x2(kv[u].z, kv[u].w, kh2.y, kl2.y);
                 const int kb = sw64(key, c4 * 4);
-                *reinterpret_cast<uint2*>(smem + AT_KHI + kb) =
-                    make_uint2((uint32_t)__bfloat16_as_ushort(kh[0]) | ((uint32_t)__bfloat16_as_ushort(kh[1]) << 16),
-                               (uint32_t)__bfloat16_as_ushort(kh[2]) | ((uint32_t)__bfloat16_as_ushort(kh[3]) << 16));
-                *reinterpret_cast<uint2*>(smem + AT_KLO + kb) =
-                    make_uint2((uint32_t)__bfloat16_as_ushort(kl[0]) | ((uint32_t)__bfloat16_as_ushort(kl[1]) << 16),
-                               (uint32_t)__bfloat16_as_ushort(kl[2]) | ((uint32_t)__bfloat16_as_ushort(kl[3]) << 16));
+                *reinterpret_cast<uint2*>(smem + AT_KHI + kb) = kh2;
+                *reinterpret_cast<uint2*>(smem + AT_KLO + kb) = kl2;
                 const int jb = (key >> 5) * 2048, col = key & 31;
+uint32_t vh2[2], vl2[2];
+                split_bf16x2(vvv[0], vvv[1], vh2[0], vl2[0]);
+                split_bf16x2(vvv[2], vvv[3], vh2[1], vl2[1]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat16 vh, vl;
-                    split_bf16(vvv[e], vh, vl);
                     const int vb = jb + sw64(c4 * 4 + e, col);
-                    *reinterpret_cast<__nv_bfloat16*>(smem + AT_VHI + vb) = vh;
-                    *reinterpret_cast<__nv_bfloat16*>(smem + AT_VLO + vb) = vl;
+                    *reinterpret_cast<uint16_t*>(smem + AT_VHI + vb) = (uint16_t)(vh2[e >> 1] >> ((e & 1) * 16));
+                    *reinterpret_cast<uint16_t*>(smem + AT_VLO + vb) = (uint16_t)(vl2[e >> 1] >> ((e & 1) * 16));
                 }
             }
         }
@@ -150,17 +147,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
                 const int qi = tile * 128 + row;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (qi < Lq) q = __ldg(reinterpret_cast<const float4*>(a.q + (qbase + qi) * a.ldq + h * 32 + c4 * 4));
-                const float qq[4] = {q.x * a.q_scale, q.y * a.q_scale, q.z * a.q_scale, q.w * a.q_scale};
-                __nv_bfloat16 qh[4], ql[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) split_bf16(qq[u], qh[u], ql[u]);
+                uint2 qh2, ql2;
+                split_bf16x2(q.x * a.q_scale, q.y * a.q_scale, qh2.x, ql2.x);
+                split_bf16x2(q.z * a.q_scale, q.w * a.q_scale, qh2.y, ql2.y);
                 const int qb = sw64(row, c4 * 4);
-                *reinterpret_cast<uint2*>(qs + qb) =
-                    make_uint2((uint32_t)__bfloat16_as_ushort(qh[0]) | ((uint32_t)__bfloat16_as_ushort(qh[1]) << 16),
-                               (uint32_t)__bfloat16_as_ushort(qh[2]) | ((uint32_t)__bfloat16_as_ushort(qh[3]) << 16));
-                *reinterpret_cast<uint2*>(qs + 8192 + qb) =
-                    make_uint2((uint32_t)__bfloat16_as_ushort(ql[0]) | ((uint32_t)__bfloat16_as_ushort(ql[1]) << 16),
-                               (uint32_t)__bfloat16_as_ushort(ql[2]) | ((uint32_t)__bfloat16_as_ushort(ql[3]) << 16));
+                *reinterpret_cast<uint2*>(qs + qb) = qh2;
+                *reinterpret_cast<uint2*>(qs + 8192 + qb) = ql2;
             }
         }
         fence_proxy_async();
@@ -382,17 +374,12 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     for (int u = 0; u < 4; ++u) {
                         const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
                         if (idx >= total) break;
-                        const float kk[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
-                        __nv_bfloat16 kh[4], kl[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) split_bf16(kk[e], kh[e], kl[e]);
+                        uint2 kh2, kl2;
+                        split_bf16x2(kv[u].x, kv[u].y, kh2.x, kl2.x);
+                        split_bf16x2(kv[u].z, kv[u].w, kh2.y, kl2.y);
                         const int kb = sw64(key, c4 * 4);
-                        *reinterpret_cast<uint2*>(smem + AT_KHI + kb) =
-                            make_uint2((uint32_t)__bfloat16_as_ushort(kh[0]) | ((uint32_t)__bfloat16_as_ushort(kh[1]) << 16),
-                                       (uint32_t)__bfloat16_as_ushort(kh[2]) | ((uint32_t)__bfloat16_as_ushort(kh[3]) << 16));
-                        *reinterpret_cast<uint2*>(smem + AT_KLO + kb) =
-                            make_uint2((uint32_t)__bfloat16_as_ushort(kl[0]) | ((uint32_t)__bfloat16_as_ushort(kl[1]) << 16),
-                                       (uint32_t)__bfloat16_as_ushort(kl[2]) | ((uint32_t)__bfloat16_as_ushort(kl[3]) << 16));
+                        *reinterpret_cast<uint2*>(smem + AT_KHI + kb) = kh2;
+                        *reinterpret_cast<uint2*>(smem + AT_KLO + kb) = kl2;
                     }
                 }
             }
@@ -409,17 +396,12 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int idx = t + 128 * i, row = idx >> 3, c4 = idx & 7;
-                    const float qq[4] = {qv[i].x * a.q_scale, qv[i].y * a.q_scale, qv[i].z * a.q_scale, qv[i].w * a.q_scale};
-                    __nv_bfloat16 qh[4], ql[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) split_bf16(qq[u], qh[u], ql[u]);
+                    uint2 qh2, ql2;
+                    split_bf16x2(qv[i].x * a.q_scale, qv[i].y * a.q_scale, qh2.x, ql2.x);
+                    split_bf16x2(qv[i].z * a.q_scale, qv[i].w * a.q_scale, qh2.y, ql2.y);
                     const int qb = sw64(row, c4 * 4);
-                    *reinterpret_cast<uint2*>(qs + qb) =
-                        make_uint2((uint32_t)__bfloat16_as_ushort(qh[0]) | ((uint32_t)__bfloat16_as_ushort(qh[1]) << 16),
-                                   (uint32_t)__bfloat16_as_ushort(qh[2]) | ((uint32_t)__bfloat16_as_ushort(qh[3]) << 16));
-                    *reinterpret_cast<uint2*>(qs + 8192 + qb) =
-                        make_uint2((uint32_t)__bfloat16_as_ushort(ql[0]) | ((uint32_t)__bfloat16_as_ushort(ql[1]) << 16),
-                                   (uint32_t)__bfloat16_as_ushort(ql[2]) | ((uint32_t)__bfloat16_as_ushort(ql[3]) << 16));
+                    *reinterpret_cast<uint2*>(qs + qb) = qh2;
+                    *reinterpret_cast<uint2*>(qs + 8192 + qb) = ql2;
                 }
             }
             if (warp == 9) {                                                   // per-block key masks of this head
@@ -458,13 +440,14 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                         if (idx >= total) break;
                         const float vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
                         const int jb = (key >> 5) * 2048, col = key & 31;
+uint32_t vh2[2], vl2[2];
+                        split_bf16x2(vvv[0], vvv[1], vh2[0], vl2[0]);
+                        split_bf16x2(vvv[2], vvv[3], vh2[1], vl2[1]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            __nv_bfloat16 vh, vl;
-                            split_bf16(vvv[e], vh, vl);
                             const int vb = jb + sw64(c4 * 4 + e, col);
-                            *reinterpret_cast<__nv_bfloat16*>(smem + AT_VHI + vb) = vh;
-                            *reinterpret_cast<__nv_bfloat16*>(smem + AT_VLO + vb) = vl;
+                            *reinterpret_cast<uint16_t*>(smem + AT_VHI + vb) = (uint16_t)(vh2[e >> 1] >> ((e & 1) * 16));
+                            *reinterpret_cast<uint16_t*>(smem + AT_VLO + vb) = (uint16_t)(vl2[e >> 1] >> ((e & 1) * 16));
                         }
                     }
                 }

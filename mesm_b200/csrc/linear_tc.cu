@@ -311,23 +311,18 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int row = r0 + i * ROW_STEP;
-                __nv_bfloat16 h[VEC], l[VEC];
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) split_bf16(cur[i * VEC + j], h[j], l[j]);
                 const int byte = sw64(row, cv * VEC);
                 if (VEC == 4) {
                     uint2 ph2, pl2;
-                    ph2.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-                    ph2.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-                    pl2.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-                    pl2.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+                    split_bf16x2(cur[i * VEC], cur[i * VEC + 1], ph2.x, pl2.x);
+                    split_bf16x2(cur[i * VEC + 2], cur[i * VEC + 3], ph2.y, pl2.y);
                     *reinterpret_cast<uint2*>(a_hi + byte) = ph2;
                     *reinterpret_cast<uint2*>(a_lo + byte) = pl2;
                 } else {
-                    *reinterpret_cast<uint32_t*>(a_hi + byte) =
-                        (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-                    *reinterpret_cast<uint32_t*>(a_lo + byte) =
-                        (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+                    uint32_t ph, pl;
+                    split_bf16x2(cur[i * VEC], cur[i * VEC + 1], ph, pl);
+                    *reinterpret_cast<uint32_t*>(a_hi + byte) = ph;
+                    *reinterpret_cast<uint32_t*>(a_lo + byte) = pl;
                 }
             }
             fence_proxy_async();                     // make the generic-proxy stores visible to the tensor-core (async) proxy

@@ -186,6 +186,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 // byte offset of element (row, k) inside a K-major SWIZZLE_64B tile whose rows hold BK = 32 bf16
 __device__ __forceinline__ int sw64(int row, int k) { return row * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) << 4) | ((k & 7) << 1)); }
 
+// Two floats -> packed bf16 hi and lo words (element a in the low half).  One F2FP.PACK_AB per word: the scalar
+// __float2bfloat16_rn compiles to F2F.BF16.F32, which issues on the quarter-rate conversion unit (16 lanes/clk/SM) - 64 of them
+// per K block and thread made the operand converters of linear_tc XU-bound.  Bit-identical to split_bf16 per element.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
