@@ -102,3 +102,53 @@ def test_repeated_forwards_are_bit_stable_and_watchdog_silent():
     _lib.lib().mesm_debug_watchdog(wd)
     assert wd[0] == 0 and wd[64] == 0, list(wd)[:8] + list(wd)[64:72]
     assert not torch.isnan(ref["pred_logits"]).any()
+
+
+@pytest.mark.parametrize("cfg_name,lv,groups", [("charades_vgg", 200, 40), ("tacos", 200, 24), ("qvhighlights", 75, 48)])
+def test_benchmark_shapes_properties(cfg_name, lv, groups):
+    """BASELINE.json configs[2] / [3] / [4] at their benchmark shapes (Lv = 200 VGG / C3D features, TwoMLP, QVH grouping), where the
+    CPU oracle is too slow to run in a test: size-independent properties instead - packed rows == padded rows at the valid clips,
+    chunking is invisible, a pair's scores do not depend on which other pairs share its batch when the lengths are uniform, and the
+    decode of the result is well formed."""
+    import mesm_b200
+    from mesm_b200.ingest import clip_counts
+    from oracle.config import CONFIGS
+    from oracle.weights import make_inputs, make_neg_index, make_state_dict
+    cfg = CONFIGS[cfg_name]
+    g = torch.Generator().manual_seed(11)
+    nc = torch.randint(1, 5 if cfg_name != "tacos" else 11, (groups,), generator=g).tolist()
+    sd = make_state_dict(cfg, 5)
+    inp = make_inputs(cfg, nc, 6, lv=lv, ragged_video=cfg_name != "qvhighlights")
+    neg = make_neg_index(nc, 7)
+    eng = mesm_b200.Engine(engine_cfg(cfg), chunk_pairs=64)
+    eng.load_state_dict(sd)
+    dev = eng.device
+    args = (inp["video_feat"].to(dev), inp["video_mask"].to(dev), inp["words_feat"].to(dev), inp["num_clips"])
+    vm = inp["video_mask"]
+    a = eng.forward(*args, neg_index=neg.to(dev), want=("core", "aux", "rec"))
+    b = eng.forward(*args, neg_index=neg.to(dev), want=("core", "aux", "rec"), video_len=clip_counts(vm))
+    eng.set_chunk_pairs(17)
+    c = eng.forward(*args, neg_index=neg.to(dev), want=("core",), video_len=clip_counts(vm))
+    torch.cuda.synchronize()
+    for k in ("pred_logits", "pred_spans", "aux_logits", "aux_spans", "recon_feat"):
+        assert not torch.isnan(a[k]).any(), k
+        assert rel_err(b[k], a[k]) < 1e-4, k
+    for k in ("saliency_scores", "neg_saliency_scores"):
+        assert rel_err(b[k], a[k], vm) < 1e-4, k
+    assert rel_err(b["enhanced_video_feat"], a["enhanced_video_feat"], vm[..., None]) < 1e-4
+    for k in ("pred_logits", "pred_spans"):
+        assert rel_err(c[k], b[k]) < 1e-4, k
+    assert rel_err(c["saliency_scores"], b["saliency_scores"], vm) < 1e-4
+    # decode: ranked by score, windows inside [0, max_ts], kept set is a subset of the queries in rank order
+    win, order, keep, cnt = mesm_b200.decode_nms(b["pred_logits"], b["pred_spans"], inp["duration"].to(dev), cfg.clip_len,
+                                                 cfg.max_ts_val, 0.7, 10, 10)
+    w = win.cpu()
+    assert (w[:, :-1, 2] >= w[:, 1:, 2]).all() and (w[..., 0] >= 0).all() and (w[..., 1] <= cfg.max_ts_val).all()
+    assert (w[..., 1] >= w[..., 0]).all() and (cnt.cpu() >= 1).all()
+    for i in range(0, w.shape[0], 7):
+        kp = keep[i, :int(cnt[i])].tolist()
+        assert kp[0] == int(order[i, 0]) and len(set(kp)) == len(kp)
+    if cfg_name == "qvhighlights":                  # uniform lengths: no cross-pair coupling -> a sub-batch reproduces its pairs
+        n0 = sum(nc[:groups // 2])
+        sub = eng.forward(args[0][:n0], args[1][:n0], args[2][:n0], inp["num_clips"][:groups // 2], want=("core",))
+        assert rel_err(sub["pred_logits"], a["pred_logits"][:n0]) < 1e-4 and rel_err(sub["pred_spans"], a["pred_spans"][:n0]) < 1e-4
