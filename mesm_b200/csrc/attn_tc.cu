@@ -436,19 +436,27 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
+                        // lanes l and l ^ 8 hold the same four dims of keys k (even) and k + 1: swap halves so that the even lane
+                        // owns dims 0,1 and the odd lane dims 2,3 of BOTH keys - adjacent keys are adjacent bf16 of a V^T row, so
+                        // each lane writes two packed 32-bit words per plane instead of four 16-bit ones (idx < total is
+                        // uniform per lane pair: total is a multiple of 256)
                         const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
-                        if (idx >= total) break;
-                        const float vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
-                        const int jb = (key >> 5) * 2048, col = key & 31;
-uint32_t vh2[2], vl2[2];
-                        split_bf16x2(vvv[0], vvv[1], vh2[0], vl2[0]);
-                        split_bf16x2(vvv[2], vvv[3], vh2[1], vl2[1]);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int vb = jb + sw64(c4 * 4 + e, col);
-                            *reinterpret_cast<uint16_t*>(smem + AT_VHI + vb) = (uint16_t)(vh2[e >> 1] >> ((e & 1) * 16));
-                            *reinterpret_cast<uint16_t*>(smem + AT_VLO + vb) = (uint16_t)(vl2[e >> 1] >> ((e & 1) * 16));
-                        }
+                        const bool odd = key & 1;
+                        const float s0 = __shfl_xor_sync(0xffffffffu, odd ? vv[u].x : vv[u].z, 8);
+                        const float s1 = __shfl_xor_sync(0xffffffffu, odd ? vv[u].y : vv[u].w, 8);
+                        if (idx >= total) continue;
+                        const float a0 = odd ? s0 : vv[u].x, b0 = odd ? vv[u].z : s0;      // (key even, key odd) of this lane's first dim
+                        const float a1 = odd ? s1 : vv[u].y, b1 = odd ? vv[u].w : s1;      // ... second dim
+                        const int d0 = c4 * 4 + (odd ? 2 : 0);
+                        const int jb = (key >> 5) * 2048, col = key & 30;
+                        uint32_t h0, l0, h1, l1;
+                        split_bf16x2(a0, b0, h0, l0);
+                        split_bf16x2(a1, b1, h1, l1);
+                        const int vb0 = jb + sw64(d0, col), vb1 = jb + sw64(d0 + 1, col);
+                        *reinterpret_cast<uint32_t*>(smem + AT_VHI + vb0) = h0;
+                        *reinterpret_cast<uint32_t*>(smem + AT_VLO + vb0) = l0;
+                        *reinterpret_cast<uint32_t*>(smem + AT_VHI + vb1) = h1;
+                        *reinterpret_cast<uint32_t*>(smem + AT_VLO + vb1) = l1;
                     }
                 }
             }
@@ -533,8 +541,13 @@ uint32_t vh2[2], vl2[2];
                         float v[32];
                         tmem_ld32(trow + c * 32, v);
                         const uint32_t mk = kmask_own[c] | (rflag ? kmask_oth[c] : 0u);
+                        if (mk == 0u) {                                      // block without masked keys (warp-uniform unless the quirk flag differs)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) mx = fmaxf(mx, v[j]);
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (!((mk >> j) & 1u)) mx = fmaxf(mx, v[j]);
+                        }
                     }
                 }
                 const float mxl = mx * 1.4426950408889634f;
@@ -548,16 +561,23 @@ uint32_t vh2[2], vl2[2];
                         float v[32];
                         tmem_ld32(trow + c * 32, v);
                         const uint32_t mk = kmask_own[c] | (rflag ? kmask_oth[c] : 0u);
+                        // exponents are <= 0 here: one MUFU.EX2 (ex2.approx.ftz, 2^-22 relative error) instead of exp2f's range fix-ups
+                        if (mk == 0u) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float p0 = ((mk >> (2 * j)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j], 1.4426950408889634f, -mxl));
-                            const float p1 = ((mk >> (2 * j + 1)) & 1u) ? 0.f : exp2f(fmaf(v[2 * j + 1], 1.4426950408889634f, -mxl));
-                            sum += p0 + p1;
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - __uint_as_float(hb << 16), p1 - __uint_as_float(hb & 0xffff0000u));
-                            hi[j] = hb;
-                            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                            for (int j = 0; j < 16; ++j) {
+                                const float p0 = ex2_approx(fmaf(v[2 * j], 1.4426950408889634f, -mxl));
+                                const float p1 = ex2_approx(fmaf(v[2 * j + 1], 1.4426950408889634f, -mxl));
+                                sum += p0 + p1;
+                                split_bf16x2(p0, p1, hi[j], lo[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float p0 = ((mk >> (2 * j)) & 1u) ? 0.f : ex2_approx(fmaf(v[2 * j], 1.4426950408889634f, -mxl));
+                                const float p1 = ((mk >> (2 * j + 1)) & 1u) ? 0.f : ex2_approx(fmaf(v[2 * j + 1], 1.4426950408889634f, -mxl));
+                                sum += p0 + p1;
+                                split_bf16x2(p0, p1, hi[j], lo[j]);
+                            }
                         }
                     } else {
 #pragma unroll
