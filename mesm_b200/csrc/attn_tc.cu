@@ -362,16 +362,16 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
             if (t == 0) ATRACE(h, 0);
             {   // K -> bf16 hi/lo, K-major SWIZZLE_64B rows of 32
                 const int total = Lkp * 8;
-                for (int base = t; base < total; base += 128 * 4) {
-                    float4 kv[4];
+                for (int base = t; base < total; base += 128 * 8) {
+                    float4 kv[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
                         kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (idx < total && key < Lk) kv[u] = __ldg(reinterpret_cast<const float4*>(a.k + (kbase + key) * a.ldk + h * 32 + c4 * 4));
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
                         if (idx >= total) break;
                         uint2 kh2, kl2;
@@ -426,16 +426,16 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
             if (t == 0) ATRACE(h, 2);
             {   // V^T -> bf16 hi/lo: per 32-key block a [32 dims][32 keys] K-major tile
                 const int total = Lkp * 8;
-                for (int base = t; base < total; base += 128 * 4) {
-                    float4 vv[4];
+                for (int base = t; base < total; base += 128 * 8) {
+                    float4 vv[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int idx = base + u * 128, key = idx >> 3, c4 = idx & 7;
                         vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (idx < total && key < Lk) vv[u] = __ldg(reinterpret_cast<const float4*>(a.v + (kbase + key) * a.ldv + h * 32 + c4 * 4));
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         // lanes l and l ^ 8 hold the same four dims of keys k (even) and k + 1: swap halves so that the even lane
                         // owns dims 0,1 and the odd lane dims 2,3 of BOTH keys - adjacent keys are adjacent bf16 of a V^T row, so
                         // each lane writes two packed 32-bit words per plane instead of four 16-bit ones (idx < total is
