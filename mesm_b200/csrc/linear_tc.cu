@@ -74,12 +74,17 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
 
     if (threadIdx.x == 0) TSTAMP(0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, nt = blockIdx.y, n0 = nt * BN;
+    // single-CTA tiles: the column tiles of a row tile are adjacent in launch order, so a row tile's operand rows are read from
+    // HBM once and from L2 by its other column tiles (N = 512 / 768 / 1024 launches used to stream A once per column tile)
+    const int ntn = (op.N + BN - 1) / BN;
+    const int mtile = PAIR ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)ntn);
+    const int nt = PAIR ? (int)blockIdx.y : (int)(blockIdx.x % (unsigned)ntn);
+    const int m0 = mtile * BM, n0 = nt * BN;
     const int nkb = nkb1 + nkbp + nkb2;
     const uint32_t cta_rank = PAIR ? (blockIdx.x & 1u) : 0u;      // cluster (2,1,1): rank 0 issues the MMAs of the pair
     // Every tile walks the K blocks in a different rotation: the CTAs of a wave start together, and without this they
     // all ask L2 for the same weight lines at the same moment (the first weight block took ~10 k cycles to arrive).
-    const int krot = (int)((blockIdx.x >> (PAIR ? 1 : 0)) % (unsigned)nkb);
+    const int krot = (int)(((unsigned)mtile >> (PAIR ? 1 : 0)) % (unsigned)nkb);
     auto rotk = [&](int it) { const int j = it + krot; return j >= nkb ? j - nkb : j; };
 
     if (threadIdx.x == 0) {
@@ -585,7 +590,8 @@ static cudaError_t launch_tc_variant(const LinearOp& op, int nkb1, int nkb2, cud
     }
     const unsigned mt = (unsigned)((op.M + tc::BM - 1) / tc::BM);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(PAIR ? ((mt + 1) & ~1u) : mt, (unsigned)((op.N + tc::BN - 1) / tc::BN), 1);
+    const unsigned ntn = (unsigned)((op.N + tc::BN - 1) / tc::BN);
+    cfg.gridDim = PAIR ? dim3((mt + 1) & ~1u, ntn, 1) : dim3(mt * ntn, 1, 1);
     cfg.blockDim = dim3(tc::THREADS, 1, 1);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = s;
