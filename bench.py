@@ -375,11 +375,13 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     h2d_box = [0]
-    vl_box = [None if vlen_host is None else sb["video_len"]]
+    vl_box = [None if vlen_host is None else sb["video_len"]] * 2
 
     def e2e_stream(total):
-        # Host order matters: a forward enqueues hundreds of launches and the launch queue is finite, so the copy of
-        # sub-batch i+1 is enqueued BEFORE the launches of sub-batch i - otherwise it would only start once they drained.
+        # Host order: scoring of sub-batch i is enqueued first, then the ingest of sub-batch i+2 into the buffer it frees.  The
+        # ragged ingest is ~800 copy commands; enqueueing it can block the host until the copy stream has drained most of them
+        # (it waits for the buffer), and with the ingest enqueued BEFORE the scoring launches that blocked time was a compute
+        # gap of 2-3 ms per sub-batch (MESM_E2E_TRACE=1: the GPU period equalled the host loop time).
         for e in freed:
             e.record(comp)
 
@@ -394,22 +396,22 @@ def main():
                     staged = mesm_b200.prepare_batch_input(dict(host, num_clips=sb["num_clips"]), dev, non_blocking=True, out=dbuf[i % 2],
                                                            shared_group_video=shared)
                     h2d_box[0] = mesm_b200.prepare_batch_input.last_h2d_bytes
-                    vl_box[0] = None if vlen_host is None else staged["video_len"]
+                    vl_box[i % 2] = None if vlen_host is None else staged["video_len"]
                 ready[i % 2].record(copy)
 
         trace = [] if os.environ.get("MESM_E2E_TRACE") else None
         t_host0 = time.perf_counter()
         prefetch(0)
+        if total > 1:
+            prefetch(1)
+        th = th1 = time.perf_counter()
         for i in range(total):
             d = dbuf[i % 2]
-            th = time.perf_counter()
-            if i + 1 < total:
-                prefetch(i + 1)
-            th1 = time.perf_counter()
+            tf0 = time.perf_counter()
             with torch.cuda.stream(comp):
                 comp.wait_event(ready[i % 2])
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
-                          dataset_name="charades", is_training=False, neg_index=d["neg_index"], video_len=vl_box[0],
+                          dataset_name="charades", is_training=False, neg_index=d["neg_index"], video_len=vl_box[i % 2],
                           shared_group_video=shared)
                 w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
@@ -418,7 +420,11 @@ def main():
                 freed[i % 2].record(comp)
                 if trace is not None:
                     e = torch.cuda.Event(enable_timing=True); e.record(comp)
-                    trace.append((e, th - t_host0, th1 - th, time.perf_counter() - th1))
+                    trace.append((e, tf0 - t_host0, th1 - th, time.perf_counter() - tf0))
+            th = time.perf_counter()
+            if i + 2 < total:
+                prefetch(i + 2)
+            th1 = time.perf_counter()
         comp.synchronize()
         copy.synchronize()
         if trace:
@@ -446,7 +452,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
-                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device prefetched on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
+                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest two sub-batches ahead on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
