@@ -12,6 +12,7 @@ Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -274,6 +275,11 @@ def main():
     del o_w
     torch.cuda.synchronize()
     _v("warmup done")
+    # Everything built so far (modules, workload, ctypes tables) is long-lived: park it in the permanent generation so that a
+    # full collection triggered by the per-step garbage (lists of clip counts, ctypes arrays) cannot stall the host for tens
+    # of milliseconds in the middle of a timed region (seen as one 55 ms forward() in MESM_E2E_TRACE runs).
+    gc.collect()
+    gc.freeze()
     if dist:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -433,8 +439,9 @@ def main():
                       f"prefetch {trace[j][2] * 1e3:6.2f} ms forward {trace[j][3] * 1e3:6.2f} ms", file=sys.stderr)
 
     d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
-    e2e_stream(nsub)
+    e2e_stream(2 * nsub)             # warm-up: both buffers, the allocator's steady state and the copy path
     torch.cuda.synchronize()
+    gc.collect()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
