@@ -426,7 +426,7 @@ def main():
                 freed[i % 2].record(comp)
                 if trace is not None:
                     e = torch.cuda.Event(enable_timing=True); e.record(comp)
-                    trace.append((e, tf0 - t_host0, th1 - th, time.perf_counter() - tf0))
+                    trace.append((e, tf0 - t_host0, th1 - th, time.perf_counter() - tf0, model._eng.last_enqueue_s))
             th = time.perf_counter()
             if i + 2 < total:
                 prefetch(i + 2)
@@ -436,7 +436,8 @@ def main():
         if trace:
             for j in range(1, len(trace)):
                 print(f"[e2e] sub {j}: gpu period {trace[j - 1][0].elapsed_time(trace[j][0]):7.2f} ms  host: t={trace[j][1] * 1e3:7.1f} "
-                      f"prefetch {trace[j][2] * 1e3:6.2f} ms forward {trace[j][3] * 1e3:6.2f} ms", file=sys.stderr)
+                      f"prefetch {trace[j][2] * 1e3:6.2f} ms forward {trace[j][3] * 1e3:6.2f} ms (engine set-up {trace[j][4][0] * 1e3:.2f}, "
+                      f"launch enqueue {trace[j][4][1] * 1e3:.2f})", file=sys.stderr)
 
     d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
     e2e_stream(2 * nsub)             # warm-up: both buffers, the allocator's steady state and the copy path

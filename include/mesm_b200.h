@@ -128,7 +128,8 @@ const char* mesm_profile_report(void);
  * (dataset/base.py:358-363, called at eval.py:62).  host_feat [B,L,Dv] fp32 and host_mask [B,L] (1 = valid) are HOST
  * buffers (pinned for asynchronous copies).  Only the valid rows of every pair cross PCIe: the collate function zero-pads
  * each video to the longest of the batch (utils/data_utils.py:66-82), so the rows after a pair's last valid clip are
- * zeros; contiguous runs are merged into one cudaMemcpyAsync each, the mask is copied whole and a kernel zero-fills
+ * zeros; contiguous runs are merged into one copy each (all of them submitted in a single cudaMemcpyBatchAsync call when the
+ * runtime has it and the stream is not the legacy default stream), the mask is copied whole and a kernel zero-fills
  * the rows with mask == 0 on the device: dev_feat ends up bit-identical to a plain copy of the zero-padded tensor.
  * num_clips (HOST [G], may be NULL): the charades / tacos collate replicates one video for every query of its group
  * (dataset/base.py:307-309).  When given, only the FIRST pair of each group is copied; the rows of the other pairs of

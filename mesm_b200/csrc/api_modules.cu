@@ -2,6 +2,10 @@
 // (drop-in classes of mesm_b200/model.py call these; the fused mesm_forward does not go through them).
 #include "ctx.h"
 
+#include <dlfcn.h>
+#include <cstdlib>
+#include <cstring>
+
 using namespace mesm;
 namespace mesm { void tc_read_watchdog(unsigned long long* out8); void tc_read_watchdog_linear(unsigned long long* out8); int tc_read_attn_trace(long long* out128); }
 
@@ -62,6 +66,19 @@ int mesm_align_scores(const float* projed_video_feat, const uint8_t* clip_mask, 
     return 0;
 }
 
+// cudaMemcpyBatchAsync (CUDA 12.8+) resolved at run time: one driver call for the ~800 ragged copies of a batch instead of one each.
+typedef cudaError_t (*memcpy_batch_fn)(void**, void**, size_t*, size_t, cudaMemcpyAttributes*, size_t*, size_t, size_t*, cudaStream_t);
+static memcpy_batch_fn resolve_memcpy_batch() {
+    static int tried = 0;
+    static memcpy_batch_fn fn = nullptr;
+    if (!tried) {
+        tried = 1;
+        const char* e = getenv("MESM_UPLOAD_BATCH");
+        if (!(e && e[0] == '0')) fn = (memcpy_batch_fn)dlsym(RTLD_DEFAULT, "cudaMemcpyBatchAsync");
+    }
+    return fn;
+}
+
 int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, float* dev_feat,
                       uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied, void* stream) {
     mesm_ctx* ctx = nullptr;
@@ -78,9 +95,18 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
     // valid rows are a prefix of each pair (utils/data_utils.py:78-82); a pair whose mask is not a prefix is copied up to its
     // last valid row.  Adjacent spans (a full-length pair followed by the next pair's prefix) are merged into one copy.
     long long run_start = -1, run_rows = 0;        // in rows of the flat [B*L] row index
+    memcpy_batch_fn batch = resolve_memcpy_batch();
+    std::vector<void*> b_dst, b_src;
+    std::vector<size_t> b_size;
     auto flush = [&]() -> cudaError_t {
         if (run_rows <= 0) return cudaSuccess;
-        cudaError_t e = cudaMemcpyAsync(dev_feat + run_start * Dv, host_feat + run_start * Dv, (size_t)run_rows * row, cudaMemcpyHostToDevice, s);
+        cudaError_t e = cudaSuccess;
+        if (batch) {
+            b_dst.push_back(dev_feat + run_start * Dv); b_src.push_back(const_cast<float*>(host_feat) + run_start * Dv);
+            b_size.push_back((size_t)run_rows * row);
+        } else {
+            e = cudaMemcpyAsync(dev_feat + run_start * Dv, host_feat + run_start * Dv, (size_t)run_rows * row, cudaMemcpyHostToDevice, s);
+        }
         total += run_rows * (long long)row;
         run_rows = 0; run_start = -1;
         return e;
@@ -103,6 +129,17 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
         if (n < L) CK(flush());
     }
     CK(flush());
+    if (batch && !b_dst.empty()) {
+        cudaMemcpyAttributes at;
+        memset(&at, 0, sizeof(at));
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t at_idx = 0, fail_idx = 0;
+        cudaError_t e = batch(b_dst.data(), b_src.data(), b_size.data(), b_dst.size(), &at, &at_idx, 1, &fail_idx, s);
+        if (e != cudaSuccess) {                      // e.g. an older driver: fall back to one copy per run
+            (void)cudaGetLastError();
+            for (size_t i = 0; i < b_dst.size(); ++i) CK(cudaMemcpyAsync(b_dst[i], b_src[i], b_size[i], cudaMemcpyHostToDevice, s));
+        }
+    }
     zero_pad_rows_kernel<<<(unsigned)((long long)B * L), 128, 0, s>>>(dev_feat, dev_mask, (long long)B * L, Dv);
     CK(cudaGetLastError());
     if (bytes_copied) *bytes_copied = total;

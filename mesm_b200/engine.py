@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and the dtype/shape checks only; ever
 libmesm_b200.so.  There is no fallback: a missing library or a non-CUDA tensor raises.
 """
 import ctypes
+import time
 from ctypes import byref, c_int64
 
 import torch
@@ -116,6 +117,7 @@ class Engine:
         ``i >= video_len[b]``): the forward then runs on packed variable-length rows and does no work on the padding.
         ``shared_group_video``: the clips of a pair are read from the first pair of its video group (what
         ``prepare_batch_input(..., shared_group_video=True)`` uploads for charades / tacos batches); needs ``video_len``."""
+        t_enter = time.perf_counter()
         video_feat = _f32(video_feat, "video_feat")
         words_feat = _f32(words_feat, "words_feat")
         vmask = _u8(video_mask, "video_mask")
@@ -159,7 +161,9 @@ class Engine:
         with torch.cuda.device(dev):
             need = self.lib.mesm_workspace_bytes(self.ctx, B, Lv, Lt, len(nc))
             ws = self._workspace(need)
+            t_call = time.perf_counter()
             check(self.lib.mesm_forward(self.ctx, byref(inp), byref(out), _ptr(ws), ws.numel(), _stream()), self.ctx)
+            self.last_enqueue_s = (t_call - t_enter, time.perf_counter() - t_call)     # host time: set-up, launch enqueue
         if "expanded_words_mask" in o:
             o["expanded_words_mask"] = o["expanded_words_mask"].view(torch.bool)
         return o
