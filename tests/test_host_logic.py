@@ -117,3 +117,29 @@ print('ok', r)
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                         "127.0.0.1", "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert p.returncode == 0, p.stdout + p.stderr
+
+
+def test_clip_counts_are_the_collate_lengths():
+    """ingest.clip_counts: index of the last valid clip + 1 (= `lengths` of utils/data_utils.py:64 for prefix masks), >= 1."""
+    from mesm_b200.ingest import clip_counts
+    L = 9
+    lens = torch.tensor([9, 1, 4, 7])
+    mask = torch.arange(L)[None] < lens[:, None]
+    assert clip_counts(mask).tolist() == lens.tolist() and clip_counts(mask).dtype == torch.int32
+    holes = torch.tensor([[1, 1, 0, 1, 0, 0], [0, 0, 0, 0, 0, 0], [1, 1, 1, 1, 1, 1], [0, 0, 0, 0, 0, 1]], dtype=torch.bool)
+    assert clip_counts(holes).tolist() == [4, 1, 6, 6]
+    assert clip_counts(mask.float()).tolist() == lens.tolist()          # the collate's float mask before .bool()
+
+
+def test_header_and_binding_agree_on_struct_layouts():
+    """mesm_inputs / mesm_cfg field order in include/mesm_b200.h == the ctypes Structures (a silent mismatch would shift pointers)."""
+    from mesm_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mesm_b200.h")).read()
+    def fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return [re.search(r"(\w+)\s*;", ln).group(1) for ln in body.split("\n") if ";" in ln]
+    assert fields("mesm_inputs") == [f[0] for f in _lib.MesmInputs._fields_]
+    assert fields("mesm_cfg") == [f[0] for f in _lib.MesmCfg._fields_]
+    assert fields("mesm_outputs") == [f[0] for f in _lib.MesmOutputs._fields_]
+    assert fields("mesm_decode_params") == [f[0] for f in _lib.MesmDecodeParams._fields_]
