@@ -18,7 +18,8 @@ from . import _lib
 from ._lib import check
 from .engine import _ptr, _stream
 
-_SKIP = ("words_weight",)       # stays on the CPU in the reference as well (dataset/base.py:360-361)
+_SKIP = ("words_weight",        # stays on the CPU in the reference as well (dataset/base.py:360-361)
+         "video_len")           # host clip counts added by this function: the engine reads them on the host
 
 
 def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=None, num_clips=None):
