@@ -161,12 +161,17 @@ int mesm_decode_nms(const float* pred_logits,   /* dev [B,nq,2] */
                     double*  windows,           /* dev [B,nq,3]  ranked [st,ed,score] after post-processing */
                     int32_t* order,             /* dev [B,nq]    query index at each rank */
                     int32_t* keep,              /* dev [B,max_after_nms] query indices kept by NMS, -1 padded (NULL ok) */
-                    int32_t* keep_count,        /* dev [B] (NULL ok) */
+                    int32_t* keep_count,        /* dev [B] (NULL ok); a single candidate (min(max_before_nms, nq) == 1) is always
+                                                   kept, even with max_after_nms == 0 (utils/temporal_nms.py:38-39) */
                     void* stream);
+/* NMS ranks its candidates - the first max_before_nms windows of the output order - by their rounded score (stable), as
+ * utils/temporal_nms.py:41 does, whether or not sort_results ranked the windows first.  The foreground score is
+ * 1/(1+exp(l1-l0)) evaluated in fp64 and rounded once to fp32. */
 
 /* replaces utils.temporal_nms (utils/temporal_nms.py:25-74) on ragged candidate lists:
  * windows dev [total,3] fp64 rows [st,ed,score]; list i = rows [offsets[i], offsets[i+1]); n_i <= 1024.
- * keep[i, :keep_count[i]] = positions (within list i) of the survivors in output order. */
+ * keep[i, :keep_count[i]] = positions (within list i) of the survivors in output order.  A list longer than 1024 rows is
+ * not processed: its keep_count is set to -1 (the offsets live on the device, so the host cannot reject it up front). */
 int mesm_temporal_nms(const double* windows, const int64_t* offsets, int32_t n_lists, double nms_thd,
                       int32_t max_after_nms, int32_t* keep, int32_t* keep_count, void* stream);
 

@@ -2,7 +2,6 @@
 // (drop-in classes of mesm_b200/model.py call these; the fused mesm_forward does not go through them).
 #include "ctx.h"
 
-#include <dlfcn.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -66,17 +65,32 @@ int mesm_align_scores(const float* projed_video_feat, const uint8_t* clip_mask, 
     return 0;
 }
 
-// cudaMemcpyBatchAsync (CUDA 12.8+) resolved at run time: one driver call for the ~800 ragged copies of a batch instead of one each.
-typedef cudaError_t (*memcpy_batch_fn)(void**, void**, size_t*, size_t, cudaMemcpyAttributes*, size_t*, size_t, size_t*, cudaStream_t);
-static memcpy_batch_fn resolve_memcpy_batch() {
-    static int tried = 0;
-    static memcpy_batch_fn fn = nullptr;
-    if (!tried) {
-        tried = 1;
-        const char* e = getenv("MESM_UPLOAD_BATCH");
-        if (!(e && e[0] == '0')) fn = (memcpy_batch_fn)dlsym(RTLD_DEFAULT, "cudaMemcpyBatchAsync");
-    }
-    return fn;
+// cudaMemcpyBatchAsync (CUDA 12.8+): one driver call for the ~800 ragged copies of a batch instead of one each.  Called
+// directly through the prototype of the toolkit this library is compiled AND linked against (libcudart.so.12 is a versioned
+// dependency of the .so), never through dlsym: CUDA 13 dropped the `failIdx` argument, so a run-time lookup could bind a
+// function with a different signature.  MESM_UPLOAD_BATCH=0 forces the per-copy path.
+#if defined(CUDART_VERSION) && CUDART_VERSION >= 12080
+#define MESM_HAVE_MEMCPY_BATCH 1
+static cudaError_t memcpy_batch_h2d(std::vector<void*>& dst, std::vector<void*>& src, std::vector<size_t>& size, cudaStream_t s) {
+    cudaMemcpyAttributes at;
+    memset(&at, 0, sizeof(at));
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t at_idx = 0;
+#if CUDART_VERSION >= 13000
+    return cudaMemcpyBatchAsync(dst.data(), src.data(), size.data(), dst.size(), &at, &at_idx, 1, s);
+#else
+    size_t fail_idx = 0;
+    return cudaMemcpyBatchAsync(dst.data(), src.data(), size.data(), dst.size(), &at, &at_idx, 1, &fail_idx, s);
+#endif
+}
+#else
+#define MESM_HAVE_MEMCPY_BATCH 0
+static cudaError_t memcpy_batch_h2d(std::vector<void*>&, std::vector<void*>&, std::vector<size_t>&, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
+static bool use_memcpy_batch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MESM_UPLOAD_BATCH"); v = (MESM_HAVE_MEMCPY_BATCH && !(e && e[0] == '0')) ? 1 : 0; }
+    return v == 1;
 }
 
 int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, float* dev_feat,
@@ -95,7 +109,7 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
     // valid rows are a prefix of each pair (utils/data_utils.py:78-82); a pair whose mask is not a prefix is copied up to its
     // last valid row.  Adjacent spans (a full-length pair followed by the next pair's prefix) are merged into one copy.
     long long run_start = -1, run_rows = 0;        // in rows of the flat [B*L] row index
-    memcpy_batch_fn batch = resolve_memcpy_batch();
+    const bool batch = use_memcpy_batch();
     std::vector<void*> b_dst, b_src;
     std::vector<size_t> b_size;
     auto flush = [&]() -> cudaError_t {
@@ -130,11 +144,7 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
     }
     CK(flush());
     if (batch && !b_dst.empty()) {
-        cudaMemcpyAttributes at;
-        memset(&at, 0, sizeof(at));
-        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-        size_t at_idx = 0, fail_idx = 0;
-        cudaError_t e = batch(b_dst.data(), b_src.data(), b_size.data(), b_dst.size(), &at, &at_idx, 1, &fail_idx, s);
+        cudaError_t e = memcpy_batch_h2d(b_dst, b_src, b_size, s);
         if (e != cudaSuccess) {                      // e.g. an older driver: fall back to one copy per run
             (void)cudaGetLastError();
             for (size_t i = 0; i < b_dst.size(); ++i) CK(cudaMemcpyAsync(b_dst[i], b_src[i], b_size[i], cudaMemcpyHostToDevice, s));

@@ -38,9 +38,10 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs a) {
     float score = -1.f, st = 0.f, ed = 0.f;
     if (act) {
         const float l0 = a.logits[((long long)b * nq + lane) * 2], l1 = a.logits[((long long)b * nq + lane) * 2 + 1];
-        const float m = fmaxf(l0, l1);
-        const float e0 = expf(__fsub_rn(l0, m)), e1 = expf(__fsub_rn(l1, m));
-        score = __fdiv_rn(e0, __fadd_rn(e0, e1));                            // softmax(...)[..., 0]
+        // softmax over two classes = 1 / (1 + exp(l1 - l0)); evaluated in fp64 and rounded once to fp32, i.e. the correctly
+        // rounded value of what eval.py:64-66 computes in fp32 (CUDA expf and the host libm differ in the last ulp, which
+        // could cross a 4-decimal rounding boundary; the fp64 value cannot be further than that ulp from either)
+        score = (float)(1.0 / (1.0 + exp((double)l1 - (double)l0)));
         const float c = a.spans[((long long)b * nq + lane) * 2], w = a.spans[((long long)b * nq + lane) * 2 + 1];
         const float dur = a.duration[b];
         const float hw = __fmul_rn(0.5f, w);
@@ -79,18 +80,40 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs a) {
         const int rj = __shfl_sync(0xffffffffu, rank, j);
         if (rj == lane && j < nq) src = j;
     }
-    const double rs = __shfl_sync(0xffffffffu, (double)stf, src);
-    const double re = __shfl_sync(0xffffffffu, (double)edf, src);
-    const int rq = __shfl_sync(0xffffffffu, lane, src);
+    double rs = __shfl_sync(0xffffffffu, (double)stf, src);
+    double re = __shfl_sync(0xffffffffu, (double)edf, src);
+    int rq = __shfl_sync(0xffffffffu, lane, src);
     const int nb = min(a.max_before, nq);
-    // the reference re-sorts by the rounded score (stable): rounding is monotone, so the order is unchanged
+    // utils/temporal_nms.py:41 re-sorts its input (the first max_before_nms windows) by the ROUNDED score, stable.  For a
+    // ranked list (sort_results) rounding is monotone and the order is unchanged; for an unranked list (sort_results = 0)
+    // this is the only sort.  Done unconditionally: lane r takes the window of NMS rank r.
+    {
+        const double rsc = __shfl_sync(0xffffffffu, scf, src);
+        int nrank = lane;
+        if (lane < nb) nrank = 0;
+        for (int j = 0; j < nb; ++j) {
+            const double sj = __shfl_sync(0xffffffffu, rsc, j);
+            if (lane < nb && (sj > rsc || (sj == rsc && j < lane))) ++nrank;
+        }
+        int nsrc = lane;
+        for (int j = 0; j < nb; ++j) {
+            const int rj = __shfl_sync(0xffffffffu, nrank, j);
+            if (rj == lane) nsrc = j;
+        }
+        rs = __shfl_sync(0xffffffffu, rs, nsrc);
+        re = __shfl_sync(0xffffffffu, re, nsrc);
+        rq = __shfl_sync(0xffffffffu, rq, nsrc);
+    }
     unsigned alive = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
     int kept = 0;
     int* kp = a.keep + (long long)b * a.max_after;
-    if (nb == 1) {                                  // utils/temporal_nms.py:38-39
-        if (lane == 0 && a.max_after >= 1) kp[0] = rq;
-        kept = 1;
-        alive = 0;
+    if (nb == 1) {                                  // utils/temporal_nms.py:38-39: a single prediction is returned untouched,
+        if (lane == 0) {                            // whatever max_after_nms says
+            if (a.max_after >= 1) kp[0] = rq;
+            for (int i = 1; i < a.max_after; ++i) kp[i] = -1;
+            if (a.keep_count) a.keep_count[b] = 1;
+        }
+        return;
     }
     while (alive && kept < a.max_after) {
         const int head = __ffs(alive) - 1;
@@ -121,6 +144,7 @@ __global__ void __launch_bounds__(256) temporal_nms_kernel(const double* __restr
     const int n = (int)(offsets[li + 1] - lo);
     int* kp = keep + (long long)li * max_after;
     for (int i = threadIdx.x; i < max_after; i += blockDim.x) kp[i] = -1;
+    if (n > 1024 || n < 0) { if (threadIdx.x == 0) keep_count[li] = -1; return; }     // list too long for the shared-memory tables: flagged, not processed
     if (n == 0) { if (threadIdx.x == 0) keep_count[li] = 0; return; }
     if (n == 1) {                                                      // :38-39 returns the list untouched
         if (threadIdx.x == 0) { if (max_after >= 1) kp[0] = 0; keep_count[li] = 1; }

@@ -171,7 +171,8 @@ __global__ void gather_blocks_kernel(const float* __restrict__ src, float* __res
                                      int B, long long block_elems, const uint8_t* __restrict__ msrc,
                                      uint8_t* __restrict__ mdst, int mlen) {
     const int b = blockIdx.y;
-    const long long sb = idx[b];
+    long long sb = idx[b];
+    sb = sb < 0 ? 0 : (sb >= B ? B - 1 : sb);        // an out-of-range index must not read outside the batch (Engine.forward validates it in debug mode)
     const float4* s4 = reinterpret_cast<const float4*>(src + sb * block_elems);
     float4* d4 = reinterpret_cast<float4*>(dst + (long long)b * block_elems);
     const long long n4 = block_elems >> 2;

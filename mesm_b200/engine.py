@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and the dtype/shape checks only; ever
 libmesm_b200.so.  There is no fallback: a missing library or a non-CUDA tensor raises.
 """
 import ctypes
+import os
 import time
 from ctypes import byref, c_int64
 
@@ -153,6 +154,14 @@ class Engine:
             if len(vl) != B or min(vl) < 1 or max(vl) > Lv:
                 raise RuntimeError("mesm_b200: `video_len` must hold B values in [1, Lv]")
             vl_arr = (ctypes.c_int32 * B)(*vl)
+        if os.environ.get("MESM_DEBUG_CHECKS"):      # device-side contracts the fast path takes on trust (each check synchronises)
+            if neg_index is not None and (int(neg_index.min()) < 0 or int(neg_index.max()) >= B):
+                raise RuntimeError("mesm_b200: `neg_index` entries must be in [0, B)")
+            if video_len is not None:
+                m = vmask.bool()
+                ar = torch.arange(Lv, device=dev)[None]
+                if not torch.equal(m, ar < torch.tensor(vl, device=dev)[:, None]):
+                    raise RuntimeError("mesm_b200: `video_len` does not describe `video_mask` (valid clips must be a prefix)")
         inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index), vl_arr,
                          int(bool(shared_group_video)))
         out = MesmOutputs(**{k: _ptr(v) for k, v in o.items()})
@@ -197,7 +206,8 @@ def decode_nms(pred_logits, pred_spans, duration, clip_len, max_ts_val, nms_thd=
 
 
 def temporal_nms_lists(windows, offsets, nms_thd, max_after_nms):
-    """Ragged-list utils.temporal_nms: windows f64[total,3], offsets i64[n+1] (device).  -> keep i32[n,max_after], count."""
+    """Ragged-list utils.temporal_nms: windows f64[total,3], offsets i64[n+1] (device).  -> keep i32[n,max_after], count
+    (count -1: that list has more than 1024 candidates and was not processed)."""
     lib = _lib.lib()
     n = offsets.numel() - 1
     keep = torch.empty(n, max_after_nms, dtype=torch.int32, device=windows.device)

@@ -68,6 +68,8 @@ def temporal_nms(predictions, nms_thd, max_after_nms=100):
     w = torch.tensor([list(map(float, p[:3])) for p in predictions], dtype=torch.float64, device=dev)
     offs = torch.tensor([0, len(predictions)], dtype=torch.int64, device=dev)
     keep, cnt = temporal_nms_lists(w, offs, nms_thd, max(int(max_after_nms), 1) if len(predictions) == 1 else int(max_after_nms))
+    if int(cnt[0]) < 0:
+        raise ValueError("temporal_nms: at most 1024 candidates per list")
     idx = keep[0, :int(cnt[0])].tolist()
     return [list(predictions[i]) if len(predictions) == 1 else [predictions[i][0], predictions[i][1], predictions[i][2]] for i in idx]
 

@@ -21,12 +21,28 @@ from .config import OracleConfig
 # matmul precision hook: used only by oracle/precision_study.py to decide the tensor-core operand format
 # ("decide with the oracle taps, not by guess").  Default = exact fp32.
 # ----------------------------------------------------------------------------------------------------------------
-_PREC = {"mode": "fp32"}
+_PREC = {"mode": "fp32", "sites": {}, "site": None}
+_MODES = ("fp32", "bf16", "tf32_trunc", "tf32_rn", "bf16x3", "bf16x2", "fp16", "fp16x2a", "fp16x2w", "fp16x3")
 
 
-def set_matmul_precision(mode: str):
-    assert mode in ("fp32", "bf16", "tf32_trunc", "tf32_rn", "bf16x3", "bf16x2")
+def set_matmul_precision(mode: str, sites=None):
+    """``mode`` applies to every product; ``sites`` ({"ffn1": mode, "ffn2": mode, ...}) overrides it for the products
+    issued under ``_site(name)`` (the per-GEMM precision budget of oracle/precision_study.py)."""
+    assert mode in _MODES and all(m in _MODES for m in (sites or {}).values())
     _PREC["mode"] = mode
+    _PREC["sites"] = dict(sites or {})
+
+
+class _site:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.prev = _PREC["site"]
+        _PREC["site"] = self.name
+
+    def __exit__(self, *a):
+        _PREC["site"] = self.prev
 
 
 def _tf32(x, rn):
@@ -38,9 +54,19 @@ def _tf32(x, rn):
 
 def _mm(a, bt):
     """a[..., K] @ bt[..., K]^T-style product under the simulated operand precision (fp32 accumulate)."""
-    m = _PREC["mode"]
+    m = _PREC["sites"].get(_PREC["site"], _PREC["mode"])
     if m == "fp32":
         return a @ bt
+    if m.startswith("fp16"):
+        ah, bh = a.half().float(), bt.half().float()
+        if m == "fp16":
+            return ah @ bh
+        al, bl = (a - ah).half().float(), (bt - bh).half().float()
+        if m == "fp16x2a":
+            return ah @ bh + al @ bh          # activations split, weights single
+        if m == "fp16x2w":
+            return ah @ bh + ah @ bl          # weights split, activations single
+        return ah @ bh + (ah @ bl + al @ bh)
     if m == "bf16":
         return a.bfloat16().float() @ bt.bfloat16().float()
     if m in ("tf32_trunc", "tf32_rn"):
@@ -120,10 +146,11 @@ def _heads(x, H):
 def _attend(q, k, v, masked, H):
     """q [B,Lq,E] (already scaled), k [B,Lk,E], v [B,Lk,Ev]; masked bool broadcastable to [B,H,Lq,Lk] (True = -inf).
     Softmax of (scores - rowmax) as model/attention.py:360-384 (== torch's softmax)."""
-    s = _mm(_heads(q, H), _heads(k, H).transpose(-1, -2))
-    s = s.masked_fill(masked, float("-inf"))
-    p = torch.softmax(s, dim=-1)
-    o = _mm(p, _heads(v, H))
+    with _site(_PREC["site"] or "attn"):
+        s = _mm(_heads(q, H), _heads(k, H).transpose(-1, -2))
+        s = s.masked_fill(masked, float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        o = _mm(p, _heads(v, H))
     B, _, Lq, hv = o.shape
     return o.permute(0, 2, 1, 3).reshape(B, Lq, H * hv)
 
@@ -154,9 +181,10 @@ def t2v_mask(q_pad, k_pad, H):
 def ffn_post(sd, p, x, suffix=""):
     """x -> LN2(x + W2 PReLU(W1 LN1(x)))   (T2V layer tail, model/transformer.py:536-539)."""
     y = layer_norm(x, sd[p + f"norm1{suffix}.weight"], sd[p + f"norm1{suffix}.bias"])
-    y = linear(prelu(linear(y, sd[p + f"linear1{suffix}.weight"], sd[p + f"linear1{suffix}.bias"]),
-                     sd[p + "activation.weight"]),
-               sd[p + f"linear2{suffix}.weight"], sd[p + f"linear2{suffix}.bias"])
+    with _site("ffn1"):
+        h = prelu(linear(y, sd[p + f"linear1{suffix}.weight"], sd[p + f"linear1{suffix}.bias"]), sd[p + "activation.weight"])
+    with _site("ffn2"):
+        y = linear(h, sd[p + f"linear2{suffix}.weight"], sd[p + f"linear2{suffix}.bias"])
     return layer_norm(x + y, sd[p + f"norm2{suffix}.weight"], sd[p + f"norm2{suffix}.bias"])
 
 
@@ -181,8 +209,10 @@ def encoder_layer(sd, p, src, pad, pos, H):
     qk = src + pos
     a = packed_mha(sd, p + "self_attn.", qk, qk, src, pad[:, None, None, :], H)
     src = layer_norm(src + a, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-    y = linear(prelu(linear(src, sd[p + "linear1.weight"], sd[p + "linear1.bias"]), sd[p + "activation.weight"]),
-               sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    with _site("ffn1"):
+        h = prelu(linear(src, sd[p + "linear1.weight"], sd[p + "linear1.bias"]), sd[p + "activation.weight"])
+    with _site("ffn2"):
+        y = linear(h, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
     return layer_norm(src + y, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
 
 

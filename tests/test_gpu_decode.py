@@ -130,3 +130,44 @@ def test_python_wrappers_keep_reference_signatures():
     pp = U.PostProcessorDETR(clip_length=2, min_ts_val=0, max_ts_val=150, process_func_names=("clip_ts", "round_multiple"))
     out = pp(lines)[0]["pred_relevant_windows"]
     assert out == decode_oracle.post_process_windows([[1.23456, 151.0, 0.55555], [-3.0, 7.1, 0.4]], 2, 150)
+
+
+def test_decode_unsorted_list_still_ranks_inside_nms():
+    """sort_results = 0 (eval.py:89 skipped): the windows stay in query order, but utils/temporal_nms.py:41 sorts its own
+    input by the rounded score, so the kept set must equal the oracle's on the unsorted list."""
+    import mesm_b200
+    rng = np.random.default_rng(21)
+    B, nq = 512, 10
+    lg = rng.normal(size=(B, nq, 2)).astype(np.float32) * 2
+    lg[::5, 2] = lg[::5, 6]
+    sp = np.stack([rng.uniform(0, 1, (B, nq)), rng.uniform(0, 0.6, (B, nq))], -1).astype(np.float32)
+    dur = rng.uniform(5, 150, B).astype(np.float32)
+    for nb, na in ((10, 10), (6, 3)):
+        win, order, keep, cnt = mesm_b200.decode_nms(torch.from_numpy(lg).cuda(), torch.from_numpy(sp).cuda(), torch.from_numpy(dur).cuda(),
+                                                     2.0, 150.0, 0.5, nb, na, sort_results=False)
+        order, keep, cnt = order.cpu().numpy(), keep.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(B):
+            od = decode_oracle.decode_pair(lg[i], sp[i], float(dur[i]), 2.0, 150.0, 0.5, nb, na, sort_results=False)
+            assert order[i].tolist() == list(range(nq))
+            assert od["keep"] == keep[i, :cnt[i]].tolist(), i
+
+
+def test_single_candidate_and_overlong_lists():
+    """utils/temporal_nms.py:38-39 returns a single prediction untouched whatever max_after_nms is; lists beyond the kernel's
+    1024-entry tables are flagged (count -1), not processed."""
+    import mesm_b200
+    from mesm_b200 import utils as U
+    lg = torch.randn(8, 10, 2).cuda()
+    sp = torch.rand(8, 10, 2).cuda() * 0.5
+    dur = torch.full((8,), 30.0).cuda()
+    win, order, keep, cnt = mesm_b200.decode_nms(lg, sp, dur, 1.0, 150.0, 0.7, 1, 0)
+    assert cnt.tolist() == [1] * 8 and keep.shape == (8, 0)
+    win, order, keep, cnt = mesm_b200.decode_nms(lg, sp, dur, 1.0, 150.0, 0.7, 1, 3)
+    assert cnt.tolist() == [1] * 8 and torch.equal(keep[:, 0], order[:, 0]) and (keep[:, 1:] == -1).all()
+    n = 1500
+    w = torch.rand(n + 5, 3, dtype=torch.float64).cuda()
+    offs = torch.tensor([0, n, n + 5], dtype=torch.int64).cuda()
+    keep, cnt = mesm_b200.temporal_nms_lists(w, offs, 0.5, 10)
+    assert int(cnt[0]) == -1 and (keep[0] == -1).all() and int(cnt[1]) >= 1
+    with pytest.raises(ValueError):
+        U.temporal_nms(w[:n].tolist(), 0.5, 10)

@@ -129,3 +129,32 @@ def test_eval_loop_drop_in_with_shared_upload(name):
     assert rel_err(out["recon_feat"], gold["recon_feat"]) <= 1e-3
     assert rel_err(out["projed_video_feat"][:, 0], gold["projed_video_row0"]) <= 1e-3
     assert not torch.isnan(out["projed_video_feat"]).any() and not torch.isnan(out["enhanced_video_feat"]).any()
+
+
+def test_pinned_source_may_be_reused_right_after_the_call():
+    """the raw async copies must not outlive their host source.  The caller drops / overwrites its pinned tensors
+    immediately after prepare_batch_input returns (what the DataLoader's pin-memory thread does with recycled blocks)."""
+    import mesm_b200
+    from mesm_b200 import ingest
+    B, L, Dv = 64, 194, 2818
+    lens = [L] * B
+    busy = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    outs, refs = [], []
+    for it in range(6):
+        vf, mask = _batch(B, L, Dv, lens, seed=100 + it)
+        refs.append(vf.clone())
+        for _ in range(8):
+            busy.add_(1)                                   # keep the stream busy so the copy is still queued on return
+        batch = dict(video_feat=vf.pin_memory(), video_mask=mask.pin_memory(), num_clips=torch.ones(B, dtype=torch.long))
+        out = mesm_b200.prepare_batch_input(batch, "cuda", non_blocking=True)
+        outs.append(out["video_feat"])
+        del batch                  # the only outside reference: the next pin_memory() would recycle the block at once
+    torch.cuda.synchronize()
+    for it, (o, r) in enumerate(zip(outs, refs)):
+        assert torch.equal(o.cpu(), r), it                 # dropped sources stayed alive until the DMA had read them
+    assert len(ingest._inflight) <= 6
+    # pageable sources and non_blocking=False complete before the call returns
+    vf, mask = _batch(4, 8, 16, [8, 3, 8, 1], seed=9)
+    out = mesm_b200.prepare_batch_input(dict(video_feat=vf.clone(), video_mask=mask), "cuda", non_blocking=False)
+    assert torch.cuda.current_stream().query()
+    assert torch.equal(out["video_feat"].cpu(), vf)
