@@ -103,8 +103,6 @@ cudaError_t launch_linear(const LinearOp& op, cudaStream_t s);        // dispatc
 cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s);   // fp32 SIMT kernel
 cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s);     // tcgen05 split-bf16 kernel
 bool linear_tc_eligible(const LinearOp& op);
-cudaError_t launch_linear_tcp(const LinearOp& op, cudaStream_t s);    // persistent CTA-pair tcgen05 kernel
-bool linear_tcp_eligible(const LinearOp& op);
 size_t tc_packed_bytes(int nrows, int K);
 cudaError_t launch_pack_tc(const float* W, int row0, int nrows, int K, const float* gamma, void* out, cudaStream_t s);
 

@@ -32,17 +32,10 @@ constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;                       // bytes of one bf16 plane of the A tile
 constexpr int W_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;      // 49152: two CTAs (2 x ~105 KB) share one SM
-// CTA-pair mode (cta_group::2): the pair computes a 256 x 256 tile, each CTA stages its own 128 rows of A and HALF of the
-// weight tile (128 of the 256 output columns), so the L2 -> SM weight traffic per output row halves.
-constexpr int W_HALF = W_TILE / 2;
-constexpr int STAGES_PAIR = 3;
-constexpr int STAGE_BYTES_PAIR = 2 * A_TILE + 2 * W_HALF; // 32768
-static_assert(STAGES_PAIR * STAGE_BYTES_PAIR == STAGES * STAGE_BYTES, "both modes use the same operand ring size");
 constexpr int NCONV = 256;                                // converter / epilogue threads (8 warps)
 constexpr int THREADS = 64 + NCONV;
 constexpr uint32_t IDESC = make_idesc(BN);
-constexpr uint32_t IDESC_PAIR = make_idesc(BN, 256);
-constexpr int BAR_BYTES = 192;                            // full_w[4] full_a[4] empty[4] peer_full[4] tmem_full tmem_ptr
+constexpr int BAR_BYTES = 192;                            // full_w[4] full_a[4] empty[4] (unused[4]) tmem_full tmem_ptr
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + 1024 + 4096 + 3072 + 2048 /*barriers, LN exchange, epilogue vectors, row offsets*/;
 
 __device__ __forceinline__ float act_fn(float v, int act, float slope) {
@@ -53,19 +46,18 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
 }
 
 // VEC = floats per global load of the A operand (4: 16-byte aligned rows; 2: 8-byte aligned rows such as Dv = 2818)
-template <int VEC, bool PAIR>
+template <int VEC>
 __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op, const int nkb1, const int nkb2) {
     // K sweeps accumulated into one tile: A.W^T, then (if present) Apos.W^T with the same weights, then A2.W2^T.
-    constexpr int NST = PAIR ? STAGES_PAIR : STAGES;
-    constexpr int STG = PAIR ? STAGE_BYTES_PAIR : STAGE_BYTES;
-    constexpr int WT = PAIR ? W_HALF : W_TILE;             // bytes of one bf16 plane of this CTA's share of the weight tile
+    constexpr int NST = STAGES;
+    constexpr int STG = STAGE_BYTES;
+    constexpr int WT = W_TILE;                             // bytes of one bf16 plane of the weight tile
     const int nkbp = op.Apos ? nkb1 : 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + NST * STG;
-    const uint32_t bar_full_w = bar_base, bar_full_a = bar_base + 32, bar_empty = bar_base + 64, bar_peer = bar_base + 96,
-                   bar_tmem = bar_base + 128;
+    const uint32_t bar_full_w = bar_base, bar_full_a = bar_base + 32, bar_empty = bar_base + 64, bar_tmem = bar_base + 128;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + NST * STG + 136);
     float* ln_x = reinterpret_cast<float*>(smem + NST * STG + BAR_BYTES);          // [2][128] partial sums
     float* vec_s = ln_x + 256;                                                      // [4][256]: bias, colsum, ln_g, ln_b of this N tile
@@ -77,14 +69,13 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     // single-CTA tiles: the column tiles of a row tile are adjacent in launch order, so a row tile's operand rows are read from
     // HBM once and from L2 by its other column tiles (N = 512 / 768 / 1024 launches used to stream A once per column tile)
     const int ntn = (op.N + BN - 1) / BN;
-    const int mtile = PAIR ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)ntn);
-    const int nt = PAIR ? (int)blockIdx.y : (int)(blockIdx.x % (unsigned)ntn);
+    const int mtile = (int)(blockIdx.x / (unsigned)ntn);
+    const int nt = (int)(blockIdx.x % (unsigned)ntn);
     const int m0 = mtile * BM, n0 = nt * BN;
     const int nkb = nkb1 + nkbp + nkb2;
-    const uint32_t cta_rank = PAIR ? (blockIdx.x & 1u) : 0u;      // cluster (2,1,1): rank 0 issues the MMAs of the pair
     // Every tile walks the K blocks in a different rotation: the CTAs of a wave start together, and without this they
     // all ask L2 for the same weight lines at the same moment (the first weight block took ~10 k cycles to arrive).
-    const int krot = (int)(((unsigned)mtile >> (PAIR ? 1 : 0)) % (unsigned)nkb);
+    const int krot = (int)((unsigned)mtile % (unsigned)nkb);
     auto rotk = [&](int it) { const int j = it + krot; return j >= nkb ? j - nkb : j; };
 
     if (threadIdx.x == 0) {
@@ -92,23 +83,16 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
             mbar_init(bar_full_w + 8 * s, 1);
             mbar_init(bar_full_a + 8 * s, NCONV / 32);
             mbar_init(bar_empty + 8 * s, 1);
-            mbar_init(bar_peer + 8 * s, 1);
         }
         mbar_init(bar_tmem, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BN));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BN));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();                  // the peer's barriers exist before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (threadIdx.x == 0) TSTAMP(1);
@@ -167,22 +151,19 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
                                          : reinterpret_cast<const uint8_t*>(op.Wp2) + ((size_t)nt * nkb2 + kk) * (2 * W_TILE);
                 mbar_arrive_expect_tx(bar_full_w + 8 * s, 2 * WT);
                 const uint32_t dst = smem_base + s * STG + 2 * A_TILE;
-                // pair mode: this CTA's 128 of the 256 weight rows = one contiguous half of each packed plane
-                bulk_copy_g2s(dst, src + cta_rank * WT, WT, bar_full_w + 8 * s);
-                bulk_copy_g2s(dst + WT, src + W_TILE + cta_rank * WT, WT, bar_full_w + 8 * s);
+                bulk_copy_g2s(dst, src, 2 * WT, bar_full_w + 8 * s);      // hi plane, lo plane: contiguous in the packed image
             }
             __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
-            // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NST;
                 const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(bar_full_w + 8 * s, ph, 2000 + kb);
                 if (kb < 8) TSTAMP(8 + kb);
                 mbar_wait(bar_full_a + 8 * s, ph, 3000 + kb);
-                if (PAIR) mbar_wait_cluster(bar_peer + 8 * s, ph, 3500 + kb);      // the peer's half of the stage has landed
                 if (kb < 8) TSTAMP(16 + kb);
                 tc_fence_after();
                 const uint32_t a_hi = smem_base + s * STG, a_lo = a_hi + A_TILE;
@@ -192,32 +173,14 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
                     const uint32_t koff = k * 32;          // 16 bf16 = 32 bytes along K inside the 64B swizzle row
                     const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
                     const uint64_t dwh = make_desc(w_hi + koff), dwl = make_desc(w_lo + koff);
-                    if (PAIR) {
-                        umma2(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC_PAIR);
-                        umma2(tmem_base, dal, dwh, 1u, IDESC_PAIR);
-                        umma2(tmem_base, dah, dwl, 1u, IDESC_PAIR);
-                    } else {
-                        umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC);
-                        umma(tmem_base, dal, dwh, 1u, IDESC);
-                        umma(tmem_base, dah, dwl, 1u, IDESC);
-                    }
+                    umma(tmem_base, dah, dwh, (kb > 0 || k > 0) ? 1u : 0u, IDESC);
+                    umma(tmem_base, dal, dwh, 1u, IDESC);
+                    umma(tmem_base, dah, dwl, 1u, IDESC);
                 }
-                if (PAIR) umma_commit2(bar_empty + 8 * s); // stage reusable (both CTAs) once these MMAs retire
-                else umma_commit(bar_empty + 8 * s);
+                umma_commit(bar_empty + 8 * s);            // stage reusable once these MMAs retire
             }
-            if (PAIR) umma_commit2(bar_tmem);              // accumulator complete (both CTAs' epilogues)
-            else umma_commit(bar_tmem);
+            umma_commit(bar_tmem);                         // accumulator complete
             TSTAMP(2);
-        } else if (PAIR && lane == 0) {
-            // ===================== peer CTA: forward "my half of stage s is in shared memory" to the leader =============
-            const uint32_t remote = map_to_cta(bar_peer, 0);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % NST;
-                const uint32_t ph = (kb / NST) & 1;
-                mbar_wait(bar_full_w + 8 * s, ph, 2000 + kb);
-                mbar_wait(bar_full_a + 8 * s, ph, 3000 + kb);
-                mbar_arrive_remote(remote + 8 * s);
-            }
         }
     } else {
         // ===================== A converters, then epilogue =====================
@@ -503,12 +466,10 @@ __global__ void __launch_bounds__(THREADS, 2) linear_tc_kernel(const LinearOp op
     if (threadIdx.x == 64) TSTAMP(5);
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();                  // neither CTA frees TMEM / leaves while the pair is still working
     if (threadIdx.x == 0) TSTAMP(6);
     if (warp == 1) {
         __syncwarp();
-        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
 }
 
@@ -577,44 +538,35 @@ bool linear_tc_eligible(const LinearOp& op) {
     return true;
 }
 
-static int g_tc_pdl = 1;         // programmatic dependent launch of the tcgen05 linear kernels (MESM_TC_PDL=0 disables)
-static int g_tc_pair = -1;       // MESM_TC_PAIR: 0 (default) = single-CTA tiles, 1 = CTA pairs, 2 = persistent CTA pairs (linear_tcp.cu)
-void tc_set_pair_mode(int mode) { g_tc_pair = mode; }
+static int g_tc_pdl = -1;        // programmatic dependent launch of the tcgen05 linear kernels (MESM_TC_PDL=0 disables)
 
-template <int VEC, bool PAIR>
+template <int VEC>
 static cudaError_t launch_tc_variant(const LinearOp& op, int nkb1, int nkb2, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        MESM_CHECK(cudaFuncSetAttribute(tc::linear_tc_kernel<VEC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MESM_CHECK(cudaFuncSetAttribute(tc::linear_tc_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         attr_set = true;
     }
     const unsigned mt = (unsigned)((op.M + tc::BM - 1) / tc::BM);
     cudaLaunchConfig_t cfg = {};
     const unsigned ntn = (unsigned)((op.N + tc::BN - 1) / tc::BN);
-    cfg.gridDim = PAIR ? dim3((mt + 1) & ~1u, ntn, 1) : dim3(mt * ntn, 1, 1);
+    cfg.gridDim = dim3(mt * ntn, 1, 1);
     cfg.blockDim = dim3(tc::THREADS, 1, 1);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<VEC, PAIR>, op, nkb1, nkb2);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<VEC>, op, nkb1, nkb2);
 }
 
 cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s) {
-    if (g_tc_pair < 0) { const char* pe = getenv("MESM_TC_PDL"); if (pe && pe[0] == '0') g_tc_pdl = 0; }
-    if (g_tc_pair < 0) { const char* e = getenv("MESM_TC_PAIR"); g_tc_pair = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }
-    if (g_tc_pair == 2 && linear_tcp_eligible(op)) return launch_linear_tcp(op, s);
+    if (g_tc_pdl < 0) { const char* pe = getenv("MESM_TC_PDL"); g_tc_pdl = (pe && pe[0] == '0') ? 0 : 1; }
     const int nkb1 = (op.K + tc::BK - 1) / tc::BK, nkb2 = op.A2 ? (op.K2 + tc::BK - 1) / tc::BK : 0;
     auto v4 = [](const float* p, int ld, int K) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0) && (K % 4 == 0)); };
     const bool vec4 = v4(op.A, op.lda, op.K) && v4(op.Apos, op.lda, op.K) && v4(op.A2, op.lda2, op.K2);
-    const bool pair = g_tc_pair && op.M > tc::BM;
-    cudaError_t e;
-    if (pair) e = vec4 ? launch_tc_variant<4, true>(op, nkb1, nkb2, s) : launch_tc_variant<2, true>(op, nkb1, nkb2, s);
-    else e = vec4 ? launch_tc_variant<4, false>(op, nkb1, nkb2, s) : launch_tc_variant<2, false>(op, nkb1, nkb2, s);
+    const cudaError_t e = vec4 ? launch_tc_variant<4>(op, nkb1, nkb2, s) : launch_tc_variant<2>(op, nkb1, nkb2, s);
     g_stats.launches++;
     return e != cudaSuccess ? e : cudaGetLastError();
 }

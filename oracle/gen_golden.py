@@ -38,6 +38,11 @@ CASES = [
     ("charades_csf_ragged", "charades_csf", [2, 3, 1, 2], dict()),
     ("charades_vgg_l64", "charades_vgg", [2, 2, 1], dict(lv=64)),
     ("tacos_l96", "tacos", [4, 3], dict(lv=96)),
+    # benchmark shapes of BASELINE configs[2] / [3] (Lv = 200, K = 4098, 201 encoder keys; TACoS
+    # groups of up to 10 queries) and the shipped max_video_l = 600 (beyond the 224-key tcgen05 attention tile)
+    ("charades_vgg_l200", "charades_vgg", [2, 1, 2], dict(lv=200)),
+    ("tacos_l200", "tacos", [10, 3, 4], dict(lv=200)),
+    ("charades_vgg_l600", "charades_vgg", [2, 1], dict(lv=600)),
 ]
 NMS_THD = 0.7
 
@@ -88,9 +93,63 @@ def reference_decode(logits, spans, duration, cfg, nms_thd):
     return out
 
 
+def gen_decode_fixture():
+    """Random differential fixture of the decode chain: the REFERENCE's utils.temporal_nms on random candidate lists
+    (ties, duplicates, zero-length windows, several thresholds / max_after_nms) and the eval.py decode loop
+    (reference_decode above) on random logits / spans for every shipped (clip_len, max_ts) setting.  Inputs are
+    regenerated from the seeds by the tests; only the reference's answers are stored."""
+    from utils import temporal_nms
+    rng = np.random.default_rng(2024)
+    lists, answers, params = [], [], []
+    for case in range(3000):
+        n = int(rng.choice([1, 2, 3, 5, 10, 10, 10, 17, 40, 100]))
+        st = rng.uniform(0, 140, n).round(int(rng.integers(0, 3)))
+        w = np.stack([st, st + rng.uniform(0, 30, n).round(int(rng.integers(0, 3))), rng.uniform(0, 1, n).round(4)], 1)
+        if n >= 3:
+            if case % 3 == 0:
+                w[1] = w[0]                                   # exact duplicate
+            if case % 4 == 0:
+                w[2, 2] = w[0, 2]                             # score tie
+            if case % 5 == 0:
+                w[n - 1, 1] = w[n - 1, 0]                     # zero-length window
+            if case % 7 == 0:
+                w[:, :2] = w[0, :2]                           # all identical spans
+        thd = float(rng.choice([0.3, 0.5, 0.7, 0.9]))
+        na = int(rng.choice([1, 3, 10, 100]))
+        kept = temporal_nms([list(map(float, r)) for r in w], nms_thd=thd, max_after_nms=na)
+        lists.append(w)
+        answers.append(np.asarray(kept, dtype=np.float64).reshape(-1, 3))
+        params.append((thd, na))
+    out = dict(nms_lists=np.concatenate(lists), nms_offsets=np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64),
+               nms_params=np.asarray(params, dtype=np.float64),
+               nms_kept=np.concatenate(answers), nms_kept_offsets=np.concatenate([[0], np.cumsum([len(a) for a in answers])]).astype(np.int64))
+    for ci, cname in enumerate(("qvhighlights", "charades_csf", "charades_vgg", "tacos")):
+        cfg = CONFIGS[cname]
+        B, nq = 300, cfg.num_queries
+        lg = (rng.normal(size=(B, nq, 2)) * 2).astype(np.float32)
+        lg[::7, 3] = lg[::7, 5]
+        sp = np.stack([rng.uniform(0, 1, (B, nq)), rng.uniform(0, 0.6, (B, nq))], -1).astype(np.float32)
+        sp[::5, 2] = sp[::5, 4]
+        sp[::11, 6, 1] = 0
+        dur = rng.uniform(5, 150 if cfg.max_ts_val <= 150 else 900, B).astype(np.float32)
+        rd = reference_decode(torch.from_numpy(lg), torch.from_numpy(sp), torch.from_numpy(dur), cfg, NMS_THD)
+        nms_n = np.array([len(r["nms_windows"]) for r in rd], dtype=np.int32)
+        nms_w = np.zeros((B, 10, 3))
+        for i, r in enumerate(rd):
+            nms_w[i, :nms_n[i]] = np.asarray(r["nms_windows"], dtype=np.float64)
+        out.update({f"dec_{cname}_logits": lg, f"dec_{cname}_spans": sp, f"dec_{cname}_duration": dur,
+                    f"dec_{cname}_windows": np.array([r["windows"] for r in rd], dtype=np.float64),
+                    f"dec_{cname}_order": np.array([r["order"] for r in rd], dtype=np.int32),
+                    f"dec_{cname}_nms_windows": nms_w, f"dec_{cname}_nms_count": nms_n})
+    np.savez_compressed(os.path.join(GOLD, "decode_random.npz"), **out)
+    print("decode_random.npz:", len(lists), "NMS lists,", 4 * 300, "decode chains")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     sys.path.insert(0, REF)
+    if "--decode-only" in sys.argv:
+        return gen_decode_fixture()
     summary = {}
     for name, cfg_name, num_clips, kw in CASES:
         cfg = CONFIGS[cfg_name]
@@ -176,6 +235,7 @@ def main():
              xx=su.span_cxw_to_xx(torch.Tensor([[0.5, 1.0], [0.3, 0.2]])).numpy())
     with open(os.path.join(GOLD, "cases.json"), "w") as f:
         json.dump(summary, f, indent=1)
+    gen_decode_fixture()
     print("golden fixtures written to", GOLD)
 
 

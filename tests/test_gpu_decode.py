@@ -171,3 +171,38 @@ def test_single_candidate_and_overlong_lists():
     assert int(cnt[0]) == -1 and (keep[0] == -1).all() and int(cnt[1]) >= 1
     with pytest.raises(ValueError):
         U.temporal_nms(w[:n].tolist(), 0.5, 10)
+
+
+def test_decode_and_nms_match_reference_random_fixture(golden_dir):
+    """CUDA decode / NMS against the reference-generated random fixture (tests/golden/decode_random.npz)."""
+    import mesm_b200
+    from oracle.config import CONFIGS
+    g = np.load(os.path.join(golden_dir, "decode_random.npz"))
+    offs, koffs, params = g["nms_offsets"], g["nms_kept_offsets"], g["nms_params"]
+    flat = torch.from_numpy(g["nms_lists"]).cuda()
+    for thd, na in sorted({(float(a), int(b)) for a, b in params}):
+        sel = [i for i in range(len(params)) if float(params[i, 0]) == thd and int(params[i, 1]) == na]
+        sub_offs = np.concatenate([[0], np.cumsum([offs[i + 1] - offs[i] for i in sel])]).astype(np.int64)
+        sub = torch.cat([flat[offs[i]:offs[i + 1]] for i in sel])
+        keep, cnt = mesm_b200.temporal_nms_lists(sub, torch.from_numpy(sub_offs).cuda(), thd, na)
+        keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+        for j, i in enumerate(sel):
+            w = g["nms_lists"][offs[i]:offs[i + 1]]
+            ref = g["nms_kept"][koffs[i]:koffs[i + 1]]
+            assert cnt[j] == len(ref) and np.array_equal(w[keep[j, :cnt[j]]], ref), (i, thd, na)
+    mism = 0
+    for cname in ("qvhighlights", "charades_csf", "charades_vgg", "tacos"):
+        cfg = CONFIGS[cname]
+        lg, sp, dur = (torch.from_numpy(g[f"dec_{cname}_{k}"]).cuda() for k in ("logits", "spans", "duration"))
+        win, order, keep, cnt = mesm_b200.decode_nms(lg, sp, dur, cfg.clip_len, cfg.max_ts_val, 0.7, 10, 10)
+        win, order, keep, cnt = win.cpu().numpy(), order.cpu().numpy(), keep.cpu().numpy(), cnt.cpu().numpy()
+        rw = g[f"dec_{cname}_windows"]
+        assert np.array_equal(order, g[f"dec_{cname}_order"]) and np.array_equal(win[..., :2], rw[..., :2])
+        d = np.abs(win[..., 2] - rw[..., 2])
+        assert d.max() <= 1.0001e-4                    # torch's fp32 softmax vs the exactly rounded score: at most one 4-decimal quantum
+        mism += int((d > 0).sum())
+        assert np.array_equal(cnt, g[f"dec_{cname}_nms_count"])
+        for i in range(len(cnt)):
+            pos = [order[i].tolist().index(q) for q in keep[i, :cnt[i]].tolist()]
+            assert np.array_equal(rw[i][pos][:, :2], g[f"dec_{cname}_nms_windows"][i, :cnt[i], :2]), (cname, i)
+    assert mism <= 12, mism                             # 12000 scores; a handful may sit within an ulp of a rounding boundary

@@ -60,3 +60,29 @@ def test_nms_probe_cases():
     assert nms([[1, 4, .9], [1, 4, .8], [1, 4, .7]], 0.7)[1] == [0]
     assert nms([[1, 4, .3]], 0.7, max_after_nms=0)[1] == [0]
     assert nms([[0, 1, .2], [5, 6, .9], [10, 11, .5]], 0.7, max_after_nms=2)[1] == [1, 2]
+
+
+def test_decode_oracle_matches_reference_random_fixture(golden_dir):
+    """tests/golden/decode_random.npz (oracle/gen_golden.py: gen_decode_fixture): 3000 random candidate lists through the
+    REFERENCE's utils.temporal_nms and 4 x 300 random decode chains through the eval.py loop with the reference's own
+    span_cxw_to_xx / PostProcessorDETR / temporal_nms - the in-repo pin of oracle/decode_oracle.py."""
+    import os
+    g = np.load(os.path.join(golden_dir, "decode_random.npz"))
+    offs, koffs = g["nms_offsets"], g["nms_kept_offsets"]
+    for i in range(len(offs) - 1):
+        w = g["nms_lists"][offs[i]:offs[i + 1]]
+        thd, na = float(g["nms_params"][i, 0]), int(g["nms_params"][i, 1])
+        kept_w, kept_pos = decode_oracle.temporal_nms(w.tolist(), thd, na)
+        ref = g["nms_kept"][koffs[i]:koffs[i + 1]]
+        assert len(kept_w) == len(ref) and np.array_equal(np.asarray(kept_w).reshape(-1, 3), ref), i
+        assert np.array_equal(w[kept_pos], ref), i
+    from oracle.config import CONFIGS
+    for cname in ("qvhighlights", "charades_csf", "charades_vgg", "tacos"):
+        cfg = CONFIGS[cname]
+        lg, sp, dur = g[f"dec_{cname}_logits"], g[f"dec_{cname}_spans"], g[f"dec_{cname}_duration"]
+        for i in range(lg.shape[0]):
+            od = decode_oracle.decode_pair(lg[i], sp[i], float(dur[i]), cfg.clip_len, cfg.max_ts_val, 0.7, 10, 10)
+            assert od["order"] == g[f"dec_{cname}_order"][i].tolist(), (cname, i)
+            assert np.array_equal(np.asarray(od["windows"]), g[f"dec_{cname}_windows"][i]), (cname, i)
+            n = int(g[f"dec_{cname}_nms_count"][i])
+            assert np.array_equal(np.asarray(od["nms_windows"]).reshape(-1, 3), g[f"dec_{cname}_nms_windows"][i, :n]), (cname, i)

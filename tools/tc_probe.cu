@@ -8,9 +8,6 @@
 namespace mesm {
 thread_local LaunchStats g_stats;
 void tc_read_times(long long* out64);
-void tc_set_pair_mode(int on);
-void tcp_read_times(long long* out128);
-void tcp_set_flags(int f);
 }
 using namespace mesm;
 
@@ -20,9 +17,7 @@ int main(int argc, char** argv) {
     const int M = argc > 1 ? atoi(argv[1]) : 74496, N = argc > 2 ? atoi(argv[2]) : 256, K = argc > 3 ? atoi(argv[3]) : 256;
     const int pos = argc > 4 ? atoi(argv[4]) : 0, resln = argc > 5 ? atoi(argv[5]) : 0, iters = argc > 6 ? atoi(argv[6]) : 20;
     const int pair = argc > 7 ? atoi(argv[7]) : 1;
-    tc_set_pair_mode(pair);
     const int flush = argc > 8 ? atoi(argv[8]) : 1, flags = argc > 9 ? atoi(argv[9]) : 0;
-    tcp_set_flags(flags);
     float *A, *P, *W, *out, *R, *g, *b, *bias; void* Wp;
     CKE(cudaMalloc(&A, (size_t)M * K * 4)); CKE(cudaMalloc(&P, (size_t)M * K * 4)); CKE(cudaMalloc(&W, (size_t)N * K * 4));
     CKE(cudaMalloc(&out, (size_t)M * N * 4)); CKE(cudaMalloc(&R, (size_t)M * N * 4)); CKE(cudaMalloc(&g, N * 4)); CKE(cudaMalloc(&b, N * 4));
@@ -57,21 +52,6 @@ int main(int argc, char** argv) {
     printf("M=%d N=%d K=%d pos=%d resln=%d pair=%d : avg %.1f us best %.1f us  -> %.1f TFLOP/s algorithmic (x3 issued: %.1f)\n", M, N, K, pos,
            resln, pair, tot / iters * 1e3, best * 1e3, fl / (tot / iters * 1e-3) / 1e12, 3 * fl / (tot / iters * 1e-3) / 1e12);
 #ifdef MESM_TC_TIMING
-    if (pair == 2) {
-        long long t[256]; tcp_read_times(t);
-        printf("persistent: setup %lld\n", t[1] - t[0]);
-        for (int g = 0; g < 16; ++g)
-            printf("  g%02d: W-producer past empty %6lld | conv loads-issued %6lld past-empty %6lld arrived %6lld | mma local-full %6lld peer-full %6lld\n", g,
-                   t[32 + g] - t[0], t[80 + g] - t[0], t[96 + g] - t[0], t[112 + g] - t[0], t[64 + g] - t[0], t[8 + g] - t[0]);
-        for (int g = 0; g < 16; ++g)
-            printf("  conv g%02d: entry %6lld math-done +%5lld loads-issued +%5lld past-empty +%5lld stored +%5lld fenced +%5lld arrived +%5lld\n", g,
-                   t[128 + g] - t[0], t[144 + g] - t[128 + g], t[80 + g] - t[144 + g], t[96 + g] - t[80 + g], t[160 + g] - t[96 + g],
-                   t[176 + g] - t[160 + g], t[112 + g] - t[176 + g]);
-        for (int ti = 0; ti < 4; ++ti)
-            printf("  tile%d: mma committed %6lld | epi waiting %6lld got-acc %6lld released %6lld\n", ti, t[56 + ti] - t[0], t[40 + 4 * ti] - t[0],
-                   t[41 + 4 * ti] - t[0], t[42 + 4 * ti] - t[0]);
-        return 0;
-    }
     long long t[64]; tc_read_times(t);
     printf("stamps rel. to start (cycles): setup %lld | mma-issue-done %lld | epi-start %lld | epi-end %lld | exit %lld\n", t[1] - t[0],
            t[2] - t[0], t[3] - t[0], t[4] - t[0], t[6] - t[0]);
