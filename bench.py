@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py — video-query pairs/sec of the MESM per-pair inference path on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N --steps K --warmup W]                 our CUDA path (one process per GPU; torchrun for N>1)
-    python bench.py --impl reference [...]                          the reference algorithm on the host CPU cores
+    python bench.py [--gpus N --steps K --warmup W] [--config NAME]     our CUDA path (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference [...]                              the reference's own modules on the host CPU cores
 
-A step = one pass of the whole hot path (MESM.forward incl. the negative branch + span decode / post-processing / NMS)
-over one batch of synthetic pairs of BASELINE.json configs[1]: Charades-STA C+SF shape, 4096 pairs per GPU, inputs
-resident in HBM (9 GB per GPU, far larger than L2).  `e2e` is the same work through the public Python API with the
-inputs starting in pinned HOST memory (H2D inside the timed region) and the ranked windows read back to the host.
+A step = one pass of the whole hot path - MESM.forward incl. the negative branch, the segment-sentence alignment scores
+(model/criterion.py:241-266) and span decode / post-processing / NMS - over one batch of synthetic pairs.  Default workload =
+BASELINE.json configs[1]: Charades-STA C+SF shape, 4096 pairs per GPU, inputs resident in HBM (far larger than L2).
+``--config`` selects the other BASELINE configs (charades_vgg = configs[2], tacos = configs[3] incl. the 100-candidate NMS pass,
+qvh = the shape of configs[0] / [4]; the 1 M-pair sweep itself is sweep.py).  `e2e` is the same work through the public Python
+API with the inputs starting in pinned HOST memory (H2D inside the timed region) and the ranked windows read back to the host.
 Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
+import dataclasses
 import gc
 import json
 import os
@@ -25,39 +28,70 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CHARADES_CSF = dict(dataset_name="charades", v_feat_dim=2818, t_feat_dim=512, hidden_dim=256, nheads=8, dim_feedforward=1024,
-                    num_queries=10, num_recfw_layers=2, t2v_layers=2, enc_layers=2, dec_layers=2, num_recss_layers=4,
-                    n_input_proj=2, rec_fw=True, rec_ss=True, share_MLP=True, max_words_l=16, max_video_l=194,
-                    aux_loss=True, vocab_size=1111, clip_len=1.0, max_ts_val=150.0)
-NMS_THD = 0.7           # shipped configs disable NMS (nms_thd -1); 0.7 is Moment-DETR's convention (SURVEY §8a A14)
-ALGO_FLOPS_PER_PAIR = 2.51e9        # positive path, video projected once, Lv=194
-ALGO_BYTES_PER_PAIR = 2219746       # fp32 feature bytes read per pair
+_COMMON = dict(hidden_dim=256, nheads=8, dim_feedforward=1024, num_queries=10, num_recfw_layers=2, t2v_layers=2, enc_layers=2,
+               dec_layers=2, num_recss_layers=4, n_input_proj=2, rec_fw=True, rec_ss=True, aux_loss=True, vocab_size=1111)
+# model keys = the reference's JSON configs (config/*/*.json); "wl" = the synthetic workload of SURVEY 8d (C1..C4)
+BENCH_CONFIGS = {
+    "charades_csf": dict(_COMMON, dataset_name="charades", v_feat_dim=2818, t_feat_dim=512, share_MLP=True, max_words_l=16,
+                         max_video_l=194, clip_len=1.0, max_ts_val=150.0,
+                         wl=dict(name="charades_sta_c+sf_inference_batch4096", baseline="configs[1]", oracle="charades_csf", split=512,
+                                 group_max=4, ragged=True, dur=(10.0, 60.0), dense_nms=0,
+                                 algo_flops=2.51e9, algo_bytes=2219746)),
+    "charades_vgg": dict(_COMMON, dataset_name="charades", v_feat_dim=4098, t_feat_dim=300, share_MLP=True, max_words_l=16,
+                         max_video_l=200, clip_len=0.17, max_ts_val=150.0,
+                         wl=dict(name="charades_sta_vgg+glove_inference", baseline="configs[2]", oracle="charades_vgg", split=0,
+                                 group_max=4, ragged=True, dur=(10.0, 60.0), dense_nms=0,
+                                 algo_flops=2.72e9, algo_bytes=3297816)),
+    "tacos": dict(_COMMON, dataset_name="tacos", v_feat_dim=4098, t_feat_dim=300, share_MLP=False, max_words_l=16,
+                  max_video_l=200, clip_len=-1.0, max_ts_val=1000.0,
+                  wl=dict(name="tacos_c3d_inference_dense_nms", baseline="configs[3]", oracle="tacos", split=0,
+                          group_max=10, ragged=True, dur=(100.0, 900.0), dense_nms=100,
+                          algo_flops=2.72e9, algo_bytes=3297816)),
+    "qvh": dict(_COMMON, dataset_name="qvhighlights", v_feat_dim=2818, t_feat_dim=512, share_MLP=True, max_words_l=32,
+                max_video_l=75, clip_len=2.0, max_ts_val=150.0,
+                wl=dict(name="qvhighlights_c+sf_inference", baseline="configs[0] shape (CPU case B=32) / configs[4] shape", oracle="qvhighlights",
+                        split=512, group_max=1, ragged=False, dur=(150.0, 150.0), dense_nms=0,
+                        algo_flops=1.043e9, algo_bytes=911043)),
+}
+CHARADES_CSF = {k: v for k, v in BENCH_CONFIGS["charades_csf"].items() if k != "wl"}      # (tests import this)
+NMS_THD = 0.7           # shipped configs disable NMS (nms_thd -1); 0.7 is Moment-DETR's convention (SURVEY 8a A14)
 
 
-def make_workload(cfg, B, seed, device):
-    """Synthetic Charades C+SF batch: video groups of 1-4 queries, ragged Lv ~ U{97..194}, per-source
-    L2-normalised N(0,1) features + tef columns, words N(0,1) with lengths U{3..16}, durations U(10,60)."""
+def model_cfg(name):
+    return {k: v for k, v in BENCH_CONFIGS[name].items() if k != "wl"}
+
+
+def make_workload(cfg, B, seed, device, wl=None):
+    """Synthetic batch shaped like the collate output: video groups of 1..group_max queries that share their video,
+    ragged Lv ~ U{Lv/2..Lv} (or uniform), per-source L2-normalised N(0,1) features + tef columns, words N(0,1) with lengths
+    U{3..Lt}, durations U(dur), a synthetic ground-truth clip mask for the alignment scores."""
+    wl = wl or BENCH_CONFIGS["charades_csf"]["wl"]
     g = torch.Generator(device="cpu").manual_seed(seed)
     Lv, Lt, Dv, Dt = cfg["max_video_l"], cfg["max_words_l"], cfg["v_feat_dim"], cfg["t_feat_dim"]
     nc = []
     while sum(nc) < B:
-        nc.append(min(int(torch.randint(1, 5, (1,), generator=g)), B - sum(nc)))
+        nc.append(min(int(torch.randint(1, wl["group_max"] + 1, (1,), generator=g)), B - sum(nc)))
     G = len(nc)
-    vlen_g = torch.randint(Lv // 2, Lv + 1, (G,), generator=g)
+    vlen_g = torch.randint(Lv // 2, Lv + 1, (G,), generator=g) if wl["ragged"] else torch.full((G,), Lv)
     vlen_g[0] = Lv
     nct = torch.tensor(nc)
     vlen = torch.repeat_interleave(vlen_g, nct)
-    dur = torch.repeat_interleave(torch.rand(G, generator=g) * 50 + 10, nct).float()
-    wl = torch.randint(3, Lt + 1, (B,), generator=g)
+    lo, hi = wl["dur"]
+    dur = torch.repeat_interleave(torch.rand(G, generator=g) * (hi - lo) + lo, nct).float()
+    wlen = torch.randint(3, Lt + 1, (B,), generator=g)
     gd = torch.Generator(device=device).manual_seed(seed)
     video = torch.empty(B, Lv, Dv, dtype=torch.float32, device=device)
     ar = torch.arange(Lv, device=device)
+    split = wl["split"]
     start = 0
     for gi in range(0, G, 64):                      # build group-wise so that queries of a group share the video
         gs = list(range(gi, min(gi + 64, G)))
         x = torch.randn(len(gs), Lv, Dv - 2, device=device, generator=gd)
-        x[..., :512] = torch.nn.functional.normalize(x[..., :512], dim=-1)
-        x[..., 512:] = torch.nn.functional.normalize(x[..., 512:], dim=-1)
+        if split:
+            x[..., :split] = torch.nn.functional.normalize(x[..., :split], dim=-1)
+            x[..., split:] = torch.nn.functional.normalize(x[..., split:], dim=-1)
+        else:
+            x = torch.nn.functional.normalize(x, dim=-1)
         L = vlen_g[gs].to(device).float()[:, None]
         tef = torch.stack([ar[None] / L, (ar[None] + 1) / L], dim=-1)
         x = torch.cat([x, tef], dim=-1) * (ar[None] < L)[..., None]
@@ -67,12 +101,22 @@ def make_workload(cfg, B, seed, device):
         start += xr.shape[0]
     mask = ar[None] < vlen.to(device)[:, None]
     words = torch.randn(B, Lt, Dt, device=device, generator=gd)
-    words = words * (torch.arange(Lt, device=device)[None] < wl.to(device)[:, None])[..., None]
-    # negative index: another video group (vectorised sample_outclass_neg)
-    from mesm_b200.model import sample_outclass_neg
-    neg = sample_outclass_neg(nct, generator=g)
-    return dict(video_feat=video, video_mask=mask, words_feat=words, num_clips=nct, duration=dur.to(device),
-                neg_index=neg.to(device), video_len=vlen.to(torch.int32))       # clip counts stay on the host (collate's `lengths`)
+    words = words * (torch.arange(Lt, device=device)[None] < wlen.to(device)[:, None])[..., None]
+    clip_mask = (torch.rand(B, Lv, device=device, generator=gd) < 0.3) & mask      # GT clips of model/criterion.py:245 (synthetic)
+    clip_mask[:, 0] = True
+    out = dict(video_feat=video, video_mask=mask, words_feat=words, num_clips=nct, duration=dur.to(device), clip_mask=clip_mask,
+               video_len=vlen.to(torch.int32))          # clip counts stay on the host (collate's `lengths`)
+    if G >= 2:                                          # negative index: another video group (vectorised sample_outclass_neg)
+        from mesm_b200.model import sample_outclass_neg
+        out["neg_index"] = sample_outclass_neg(nct, generator=g).to(device)
+    if wl["dense_nms"]:                                 # a 100-candidate / pair list for the NMS kernel
+        n = wl["dense_nms"]
+        st = torch.rand(B, n, device=device, generator=gd, dtype=torch.float64) * out["duration"][:, None].double() * 0.9
+        w = torch.rand(B, n, device=device, generator=gd, dtype=torch.float64) * out["duration"][:, None].double() * 0.3
+        sc = torch.round(torch.rand(B, n, device=device, generator=gd, dtype=torch.float64) * 1e4) / 1e4
+        out["dense_windows"] = torch.stack([st, st + w, sc], dim=-1).reshape(B * n, 3).contiguous()
+        out["dense_offsets"] = (torch.arange(B + 1, device=device, dtype=torch.int64) * n)
+    return out
 
 
 class ClockSampler:
@@ -156,39 +200,135 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_pairs_per_s(cfg_name, state_dict, batch, steps, warmup, threads):
-    """The reference algorithm (oracle port, checker code used here only as the CPU baseline) on the host cores."""
-    from oracle import decode_oracle, mesm_oracle
+# ---------------------------------------------------------------------------------------------------------------------
+# reference legs (checker code: the only places bench.py executes anything under oracle/)
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_cfg(name, cfg):
     from oracle.config import CONFIGS
-    ocfg = CONFIGS[cfg_name]
+    return dataclasses.replace(CONFIGS[BENCH_CONFIGS[name]["wl"]["oracle"]], max_video_l=cfg["max_video_l"])
+
+
+def _ref_align_scores(out, clip_mask, tau):
+    """model/criterion.py:241-266 up to cos_sim / tau, on the reference's output dict."""
+    import torch.nn.functional as F
+    cm = clip_mask.unsqueeze(-1)
+    cf = (out["projed_video_feat"] * cm).sum(1) / cm.sum(1)
+    wm = out["expanded_words_mask"].unsqueeze(-1)
+    wf = (out["expanded_words_feat"] * wm).sum(1) / wm.sum(1)
+    return F.normalize(cf, dim=-1, p=2) @ F.normalize(wf, dim=-1, p=2).permute(1, 0) / tau
+
+
+class ReferencePath:
+    """The reference's own modules (oracle/_ref, staged by oracle/make_ref.py) driven as eval.py drives them - or, when they did
+    not travel, the oracle port.  One call = forward (+ negative branch) + alignment scores + decode / post-process / NMS."""
+
+    def __init__(self, name, cfg, state_dict, device="cpu"):
+        from oracle import ref_harness
+        self.name, self.cfg, self.ocfg, self.device = name, cfg, _oracle_cfg(name, cfg), torch.device(device)
+        self.kind = "port"
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
+        if ref_harness.reference_root() is not None and not os.environ.get("MESM_REF_PORT"):
+            try:
+                ref_harness.import_reference()
+                self.model = ref_harness.build_reference(self.ocfg)
+                self.model.load_state_dict(self.sd, strict=True)
+                self.model = self.model.to(self.device).eval()
+                self.kind = "reference"
+            except Exception as e:                                   # noqa: BLE001 - any import problem -> the port
+                print(f"[bench] reference modules unusable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        if self.kind == "port" and self.device.type != "cpu":
+            raise RuntimeError("the oracle port runs on the CPU only")
+
+    def batch(self, wl):
+        d = self.device
+        return {k: (v.to(d) if torch.is_tensor(v) and k not in ("num_clips", "video_len") else v) for k, v in wl.items()}
+
+    def __call__(self, b, decode=True):
+        from oracle import decode_oracle, mesm_oracle, ref_harness
+        ocfg, dense = self.ocfg, self.cfg_wl()["dense_nms"]
+        if self.kind == "reference":
+            o = ref_harness.reference_forward(self.model, ocfg, b)
+            S = _ref_align_scores(o, b["clip_mask"], ocfg.recss_tau)
+            if decode:
+                ref_harness.reference_decode(o["pred_logits"], o["pred_spans"], b["duration"], ocfg, NMS_THD)
+                if dense:
+                    from utils import temporal_nms
+                    rows = b["dense_windows"].cpu().reshape(-1, dense, 3).tolist()
+                    for r in rows:
+                        temporal_nms(r, nms_thd=NMS_THD, max_after_nms=10)
+        else:
+            o = mesm_oracle.mesm_forward(self.sd, ocfg, b["video_feat"], b["video_mask"], b["words_feat"], b["num_clips"],
+                                         neg_index=b["neg_index"])
+            S = mesm_oracle.align_scores(o["projed_video_feat"], b["clip_mask"], o["expanded_words_feat"], o["expanded_words_mask"],
+                                         ocfg.recss_tau)
+            if decode:
+                lg, sp = o["pred_logits"].numpy(), o["pred_spans"].numpy()
+                for i in range(lg.shape[0]):
+                    decode_oracle.decode_pair(lg[i], sp[i], float(b["duration"][i]), ocfg.clip_len, ocfg.max_ts_val, NMS_THD, 10, 10)
+                if dense:
+                    for r in b["dense_windows"].reshape(-1, dense, 3).tolist():
+                        decode_oracle.temporal_nms(r, NMS_THD, 10)
+        return o, S
+
+    def cfg_wl(self):
+        return BENCH_CONFIGS[self.name]["wl"]
+
+    def describe(self):
+        return ("the reference's own model.MESM + utils (span_cxw_to_xx, PostProcessorDETR, temporal_nms) driven as eval.py:63-116,476-485"
+                if self.kind == "reference" else "oracle port of the reference forward + decode/NMS") + ", torch fp32"
+
+
+def cpu_reference_pairs_per_s(name, cfg, state_dict, batch, steps, warmup, threads):
     torch.set_num_threads(threads)
-    sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
-    vf, vm, wf = batch["video_feat"].cpu(), batch["video_mask"].cpu(), batch["words_feat"].cpu()
-    nc, neg, dur = batch["num_clips"].cpu(), batch["neg_index"].cpu(), batch["duration"].cpu()
-    B = vf.shape[0]
+    ref = ReferencePath(name, cfg, state_dict, "cpu")
+    b = ref.batch(batch)
+    B = b["video_feat"].shape[0]
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        o = mesm_oracle.mesm_forward(sd, ocfg, vf, vm, wf, nc, neg_index=neg)
-        lg, sp = o["pred_logits"].numpy(), o["pred_spans"].numpy()
-        for i in range(B):
-            decode_oracle.decode_pair(lg[i], sp[i], float(dur[i]), ocfg.clip_len, ocfg.max_ts_val, NMS_THD, 10, 10)
+        ref(b)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return B * len(times) / sum(times), sum(times) / len(times)
+    return B * len(times) / sum(times), sum(times) / len(times), ref
+
+
+def gpu_eager_pairs_per_s(name, cfg, state_dict, wl_full, pairs, device, steps=3):
+    """The GPU bar of SURVEY 8d / BASELINE.md: the reference's modules in PyTorch eager mode on the same B200, fp32 with TF32 off."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref = ReferencePath(name, cfg, state_dict, device)
+    b = ref.batch(take_groups(wl_full, pairs))
+    B = b["video_feat"].shape[0]
+    res = {}
+    for decode in (False, True):
+        ref(b, decode=decode)                      # warm-up (lazy kernel loading, allocator)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ref(b, decode=decode)
+        torch.cuda.synchronize()
+        res["forward_decode" if decode else "forward"] = B * steps / (time.perf_counter() - t0)
+    return res, B, ref
 
 
 def take_groups(wl, n_pairs):
-    """First whole video groups covering >= n_pairs pairs (CPU sample of the same workload)."""
+    """First whole video groups covering >= n_pairs pairs (sample of the same workload)."""
     nc = wl["num_clips"].tolist()
     tot, k = 0, 0
     while tot < n_pairs and k < len(nc):
         tot += nc[k]
         k += 1
+    if k < 2 and len(nc) >= 2:                     # the negative branch needs two groups
+        k = 2
+        tot = nc[0] + nc[1]
     from mesm_b200.model import sample_outclass_neg
-    sub = dict(video_feat=wl["video_feat"][:tot], video_mask=wl["video_mask"][:tot], words_feat=wl["words_feat"][:tot],
-               num_clips=wl["num_clips"][:k], duration=wl["duration"][:tot], video_len=wl["video_len"][:tot])
-    sub["neg_index"] = sample_outclass_neg(sub["num_clips"], generator=torch.Generator().manual_seed(5))
+    sub = {key: wl[key][:tot] for key in ("video_feat", "video_mask", "words_feat", "duration", "video_len", "clip_mask")}
+    sub["num_clips"] = wl["num_clips"][:k]
+    sub["neg_index"] = sample_outclass_neg(sub["num_clips"], generator=torch.Generator().manual_seed(5)).to(wl["video_feat"].device)
+    if "dense_windows" in wl:
+        n = wl["dense_windows"].shape[0] // wl["video_feat"].shape[0]
+        sub["dense_windows"] = wl["dense_windows"][:tot * n]
+        sub["dense_offsets"] = wl["dense_offsets"][:tot + 1]
     return sub
 
 
@@ -198,9 +338,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="charades_csf", choices=sorted(BENCH_CONFIGS))
     ap.add_argument("--pairs", type=int, default=4096, help="pairs per GPU per step")
     ap.add_argument("--chunk-pairs", type=int, default=0, help="pairs per internal chunk (0 = engine default)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=32)
+    ap.add_argument("--eager-pairs", type=int, default=1024, help="pairs of the PyTorch-eager-on-GPU reference leg (0 = skip)")
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--e2e-sub", type=int, default=2048, help="pairs per host->device sub-batch of the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -208,11 +350,15 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    cfg = dict(CHARADES_CSF)
-    config = {"workload": "charades_sta_c+sf_inference_batch4096", "config": "configs[1]", "pairs_per_gpu": args.pairs,
-              "Lv": cfg["max_video_l"], "Lt": cfg["max_words_l"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": 512,
-              "ragged_video": "U{97..194}", "negative_branch": True, "nms_thd": NMS_THD, "parallelism": f"dp{world}",
-              "l2": "inputs (9 GB/GPU) larger than L2; no flush needed"}
+    cfg, wlc = model_cfg(args.config), BENCH_CONFIGS[args.config]["wl"]
+    config = {"workload": wlc["name"] if args.pairs == 4096 or args.config != "charades_csf" else f"charades_sta_c+sf_inference_batch{args.pairs}",
+              "config": wlc["baseline"], "pairs_per_gpu": args.pairs,
+              "Lv": cfg["max_video_l"], "Lt": cfg["max_words_l"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
+              "ragged_video": f"U{{{cfg['max_video_l'] // 2}..{cfg['max_video_l']}}}" if wlc["ragged"] else "uniform",
+              "negative_branch": True, "align_scores": True, "nms_thd": NMS_THD, "parallelism": f"dp{world}",
+              "l2": "inputs (GBs per GPU) larger than L2; no flush needed"}
+    if wlc["dense_nms"]:
+        config["dense_nms_candidates"] = wlc["dense_nms"]
 
     from mesm_b200.model import build_model
     torch.manual_seed(0)
@@ -227,15 +373,14 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        wl = make_workload(cfg, 64, 1234, "cpu")
+        wl = make_workload(cfg, 64, 1234, "cpu", wlc)
         sub = take_groups(wl, args.cpu_sample_pairs)
-        pps, sec = cpu_reference_pairs_per_s("charades_csf", model.state_dict(), sub, max(args.steps, 1), min(args.warmup, 2), threads)
+        pps, sec, ref = cpu_reference_pairs_per_s(args.config, cfg, model.state_dict(), sub, max(args.steps, 1), max(args.warmup, 0), threads)
         line = {"impl": "reference", "metric": "video-query pairs/sec", "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                 "sample": f"{sub['video_feat'].shape[0]} pairs of the same workload per step (oracle port of the "
-                                           "reference forward + decode/NMS, torch CPU fp32, all host threads)"},
+                "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": threads, "kind": ref.kind,
+                                 "sample": f"{sub['video_feat'].shape[0]} pairs of the same workload per step ({ref.describe()}, all host threads)"},
                 "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -251,22 +396,28 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     model = model.to(dev)
     model.chunk_pairs = args.chunk_pairs
-    wl = make_workload(cfg, args.pairs, 1234 + rank, dev)
+    wl = make_workload(cfg, args.pairs, 1234 + rank, dev, wlc)
     B, Lv = args.pairs, cfg["max_video_l"]
     lib = _lib.lib()
     from mesm_b200.sharding import gather_topk
 
     # host clip counts (what the collate step knows): the engine then runs on packed variable-length rows
     vlen_host = None if os.environ.get("MESM_PADDED_ROWS") else wl["video_len"]
-    config["rows"] = "zero-padded [B, Lv]" if vlen_host is None else "packed variable-length (host clip counts passed as video_len)"
-    config["clip_rows_per_gpu"] = int(B * Lv if vlen_host is None else wl["video_len"].sum())
+    layout = {"rows": "zero-padded [B, Lv]" if vlen_host is None else "packed variable-length (host clip counts passed as video_len)",
+              "clip_rows_per_gpu": int(B * Lv if vlen_host is None else wl["video_len"].sum())}
+    dname = cfg["dataset_name"]
 
     def step():
         out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"],
-                    dataset_name="charades", is_training=False, neg_index=wl["neg_index"], video_len=vlen_host)
+                    dataset_name=dname, is_training=False, neg_index=wl["neg_index"], video_len=vlen_host)
+        S = mesm_b200.align_scores(out["projed_video_feat"], wl["clip_mask"], out["expanded_words_feat"], out["expanded_words_mask"], 0.5)
         win, order, keep, cnt = mesm_b200.decode_nms(out["pred_logits"], out["pred_spans"], wl["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
-        return out, win, order, keep, cnt
+        n = 3
+        if wlc["dense_nms"]:
+            mesm_b200.temporal_nms_lists(wl["dense_windows"], wl["dense_offsets"], NMS_THD, 10)
+            n += 1
+        return out, win, order, keep, cnt, S, n
 
     _v = lambda m: print(f"[bench] {m}", file=sys.stderr, flush=True) if os.environ.get("MESM_BENCH_VERBOSE") else None
     for _ in range(args.warmup):
@@ -289,8 +440,8 @@ def main():
         ev0.record()
         step_ev = [ev0]
         for _ in range(args.steps):
-            out, win, order, keep, cnt = step()
-            launches += model._eng.last_launch_count + 1
+            out, win, order, keep, cnt, S, n_extra = step()
+            launches += model._eng.last_launch_count + n_extra
             step_ev.append(torch.cuda.Event(enable_timing=True))
             step_ev[-1].record()
         top = gather_topk(win, wl["num_clips"], args.topk, rank, world, B)      # one NCCL all_gather of top-k spans
@@ -307,7 +458,7 @@ def main():
     ms = float(t)
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- roofline of the dominant kernel (fused linear): one extra step with CUDA events around each launch ----------
+    # ---- roofline of the dominant kernel (fused FFN): one extra step with CUDA events around each launch ----------
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib.mesm_profile_begin()
     pe0.record()
@@ -318,10 +469,10 @@ def main():
     torch.cuda.synchronize()
     profile_step_ms = pe0.elapsed_time(pe1)
     _v("profile step done")
+    rep_rows = {r[0]: (int(r[1]), float(r[2])) for r in (l.split("\t") for l in lib.mesm_profile_report().decode().strip().split("\n")) if len(r) >= 3}
     if os.environ.get("MESM_PROFILE_REPORT"):
-        rep = sorted((l.split("\t") for l in lib.mesm_profile_report().decode().strip().split("\n")), key=lambda r: -float(r[2]))
-        for r in rep:
-            print(f"{float(r[2]):9.3f} ms  n={int(r[1]):5d}  {r[0]}", file=sys.stderr)
+        for k, (n, t_ms) in sorted(rep_rows.items(), key=lambda kv: -kv[1][1]):
+            print(f"{t_ms:9.3f} ms  n={n:5d}  {k}", file=sys.stderr)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -329,42 +480,53 @@ def main():
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
     lin_ms, lin_flops = prof[0], prof[1]
     step_ms = ms / args.steps
-    # dominant kernel = the fused FFN (ffn_pair_kernel): 8 T2V launches on B*Lv rows + 4 encoder launches on B*(Lv+1) rows per step
-    rep_rows = {r[0]: (int(r[1]), float(r[2])) for r in (l.split("\t") for l in lib.mesm_profile_report().decode().strip().split("\n")) if len(r) >= 3}
+    clip_rows = float(layout["clip_rows_per_gpu"])      # rows the kernels actually process
+    traffic_tab = {}
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                traffic_tab = json.load(f)
+            break
+        except Exception:
+            pass
+    # dominant kernel = the fused FFN (ffn_pair_kernel): 8 T2V launches on the clip rows + 4 encoder launches on clip rows + B per step
     ffn_n, ffn_ms = rep_rows.get("ffn_fused", (0, 0.0))
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f)["ffn_pair_kernel"]["dram_bytes_per_row"] * (B * Lv if vlen_host is None else int(wl["video_len"].sum()))   # ncu DRAM bytes per row x rows of one launch
-    except Exception:
-        pass
     if ffn_n:
-        clip_rows = float(B * Lv) if vlen_host is None else float(wl["video_len"].sum())      # rows the kernels actually process
         ffn_flops = 4.0 * 256 * 1024 * (8.0 * clip_rows + 4.0 * (clip_rows + B)) * (ffn_n / 12.0)
         ach = ffn_flops / (ffn_ms * 1e-3) / 1e12
+        tr = traffic_tab.get("ffn_pair_kernel", {}).get("dram_bytes_per_row")
         roof = {"bound": "tensor", "kernel": "ffn_pair_kernel (fused FFN block, tcgen05 CTA pairs; bf16x3 = 3 MMAs per algorithmic MAC)",
                 "achieved": ach, "peak": peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback B200_PROFILING.md",
-                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "launches_per_step": ffn_n, "kernel_ms_per_step": ffn_ms,
-                "share_of_step": ffn_ms / step_ms, "issued_frac": 3 * ach / peak_tf}
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": tr * clip_rows if tr else None, "launches_per_step": ffn_n,
+                "kernel_ms_per_step": ffn_ms, "share_of_step": ffn_ms / step_ms, "issued_frac": 3 * ach / peak_tf}
     else:
         roof = {"bound": "tensor", "kernel": "tcgen05 linear (all GEMM launches of one step)", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": None, "traffic": None}
     roof["all_gemm_launches"] = {"achieved": lin_flops / (lin_ms * 1e-3) / 1e12 if lin_ms else None,
                                  "frac": (lin_flops / (lin_ms * 1e-3) / 1e12 / peak_tf) if lin_ms else None,
                                  "launches_per_step": int(prof[3]), "kernel_ms_per_step": lin_ms, "share_of_step": lin_ms / step_ms}
+    # second entry: the one HBM-bound stage - the K = Dv input projection that streams the clip features
+    k1 = [(k, v) for k, v in rep_rows.items() if k.startswith("input_proj")]
+    if k1:
+        k1_ms = sum(v[1] for _, v in k1)
+        feat_bytes = float(getattr(model._eng, "last_feature_bytes", 0)) or clip_rows * cfg["v_feat_dim"] * 4.0
+        roof["input_projection"] = {"bound": "hbm", "kernel": k1[0][0], "achieved": feat_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak_hbm,
+                                    "unit": "GB/s", "frac": feat_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm, "kernel_ms_per_step": k1_ms,
+                                    "algorithmic_bytes": feat_bytes}
     roof["profiled_step_ms"] = profile_step_ms
     roof["profiled_kernels_ms"] = sum(v[1] for v in rep_rows.values())
-    roof["hbm_frac_whole_step"] = (ALGO_BYTES_PER_PAIR * B / (step_ms * 1e-3)) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))
+    roof["hbm_frac_whole_step"] = (wlc["algo_bytes"] * B / (step_ms * 1e-3)) / 1e9 / peak_hbm
 
     # ---- e2e: same work through the public API from pinned host memory, sub-batches double-buffered over two streams -----
     sub = args.e2e_sub if B >= args.e2e_sub else B
     nsub = max(1, B // sub)
-    # sub-batches must hold whole groups: rebuild a slice with its own grouping
-    sb = take_groups(wl, sub)
+    sb = take_groups(wl, sub)                      # sub-batches hold whole groups: a slice with its own grouping
     Bs = sb["video_feat"].shape[0]
-    host = {k: sb[k].cpu().pin_memory() for k in ("video_feat", "video_mask", "words_feat", "duration", "neg_index")}
+    host_keys = ["video_feat", "video_mask", "words_feat", "duration", "neg_index", "clip_mask"] + (["dense_windows", "dense_offsets"] if wlc["dense_nms"] else [])
+    host = {k: sb[k].cpu().pin_memory() for k in host_keys}
     padded = bool(os.environ.get("MESM_E2E_PADDED"))            # A/B switch: plain copy of the zero-padded tensor
     # One context = one compute stream (a mesm_ctx is not re-entrant).  A second stream prefetches the next sub-batch from
     # pinned host memory while the current one is being scored; events order copy -> compute -> buffer reuse.  Steps are
@@ -374,7 +536,7 @@ def main():
     # (the copy stream has the higher priority: its one small kernel - the pad-row zero fill - must not queue behind the
     # compute stream's grids, or the copy engine idles until it has run)
     comp, copy = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
-    shared = not padded and vlen_host is not None and not os.environ.get("MESM_E2E_NO_SHARED")
+    shared = (not padded and vlen_host is not None and not os.environ.get("MESM_E2E_NO_SHARED") and dname != "qvhighlights")
     dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
     hkeep = [torch.empty(Bs, 10, dtype=torch.int32).pin_memory() for _ in range(2)]
@@ -384,10 +546,7 @@ def main():
     vl_box = [None if vlen_host is None else sb["video_len"]] * 2
 
     def e2e_stream(total):
-        # Host order: scoring of sub-batch i is enqueued first, then the ingest of sub-batch i+2 into the buffer it frees.  The
-        # ragged ingest is ~800 copy commands; enqueueing it can block the host until the copy stream has drained most of them
-        # (it waits for the buffer), and with the ingest enqueued BEFORE the scoring launches that blocked time was a compute
-        # gap of 2-3 ms per sub-batch (MESM_E2E_TRACE=1: the GPU period equalled the host loop time).
+        # Host order: scoring of sub-batch i is enqueued first, then the ingest of sub-batch i+2 into the buffer it frees.
         for e in freed:
             e.record(comp)
 
@@ -417,10 +576,13 @@ def main():
             with torch.cuda.stream(comp):
                 comp.wait_event(ready[i % 2])
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
-                          dataset_name="charades", is_training=False, neg_index=d["neg_index"], video_len=vl_box[i % 2],
+                          dataset_name=dname, is_training=False, neg_index=d["neg_index"], video_len=vl_box[i % 2],
                           shared_group_video=shared)
+                mesm_b200.align_scores(o["projed_video_feat"], d["clip_mask"], o["expanded_words_feat"], o["expanded_words_mask"], 0.5)
                 w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
+                if wlc["dense_nms"]:
+                    mesm_b200.temporal_nms_lists(d["dense_windows"], d["dense_offsets"], NMS_THD, 10)
                 hres[i % 2].copy_(w, non_blocking=True)
                 hkeep[i % 2].copy_(kp, non_blocking=True)
                 freed[i % 2].record(comp)
@@ -458,17 +620,40 @@ def main():
 
     line = {"metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "layout": layout, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
                     "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest two sub-batches ahead on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        cs = take_groups(wl, args.cpu_sample_pairs)
-        pps, sec = cpu_reference_pairs_per_s("charades_csf", model.state_dict(), cs, 3, 1, threads)
-        line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": threads, "kind": "port",
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        cs = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in take_groups(wl, args.cpu_sample_pairs).items()}
+        pps, sec, ref = cpu_reference_pairs_per_s(args.config, cfg, sd_cpu, cs, 3, 1, threads)
+        line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": threads, "kind": ref.kind,
                                 "sample": f"{cs['video_feat'].shape[0]} pairs of the same workload, 3 timed iterations after 1 warm-up "
-                                          "(oracle port of the reference forward + decode/NMS, torch CPU fp32)"}
+                                          f"({ref.describe()})"}
+        del ref
+        # SURVEY 8d C1 (the reference's own CPU-runnable case, BASELINE configs[0]): QVHighlights shape, batch 32
+        try:
+            qcfg, qwl = model_cfg("qvh"), BENCH_CONFIGS["qvh"]["wl"]
+            torch.manual_seed(0)
+            qsd = build_model(qcfg).state_dict()
+            qb = make_workload(qcfg, 32, 77, "cpu", qwl)
+            qpps, _, qref = cpu_reference_pairs_per_s("qvh", qcfg, qsd, qb, 3, 1, threads)
+            line["cpu_baseline"]["c1_qvh_b32"] = {"value": qpps, "unit": "pairs/s", "kind": qref.kind,
+                                                  "sample": "BASELINE configs[0]: QVHighlights C+SF shape, batch 32, forward + decode/NMS, 3 iterations"}
+            del qref, qsd, qb
+        except Exception as e:                      # noqa: BLE001
+            line["cpu_baseline"]["c1_qvh_b32"] = {"error": f"{type(e).__name__}: {e}"}
+        if args.eager_pairs > 0:
+            try:
+                res, Be, gref = gpu_eager_pairs_per_s(args.config, cfg, sd_cpu, wl, min(args.eager_pairs, B), dev)
+                line["gpu_eager_baseline"] = {"value": res["forward_decode"], "forward_only": res["forward"], "unit": "pairs/s", "kind": gref.kind,
+                                              "sample": f"{Be} pairs of the same workload on the same B200: {gref.describe()}, PyTorch eager, TF32 off; "
+                                                        "forward_only excludes the Python decode loop"}
+                line["vs_gpu_eager"] = {"value_over_eager_forward_only": value / res["forward"], "value_over_eager_forward_decode": value / res["forward_decode"]}
+            except Exception as e:                  # noqa: BLE001
+                line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(line))
     if dist:

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs a) {
         w[0] = (double)stf; w[1] = (double)edf; w[2] = scf;
         a.order[(long long)b * nq + rank] = lane;
     }
-    if (!a.do_nms || a.keep == nullptr) return;
+    if (!a.do_nms || (a.keep == nullptr && a.keep_count == nullptr)) return;      // keep may be NULL when max_after_nms == 0
 
     // bring the ranked list into lane order: lane r holds the window of rank r
     int src = 0;
@@ -106,11 +106,11 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs a) {
     }
     unsigned alive = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
     int kept = 0;
-    int* kp = a.keep + (long long)b * a.max_after;
+    int* kp = a.keep ? a.keep + (long long)b * a.max_after : nullptr;
     if (nb == 1) {                                  // utils/temporal_nms.py:38-39: a single prediction is returned untouched,
         if (lane == 0) {                            // whatever max_after_nms says
-            if (a.max_after >= 1) kp[0] = rq;
-            for (int i = 1; i < a.max_after; ++i) kp[i] = -1;
+            if (kp && a.max_after >= 1) kp[0] = rq;
+            for (int i = 1; kp && i < a.max_after; ++i) kp[i] = -1;
             if (a.keep_count) a.keep_count[b] = 1;
         }
         return;
@@ -123,11 +123,11 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs a) {
         const unsigned supmask = __ballot_sync(0xffffffffu, sup);
         alive &= ~supmask;
         alive &= ~(1u << head);
-        if (lane == 0) kp[kept] = hq;
+        if (lane == 0 && kp) kp[kept] = hq;
         ++kept;
     }
     if (lane == 0) {
-        for (int i = kept; i < a.max_after; ++i) kp[i] = -1;
+        for (int i = kept; kp && i < a.max_after; ++i) kp[i] = -1;
         if (a.keep_count) a.keep_count[b] = min(kept, a.max_after);
     }
 }
@@ -251,7 +251,7 @@ extern "C" int mesm_decode_nms(const float* pred_logits, const float* pred_spans
     a.nms_thd = p->nms_thd; a.max_before = p->max_before_nms; a.max_after = p->max_after_nms;
     a.sort_results = p->sort_results; a.do_nms = (p->nms_thd != -1.0) ? 1 : 0;
     a.windows = windows; a.order = order; a.keep = keep; a.keep_count = keep_count;
-    if (a.do_nms && keep && (a.max_after < 0 || a.max_before < 1)) return (int)cudaErrorInvalidValue;
+    if (a.do_nms && (a.max_after < 0 || a.max_before < 1 || (!keep && a.max_after > 0 && keep_count))) return (int)cudaErrorInvalidValue;
     decode_nms_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a);
     g_stats.launches++;
     return (int)cudaGetLastError();
@@ -259,7 +259,7 @@ extern "C" int mesm_decode_nms(const float* pred_logits, const float* pred_spans
 
 extern "C" int mesm_temporal_nms(const double* windows, const int64_t* offsets, int32_t n_lists, double nms_thd,
                                  int32_t max_after_nms, int32_t* keep, int32_t* keep_count, void* stream) {
-    if (!windows || !offsets || !keep || !keep_count || max_after_nms < 0) return (int)cudaErrorInvalidValue;
+    if (!windows || !offsets || (!keep && max_after_nms > 0) || !keep_count || max_after_nms < 0) return (int)cudaErrorInvalidValue;
     if (n_lists <= 0) return 0;
     temporal_nms_kernel<<<n_lists, 256, 0, (cudaStream_t)stream>>>(windows, offsets, nms_thd, max_after_nms, keep, keep_count);
     g_stats.launches++;

@@ -47,50 +47,7 @@ CASES = [
 NMS_THD = 0.7
 
 
-def build_reference(cfg):
-    from model.model import MESM
-    from model.transformer import T2VEncoder, T2VEncoder_TwoMLP, Transformer
-    from model.position_encoding import PositionEmbeddingSine, TrainablePositionalEncoding
-    kw = dict(d_model=cfg.hidden_dim, dropout=0.1, nhead=cfg.nheads, dim_feedforward=cfg.dim_feedforward,
-              normalize_before=False, activation="prelu")
-    enh = (T2VEncoder if cfg.share_mlp else T2VEncoder_TwoMLP)(num_encoder_layers=cfg.num_recfw_layers, **kw)
-    t2v = T2VEncoder(num_encoder_layers=cfg.t2v_layers, **kw)
-    tr = Transformer(num_encoder_layers=cfg.enc_layers, num_decoder_layers=cfg.dec_layers,
-                     return_intermediate_dec=True, **kw)
-    vpos = PositionEmbeddingSine(cfg.hidden_dim, normalize=True)
-    tpos = TrainablePositionalEncoding(cfg.max_words_l + 1 if cfg.rec_ss else cfg.max_words_l, cfg.hidden_dim, 0.5)
-    m = MESM(text_encoder=None, enhance_encoder=enh, t2v_encoder=t2v, transformer=tr, vid_position_embed=vpos,
-             txt_position_embed=tpos, txt_dim=cfg.t_feat_dim, vid_dim=cfg.v_feat_dim, num_queries=cfg.num_queries,
-             input_dropout=0.5, aux_loss=cfg.aux_loss, max_video_l=cfg.max_video_l, max_words_l=cfg.max_words_l,
-             normalize_txt=True, use_txt_pos=False, span_loss_type="l1", n_input_proj=cfg.n_input_proj,
-             rec_fw=cfg.rec_fw, vocab_size=cfg.vocab_size, rec_ss=cfg.rec_ss, num_recss_layers=cfg.num_recss_layers)
-    return m.eval()
-
-
-def reference_decode(logits, spans, duration, cfg, nms_thd):
-    """eval.py:64-99, 111-116, 476-485 with the reference's own utils."""
-    import torch.nn.functional as F
-    from utils import span_cxw_to_xx, PostProcessorDETR, temporal_nms
-    prob = F.softmax(logits, -1)
-    scores = prob[..., 0]
-    res = []
-    for idx, (sp, sc) in enumerate(zip(spans, scores)):
-        sp = span_cxw_to_xx(sp) * duration[idx]
-        rows = torch.cat([sp, sc[:, None]], dim=1).cpu().tolist()
-        order = sorted(range(len(rows)), key=lambda i: rows[i][2], reverse=True)
-        rows = sorted(rows, key=lambda x: x[2], reverse=True)
-        rows = [[float(f"{e:.4f}") for e in row] for row in rows]
-        res.append(dict(pred_relevant_windows=rows, order=order))
-    pp = PostProcessorDETR(clip_length=cfg.clip_len, min_ts_val=0, max_ts_val=cfg.max_ts_val, min_w_l=2, max_w_l=150,
-                           move_window_method="left",
-                           process_func_names=("clip_ts", "round_multiple") if cfg.clip_len != -1 else ("clip_ts",))
-    res = pp(res)
-    out = []
-    for r in res:
-        w = r["pred_relevant_windows"]
-        kept = temporal_nms(w[:10], nms_thd=nms_thd, max_after_nms=10)
-        out.append(dict(windows=w, order=r["order"], nms_windows=kept))
-    return out
+from oracle.ref_harness import build_reference, reference_decode  # noqa: E402
 
 
 def gen_decode_fixture():
