@@ -328,15 +328,51 @@ int mesm_debug_linear(const float* A, const float* Apos, const float* W, const f
         op.rowstat = rowstat; op.colsum = cs;
     }
     int rc = 0;
-    if (use_tc) {
+    uint16_t* planes = nullptr; void* wtm = nullptr;
+    if (use_tc >= 2) {
+        // TMA-fed kernel: A pre-split into bf16 hi/lo planes (use_tc 2: fp32 result; 3: result as planes, merged back into `out`;
+        // 4: A as ONE exact fp16 plane - the caller passes fp16-representable values - against fp16 hi/lo weights)
+        const bool f16 = use_tc == 4;
+        const int ldp = (K + 7) / 8 * 8;
+        CK(cudaMalloc((void**)&planes, ((size_t)2 * M * ldp + (size_t)2 * M * N) * sizeof(uint16_t)));
+        uint16_t* a_hi = planes; uint16_t* a_lo = planes + (size_t)M * ldp; uint16_t* o_hi = a_lo + (size_t)M * ldp; uint16_t* o_lo = o_hi + (size_t)M * N;
+        CK(cudaMemsetAsync(planes, 0, (size_t)2 * M * ldp * sizeof(uint16_t), s));
+        if (Apos || (K & 1) || (lda & 1)) rc = fail(ctx, 3, "mesm_debug_linear: the TMA kernel takes no Apos / odd K");
+        else if (f16) CK(launch_f32_to_f16(A, M, K, lda, a_hi, ldp, s));
+        else CK(launch_split_planes(A, M, K, lda, a_hi, a_lo, ldp, s));
+        wtm = tma_pack_weights(W, 0, N, K, nullptr, f16, s);
+        CK(cudaStreamSynchronize(s));
+        op.a_hi = a_hi; op.a_lo = f16 ? nullptr : a_lo; op.lda_p = ldp; op.Wtm = wtm;
+        if (use_tc == 3) { op.out = nullptr; op.out_hi = o_hi; op.out_lo = o_lo; op.ldp = N; }
+        if (rc == 0) {
+            if (!wtm || !linear_tma_eligible(op)) rc = fail(ctx, 3, "mesm_debug_linear: shape not eligible for the TMA-fed tcgen05 kernel");
+            else { cudaError_t e = launch_linear_tma(op, s); if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e)); }
+        }
+        if (rc == 0 && use_tc == 3) { cudaError_t e = launch_merge_planes(o_hi, o_lo, (long long)M * N, out, s); if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e)); }
+    } else if (use_tc) {
         if (!linear_tc_eligible(op)) rc = fail(ctx, 3, "mesm_debug_linear: shape not eligible for the tcgen05 kernel");
         else { cudaError_t e = launch_linear_tc(op, s); if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e)); }
     } else {
         cudaError_t e = launch_linear_simt(op, s); if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e));
     }
+    if (rc == 0 && getenv("MESM_DEBUG_LINEAR_ITERS")) {      // developer timing loop (tools/linear_bench.py): same launch repeated, CUDA events
+        const int iters = atoi(getenv("MESM_DEBUG_LINEAR_ITERS"));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters; ++i) {
+            if (use_tc >= 2) launch_linear_tma(op, s); else if (use_tc) launch_linear_tc(op, s); else launch_linear_simt(op, s);
+        }
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[linear_bench] mode %d M %d N %d K %d: %.1f us per launch\n", use_tc, M, N, K, 1e3f * ms / iters);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess && rc == 0) rc = fail(ctx, (int)e, std::string("mesm_debug_linear: ") + cudaGetErrorString(e));
-    cudaFree(Wt); cudaFree(Wp); cudaFree(cs);
+    cudaFree(Wt); cudaFree(Wp); cudaFree(cs); cudaFree(planes); tma_free_weights(wtm);
     return rc;
 }
 

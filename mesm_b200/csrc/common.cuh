@@ -68,6 +68,11 @@ struct LinearOp {
     float* pre_ln;                                // optional store of the value before LayerNorm ([M,N], ld = N)
     int nbatch;                                   // >1: blockIdx.z batches (per-head GEMMs); element strides below
     long long bsA, bsW, bsBias, bsOut;
+    // Pre-split 16-bit planes: an activation x is stored as hi = bf16(x) and lo = bf16(x - hi), two row-major
+    // [M, ld] planes - the form the tensor pipe consumes, so the TMA-fed GEMM (linear_tma.cu) needs no converter warps.
+    const uint16_t* a_hi; const uint16_t* a_lo; int lda_p;    // A given as planes (A is then ignored); a_lo == nullptr: ONE fp16 plane (exact)
+    uint16_t* out_hi; uint16_t* out_lo; int ldp;              // optional store of the final value as planes (row m -> row m)
+    const void* Wtm;                                          // host object: the weights as TMA-addressable planes (TmaWeights, linear_tma.cu)
 };
 
 static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda, const float* Wt, int ldw,
@@ -79,6 +84,7 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
     op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
     op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr;
     op.nbatch = 1; op.bsA = op.bsW = op.bsBias = op.bsOut = 0;
+    op.a_hi = op.a_lo = nullptr; op.lda_p = 0; op.out_hi = op.out_lo = nullptr; op.ldp = 0; op.Wtm = nullptr;
     return op;
 }
 
@@ -103,6 +109,15 @@ cudaError_t launch_linear(const LinearOp& op, cudaStream_t s);        // dispatc
 cudaError_t launch_linear_simt(const LinearOp& op, cudaStream_t s);   // fp32 SIMT kernel
 cudaError_t launch_linear_tc(const LinearOp& op, cudaStream_t s);     // tcgen05 split-bf16 kernel
 bool linear_tc_eligible(const LinearOp& op);
+// TMA-fed persistent tcgen05 kernel (linear_tma.cu): A and W as 16-bit planes, no operand conversion in the kernel
+cudaError_t launch_linear_tma(const LinearOp& op, cudaStream_t s);
+bool linear_tma_eligible(const LinearOp& op);
+// weights as planes + their tensor maps; fp16 = single-plane-A mode (exact fp16 activations x fp16 hi/lo weights, 2 MMAs)
+void* tma_pack_weights(const float* W, int row0, int nrows, int K, const float* gamma, bool fp16, cudaStream_t s);   // host object, free with tma_free_weights
+void tma_free_weights(void* w);
+cudaError_t launch_f32_to_f16(const float* x, long long rows, int cols, int ldx, uint16_t* y, int ldy, cudaStream_t s);
+cudaError_t launch_merge_planes(const uint16_t* hi, const uint16_t* lo, long long n, float* out, cudaStream_t s);     // out = hi + lo (bf16 planes)
+cudaError_t launch_split_planes(const float* x, long long rows, int cols, int ldx, uint16_t* hi, uint16_t* lo, int ldp, cudaStream_t s);
 size_t tc_packed_bytes(int nrows, int K);
 cudaError_t launch_pack_tc(const float* W, int row0, int nrows, int K, const float* gamma, void* out, cudaStream_t s);
 
