@@ -281,7 +281,7 @@ class ReferencePath:
 def cpu_reference_pairs_per_s(name, cfg, state_dict, batch, steps, warmup, threads):
     torch.set_num_threads(threads)
     ref = ReferencePath(name, cfg, state_dict, "cpu")
-    b = ref.batch(batch)
+    b = _f32_features(ref.batch(batch))
     B = b["video_feat"].shape[0]
     times = []
     for it in range(warmup + steps):
@@ -297,7 +297,7 @@ def gpu_eager_pairs_per_s(name, cfg, state_dict, wl_full, pairs, device, steps=3
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     ref = ReferencePath(name, cfg, state_dict, device)
-    b = ref.batch(take_groups(wl_full, pairs))
+    b = _f32_features(ref.batch(take_groups(wl_full, pairs)))
     B = b["video_feat"].shape[0]
     res = {}
     for decode in (False, True):
@@ -309,6 +309,13 @@ def gpu_eager_pairs_per_s(name, cfg, state_dict, wl_full, pairs, device, steps=3
         torch.cuda.synchronize()
         res["forward_decode" if decode else "forward"] = B * steps / (time.perf_counter() - t0)
     return res, B, ref
+
+
+def _f32_features(b):
+    """The reference legs take fp32 tensors: the stored fp16 values upcast (exactly the values our arm computes on)."""
+    if b["video_feat"].dtype == torch.float16:
+        b = dict(b, video_feat=b["video_feat"].float())
+    return b
 
 
 def take_groups(wl, n_pairs):
@@ -346,6 +353,10 @@ def main():
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--e2e-sub", type=int, default=2048, help="pairs per host->device sub-batch of the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--feature-dtype", default="f16", choices=["f16", "f32"],
+                    help="storage format of the clip features (host and HBM): f16 = the 16-bit storage option of the ingest front-end "
+                         "(values used exactly; every arm - ours, the CPU reference, the eager GPU reference - is fed the same values), "
+                         "f32 = fp32 tensors as the reference's loaders deliver them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -356,6 +367,7 @@ def main():
               "Lv": cfg["max_video_l"], "Lt": cfg["max_words_l"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
               "ragged_video": f"U{{{cfg['max_video_l'] // 2}..{cfg['max_video_l']}}}" if wlc["ragged"] else "uniform",
               "negative_branch": True, "align_scores": True, "nms_thd": NMS_THD, "parallelism": f"dp{world}",
+              "feature_storage": "fp16 (fp16-representable clip features, used exactly; computed in fp32 accumulate)" if args.feature_dtype == "f16" else "fp32",
               "l2": "inputs (GBs per GPU) larger than L2; no flush needed"}
     if wlc["dense_nms"]:
         config["dense_nms_candidates"] = wlc["dense_nms"]
@@ -374,6 +386,8 @@ def main():
             return
         threads = os.cpu_count() or 1
         wl = make_workload(cfg, 64, 1234, "cpu", wlc)
+        if args.feature_dtype == "f16":
+            wl["video_feat"] = wl["video_feat"].half().float()       # the same fp16-representable values our arm stores in 16 bits
         sub = take_groups(wl, args.cpu_sample_pairs)
         pps, sec, ref = cpu_reference_pairs_per_s(args.config, cfg, model.state_dict(), sub, max(args.steps, 1), max(args.warmup, 0), threads)
         line = {"impl": "reference", "metric": "video-query pairs/sec", "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
@@ -397,6 +411,9 @@ def main():
     model = model.to(dev)
     model.chunk_pairs = args.chunk_pairs
     wl = make_workload(cfg, args.pairs, 1234 + rank, dev, wlc)
+    f16 = args.feature_dtype == "f16"
+    if f16:
+        wl["video_feat"] = wl["video_feat"].half()                   # resident in HBM in the storage format
     B, Lv = args.pairs, cfg["max_video_l"]
     lib = _lib.lib()
     from mesm_b200.sharding import gather_topk
@@ -406,10 +423,15 @@ def main():
     layout = {"rows": "zero-padded [B, Lv]" if vlen_host is None else "packed variable-length (host clip counts passed as video_len)",
               "clip_rows_per_gpu": int(B * Lv if vlen_host is None else wl["video_len"].sum())}
     dname = cfg["dataset_name"]
+    # the collate step replicates a group's video for each of its queries (dataset/base.py:307-309): the engine may read a pair's
+    # clips from its group's first pair and project every video once (charades / tacos grouping only)
+    shared_res = vlen_host is not None and dname != "qvhighlights" and not os.environ.get("MESM_NO_SHARED")
+    layout["video_projection"] = "once per video (shared_group_video)" if shared_res else "once per pair"
 
     def step():
         out = model(wl["video_feat"], wl["video_mask"], wl["words_feat"], None, None, wl["num_clips"],
-                    dataset_name=dname, is_training=False, neg_index=wl["neg_index"], video_len=vlen_host)
+                    dataset_name=dname, is_training=False, neg_index=wl["neg_index"], video_len=vlen_host,
+                    shared_group_video=shared_res)
         S = mesm_b200.align_scores(out["projed_video_feat"], wl["clip_mask"], out["expanded_words_feat"], out["expanded_words_mask"], 0.5)
         win, order, keep, cnt = mesm_b200.decode_nms(out["pred_logits"], out["pred_spans"], wl["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
@@ -512,7 +534,7 @@ def main():
     k1 = [(k, v) for k, v in rep_rows.items() if k.startswith("input_proj")]
     if k1:
         k1_ms = sum(v[1] for _, v in k1)
-        feat_bytes = float(getattr(model._eng, "last_feature_bytes", 0)) or clip_rows * cfg["v_feat_dim"] * 4.0
+        feat_bytes = float(model._eng.last_feature_bytes)
         roof["input_projection"] = {"bound": "hbm", "kernel": k1[0][0], "achieved": feat_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak_hbm,
                                     "unit": "GB/s", "frac": feat_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm, "kernel_ms_per_step": k1_ms,
                                     "algorithmic_bytes": feat_bytes}

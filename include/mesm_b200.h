@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MESM_ABI_VERSION 2
+#define MESM_ABI_VERSION 3
 
 typedef struct mesm_ctx mesm_ctx;
 
@@ -70,7 +70,7 @@ typedef struct mesm_inputs {
     int32_t Lv;                    /* padded clip count */
     int32_t Lt;                    /* padded word count */
     int32_t G;                     /* video groups */
-    const float*   video_feat;     /* dev  [B,Lv,v_feat_dim] */
+    const void*    video_feat;     /* dev  [B,Lv,v_feat_dim] fp32 (fp16 when video_feat_f16 = 1) */
     const uint8_t* video_mask;     /* dev  [B,Lv] 1 = valid */
     const float*   words_feat;     /* dev  [B,Lt,t_feat_dim] — `words_id` of the text_encoder=None path (model.py:160-161) */
     const int64_t* num_clips;      /* HOST [G]  (the reference calls .tolist() on it, model.py:191) */
@@ -84,7 +84,13 @@ typedef struct mesm_inputs {
                                     * (eval.py:70-72 truncates them).  NULL: every pair is processed at Lv rows. */
     int32_t shared_group_video;    /* 1: the clips of pair b are read from the FIRST pair of its video group (the
                                     * charades / tacos collate replicates the video per query, dataset/base.py:307-309;
-                                    * see mesm_upload_clips).  Needs video_len; must be 0 for qvhighlights grouping. */
+                                    * see mesm_upload_clips).  Needs video_len; must be 0 for qvhighlights grouping.
+                                    * The first input projection (K = v_feat_dim, the HBM-bound stage) then runs once per
+                                    * video instead of once per pair. */
+    int32_t video_feat_f16;        /* 1: video_feat holds IEEE fp16 values - the 16-bit feature-storage option of the ingest
+                                    * front-end.  The values are used exactly (parity = the reference fed the
+                                    * same values upcast to fp32): the first projection multiplies the exact fp16 plane by
+                                    * fp16 hi/lo weights on the tensor pipe (2 MMAs per product).  Needs video_len. */
 } mesm_inputs;
 
 /* Every pointer may be NULL (that output is then not materialised).  Shapes follow model/model.py:334-351. */
@@ -114,6 +120,8 @@ int    mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_outputs* ou
 int    mesm_set_chunk_pairs(mesm_ctx* ctx, int32_t pairs);
 /* Number of kernel launches the last mesm_forward issued (bench.py's gpu_launches). */
 int64_t mesm_last_launch_count(const mesm_ctx* ctx);
+/* Clip-feature bytes the first input projection of the last mesm_forward streamed from HBM (bench.py's HBM roofline entry). */
+int64_t mesm_last_feature_bytes(const mesm_ctx* ctx);
 
 /* Measurement aid for bench.py: between begin/end every fused-linear launch of the calling thread is bracketed by CUDA
  * events on its stream.  end() synchronises those events and writes {linear ms, algorithmic flops, algorithmic bytes,
@@ -139,6 +147,10 @@ const char* mesm_profile_report(void);
 int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv,
                       float* dev_feat, uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied,
                       void* stream);
+/* the same for features stored as fp16 (host_feat / dev_feat [B,L,Dv] IEEE half): half the bytes cross PCIe */
+int mesm_upload_clips_f16(const void* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv,
+                          void* dev_feat, uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied,
+                          void* stream);
 
 /* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
 /* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),

@@ -22,7 +22,7 @@ class MesmInputs(Structure):
     _fields_ = [("B", c_int32), ("Lv", c_int32), ("Lt", c_int32), ("G", c_int32),
                 ("video_feat", c_void_p), ("video_mask", c_void_p), ("words_feat", c_void_p),
                 ("num_clips", POINTER(c_int64)), ("neg_index", c_void_p), ("video_len", POINTER(c_int32)),
-                ("shared_group_video", c_int32)]
+                ("shared_group_video", c_int32), ("video_feat_f16", c_int32)]
 
 
 class MesmOutputs(Structure):
@@ -49,11 +49,14 @@ SYMBOLS = {
     "mesm_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "mesm_forward": (c_int, [c_void_p, POINTER(MesmInputs), POINTER(MesmOutputs), c_void_p, c_size_t, c_void_p]),
     "mesm_last_launch_count": (c_int64, [c_void_p]),
+    "mesm_last_feature_bytes": (c_int64, [c_void_p]),
     "mesm_profile_begin": (None, []),
     "mesm_profile_end": (None, [POINTER(c_double)]),
     "mesm_profile_report": (c_char_p, []),
     "mesm_upload_clips": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_int32,
                                   POINTER(c_int64), c_void_p]),
+    "mesm_upload_clips_f16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_int32,
+                                      POINTER(c_int64), c_void_p]),
     "mesm_decode_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(MesmDecodeParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mesm_temporal_nms": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),
@@ -94,7 +97,7 @@ def lib():
             fn = getattr(l, name)      # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if l.mesm_abi_version() != 2:
+        if l.mesm_abi_version() != 3:
             raise ImportError("libmesm_b200.so ABI version mismatch")
         _lib = l
     return _lib

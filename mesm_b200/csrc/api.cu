@@ -110,6 +110,10 @@ struct Packer {
             launch_pack_tc(W->p, row0, nrows, (int)K, gamma, wp, s);
             r.Wp = wp;
         }
+        if (nrows % 256 == 0 && K % 8 == 0 && !gamma) {          // TMA-fed kernel: weights as plain bf16 hi/lo planes + tensor maps
+            void* wt = tma_pack_weights(W->p, row0, nrows, (int)K, nullptr, false, s);
+            if (wt) { ctx->owned_tma.push_back(wt); r.Wtm = wt; }
+        }
         if (gamma) {
             float* cs = alloc(nrows);
             float* cb = alloc(nrows);
@@ -376,10 +380,16 @@ static int force_simt() {
     return v;
 }
 cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) {
+    if (op.a_hi) {                                     // A as pre-split planes: the TMA-fed kernel is the only consumer
+        if (!linear_tma_eligible(op)) return cudaErrorInvalidValue;
+        const double fl = 2.0 * op.M * (double)op.N * (double)op.K;
+        ProfScope ps(op.a_lo ? (op.ln_g ? "linear_tma +LN" : "linear_tma") : "input_proj linear_tma fp16 features", s, fl, op.M);
+        return launch_linear_tma(op, s);
+    }
     const bool tc = !force_simt() && linear_tc_eligible(op);
     const double flops = 2.0 * op.M * (double)op.N * ((double)op.K + op.K2) * (op.nbatch > 1 ? op.nbatch : 1);
     const char* name = "linear_simt";
-    if (tc) name = op.K > 1024 ? "linear_tc K>1024" : (op.K == 1024 ? "linear_tc K=1024" : (op.N > 256 ? "linear_tc K<=512 N>256" : (op.ln_g ? "linear_tc K<=512 N=256 +LN" : "linear_tc K<=512 N=256")));
+    if (tc) name = op.K > 1024 ? "input_proj linear_tc fp32 features" : (op.K == 1024 ? "linear_tc K=1024" : (op.N > 256 ? "linear_tc K<=512 N>256" : (op.ln_g ? "linear_tc K<=512 N=256 +LN" : "linear_tc K<=512 N=256")));
     ProfScope ps(name, s, flops, op.M);
     return tc ? launch_linear_tc(op, s) : launch_linear_simt(op, s);
 }
@@ -433,6 +443,7 @@ void mesm_destroy(mesm_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (void* p : ctx->owned) cudaFree(p);
     for (void* p : ctx->owned_host) free(p);
+    for (void* p : ctx->owned_tma) tma_free_weights(p);
     for (auto& kv : ctx->w) cudaFree(kv.second.p);
     for (int i = 0; i < mesm_ctx::kTabSlots; ++i) {
         if (ctx->h_tab[i]) cudaFreeHost(ctx->h_tab[i]);
@@ -448,6 +459,7 @@ int mesm_set_chunk_pairs(mesm_ctx* ctx, int32_t pairs) {
 }
 
 int64_t mesm_last_launch_count(const mesm_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+int64_t mesm_last_feature_bytes(const mesm_ctx* ctx) { return ctx ? ctx->last_feature_bytes : 0; }
 
 void mesm_profile_begin(void) {
     g_stats.profile = true;
@@ -491,6 +503,9 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
     ctx->owned.clear();
     for (void* p : ctx->owned_host) free(p);
     ctx->owned_host.clear();
+    for (void* p : ctx->owned_tma) tma_free_weights(p);
+    ctx->owned_tma.clear();
+    ctx->vid0_f16 = nullptr;
     const mesm_cfg& cf = ctx->cfg;
     Packer P{ctx, s};
     // input projections: LinearLayer.0 = LN(in)->Linear->ReLU (LN folded into the GEMM), LinearLayer.1 = LN(256)->Linear
@@ -499,6 +514,13 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
         const Tensor* b = P.get("input_vid_proj.0.LayerNorm.bias", {cf.v_feat_dim});
         ctx->vid0 = P.pack("input_vid_proj.0.net.1.weight", "input_vid_proj.0.net.1.bias", D, cf.v_feat_dim, 0, D,
                            g ? g->p : nullptr, b ? b->p : nullptr);
+        {   // the same folded weights as fp16 hi/lo planes: first projection of 16-bit stored features (exact fp16 A plane)
+            const Tensor* W0 = P.get("input_vid_proj.0.net.1.weight", {D, cf.v_feat_dim});
+            if (W0 && g) {
+                void* wt = tma_pack_weights(W0->p, 0, D, cf.v_feat_dim, g->p, true, s);
+                if (wt) { ctx->owned_tma.push_back(wt); ctx->vid0_f16 = wt; }
+            }
+        }
         ctx->vid1_ln = P.norm("input_vid_proj.1.LayerNorm");
         ctx->vid1 = P.lin("input_vid_proj.1.net.1", D, D);
         g = P.get("input_txt_proj.0.LayerNorm.weight", {cf.t_feat_dim});
@@ -580,12 +602,16 @@ int mesm_finalize_weights(mesm_ctx* ctx, void* stream) {
 // =====================================================================================================================
 namespace {
 
+constexpr int kF16ChunkRows = 65536;      // rows of 16-bit features repacked + projected per launch pair (bounds the staging buffer)
+
 struct FwdPlan {
     // whole-batch buffers
     float *wn, *wstat, *t1, *expw, *negw, *projV, *recon;
     uint8_t *wmask, *emask, *epad, *wpad, *neg_epad, *neg_wpad, *padV_all;
     int* d_tab;
     int *t_pad, *t_in, *t_c2e, *t_g, *t_posV, *t_posE;   // packed-layout gather tables (kernels.h: launch_pack_table / launch_chunk_tables)
+    int *t_vin, *t_p2v;                                  // per-video tables (launch_video_tables)
+    uint16_t* xf16;                                      // staging of the repacked fp16 feature rows (kF16ChunkRows at a time)
     // chunk buffers
     float *vstat, *v1, *posV, *posE, *xa, *xb, *enh, *E, *E2, *P1, *P2, *Qenh0;
     uint8_t *padV, *padE;
@@ -606,7 +632,9 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.recon = ar.get<float>((size_t)B * D);
     p.wmask = ar.get<uint8_t>(Rt); p.emask = ar.get<uint8_t>(Rte); p.epad = ar.get<uint8_t>(Rte); p.wpad = ar.get<uint8_t>(Rt);
     p.neg_epad = ar.get<uint8_t>(Rte); p.neg_wpad = ar.get<uint8_t>(Rt); p.padV_all = ar.get<uint8_t>((size_t)B * Lv);
-    p.d_tab = ar.get<int>((size_t)3 * B + 2 * (G + 1) + 2 + 3 * (size_t)Lv + 2);
+    p.d_tab = ar.get<int>((size_t)3 * B + 3 * (G + 1) + 2 + 3 * (size_t)Lv + 2);
+    p.t_vin = ar.get<int>((size_t)B * Lv); p.t_p2v = ar.get<int>((size_t)B * Lv);
+    p.xf16 = ar.get<uint16_t>((size_t)kF16ChunkRows * ((c->cfg.v_feat_dim + 7) / 8 * 8));
     p.t_posV = ar.get<int>((size_t)Bc * Lv); p.t_posE = ar.get<int>((size_t)Bc * (Lv + 1));
     {   // position table and its products with every projection that consumes positions (packed layout only)
         const size_t nPT = 1 + std::min<size_t>((size_t)Lv * (Lv + 1) / 2, (size_t)B * Lv);
@@ -666,7 +694,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     if (tot != B) return fail(ctx, 1, "sum(num_clips) != B");
     if (in->neg_index && G < 2) return fail(ctx, 1, "the negative branch needs >= 2 video groups (sample_outclass_neg raises in the reference)");
     const bool packed = in->video_len != nullptr;       // variable-length clip rows: no work on the zero padding
-    const size_t tab_ints = (size_t)3 * B + (G + 1) + 1 + 3 * (size_t)Lv + 1;
+    const size_t tab_ints = (size_t)3 * B + (G + 1) + 1 + 3 * (size_t)Lv + 1 + (G + 1);
     const int ts = ctx->tab_turn;                    // this forward's slot of the pinned-table ring
     ctx->tab_turn = (ts + 1) % mesm_ctx::kTabSlots;
     if (ctx->tab_event_pending[ts]) { CK(cudaEventSynchronize(ctx->tab_event[ts])); ctx->tab_event_pending[ts] = false; }   // its last reader has run
@@ -716,6 +744,16 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     }
     int Bc_max = 0;
     for (auto& ch : chunks) Bc_max = std::max(Bc_max, ch.second - ch.first);
+    // videos of the batch: one per group when the group's pairs share it (prefix sums of their clip counts), else one per pair
+    const bool shared_video = in->shared_group_video != 0;
+    const bool f16 = in->video_feat_f16 != 0;
+    if ((shared_video || f16) && !packed) return fail(ctx, 1, "mesm_forward: shared_group_video / video_feat_f16 need video_len");
+    if (shared_video && cf.qvh_grouping) return fail(ctx, 1, "mesm_forward: shared_group_video needs the charades / tacos grouping");
+    if (f16 && !ctx->vid0_f16) return fail(ctx, 1, "mesm_forward: fp16 features need the TMA weight planes (cuTensorMapEncodeTiled unavailable?)");
+    int* h_vcu = h_dloff + Lv;
+    h_vcu[0] = 0;
+    for (int g = 0; g < G; ++g) h_vcu[g + 1] = h_vcu[g] + (shared_video ? in->video_len[h_gstart[g]] : 0);
+    const long long n_vrows = shared_video ? h_vcu[G] : (packed ? h_cu[B] : (long long)B * Lv);
 
     Arena ar(workspace, workspace_bytes);
     FwdPlan p;
@@ -729,7 +767,8 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     if (!projV_all || packed) projV_all = p.projV;
     int* d_group = p.d_tab; int* d_slot = d_group + B; int* d_gstart = d_slot + B; int* d_cu_all = d_gstart + (G + 1);
     int* d_lenoff = d_cu_all + (B + 1); int* d_dllen = d_lenoff + (Lv + 1); int* d_dloff = d_dllen + Lv;
-    int* d_glen = d_dloff + Lv;
+    int* d_vcu = d_dloff + Lv;                          // per-video prefix sums (shared group videos)
+    int* d_glen = d_vcu + (G + 1);
     const int* d_cu = packed ? d_cu_all : nullptr;
     {
         int* h_dev = nullptr;                       // device alias of the pinned table (identical under UVA)
@@ -741,12 +780,9 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));
     // t_pad: packed clip row -> this pair's row in the zero-padded [B, Lv] layout (outputs); t_in: the row its features are
     // read from (the same, or the group's first pair when the collate-replicated video was uploaded once per group)
-    const bool shared_video = in->shared_group_video != 0;
-    if (shared_video && (!packed || cf.qvh_grouping))
-        return fail(ctx, 1, "mesm_forward: shared_group_video needs video_len and the charades / tacos grouping");
-    const int* t_in = shared_video ? p.t_in : p.t_pad;
     if (packed) CK(launch_pack_table(d_cu, B, Lv, p.t_pad, s));
-    if (shared_video) CK(launch_pack_table(d_cu, B, Lv, p.t_in, s, d_group, d_gstart));
+    if (shared_video) CK(launch_video_tables(d_cu, d_vcu, d_group, d_gstart, B, G, Lv, p.t_vin, p.t_p2v, s));
+    const int* t_vin = shared_video ? p.t_vin : p.t_pad;          // video row -> row of the padded input
     // Position terms (packed layout).  PositionEmbeddingSine of a clip depends only on (clip count, clip index): build the
     // table once per distinct clip count of the batch and push it through every projection that adds positions to its
     // input - (x + pos) W = x W + (pos W)[row] - so those GEMMs lose their second K-sweep and the decoder's k_pos GEMMs
@@ -786,21 +822,41 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     const int recon_max_keys = cf.qvh_grouping ? max_nc * Lv : Lv;
 
     // ---- whole batch: input projection of the clips (model/model.py:166) — row-wise, no reason to chunk ---------------
+    //      LinearLayer 0 (K = v_feat_dim: the one HBM-bound stage) runs once per VIDEO: the queries of a charades / tacos group
+    //      share their video (dataset/base.py:307-309), so its projection is computed for the group's first pair only and
+    //      LinearLayer 1 gathers it per pair (t_p2v).
     {
         const long long Rall = packed ? h_cu[B] : (long long)B * Lv;
-        const RowMap inmap = packed ? table_map(t_in) : identity_map();        // packed row -> row of the padded input
         const RowMap outmap = packed ? table_map(p.t_pad) : identity_map();    // packed row -> row of a padded output
-        // LayerNorm(Dv) is folded into the GEMM; its row statistics are accumulated by the kernel's operand converters
-        // while the features stream through (one pass over the feature bytes - the only HBM-bound stage of the path)
-        Lin fused((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D);
-        fused.amap(inmap).fold_fused(ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln);
-        if (linear_tc_eligible(fused.op) && !getenv("MESM_FORCE_SIMT")) {
-            CK(fused.run(s));
+        // LayerNorm(Dv) is folded into the GEMM: out = rstd * (x . W gamma - mean * colsum) + (W beta + b)
+        if (f16) {
+            // 16-bit stored features: rows gathered into a 16-byte-aligned staging buffer (with their LayerNorm statistics), then
+            // ONE exact fp16 A plane x fp16 hi/lo weight planes through the TMA engine (linear_tma.cu), kF16ChunkRows at a time
+            const int ldx = (cf.v_feat_dim + 7) / 8 * 8;
+            for (long long r0 = 0; r0 < n_vrows; r0 += kF16ChunkRows) {
+                const int R = (int)std::min<long long>(kF16ChunkRows, n_vrows - r0);
+                CK(launch_repack_f16_rows((const uint16_t*)in->video_feat, t_vin, r0, R, cf.v_feat_dim, p.xf16, ldx, p.vstat + 2 * r0, s));
+                Lin k1(R, ctx->vid0, nullptr, 0, p.v1 + r0 * D, D);
+                k1.aplanes(p.xf16, nullptr, ldx).wtm(ctx->vid0_f16).fold(p.vstat + 2 * r0, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln);
+                CK(k1.run(s));
+            }
+            ctx->last_feature_bytes = n_vrows * (long long)cf.v_feat_dim * 2;
         } else {
-            CK(launch_row_stats(in->video_feat, Rall, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s, packed ? t_in : nullptr));
-            CK(Lin((int)Rall, ctx->vid0, in->video_feat, cf.v_feat_dim, p.v1, D).amap(inmap).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+            const float* vf = (const float*)in->video_feat;
+            const RowMap inmap = packed ? table_map(t_vin) : identity_map();      // video row -> row of the padded input
+            // the row statistics are accumulated by the kernel's operand converters while the features stream through
+            Lin fused((int)n_vrows, ctx->vid0, vf, cf.v_feat_dim, p.v1, D);
+            fused.amap(inmap).fold_fused(ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln);
+            if (linear_tc_eligible(fused.op) && !getenv("MESM_FORCE_SIMT")) {
+                CK(fused.run(s));
+            } else {
+                CK(launch_row_stats(vf, n_vrows, cf.v_feat_dim, cf.v_feat_dim, p.vstat, s, packed ? t_vin : nullptr));
+                CK(Lin((int)n_vrows, ctx->vid0, vf, cf.v_feat_dim, p.v1, D).amap(inmap).fold(p.vstat, ctx->vid0.colsum).act(ACT_RELU).ln(ctx->vid1_ln).run(s));
+            }
+            ctx->last_feature_bytes = n_vrows * (long long)cf.v_feat_dim * 4;
         }
         Lin second((int)Rall, ctx->vid1, p.v1, D, projV_all, D);
+        if (shared_video) second.amap(table_map(p.t_p2v));                    // pair row -> its video's row
         if (projV_padded_out) {           // the caller's [B, Lv, 256] output: valid rows scattered, pad rows zero
             second.op.out2 = projV_padded_out; second.op.ldo2 = D; second.op.o2map = outmap;
         }

@@ -24,16 +24,20 @@ __global__ void build_enc_kernel(const float* __restrict__ src, const float* __r
     }
 }
 
-// Zero the clip rows the ragged upload skipped (pad rows, mask == 0): one CTA per row, 8-byte stores when the pitch allows.
-__global__ void zero_pad_rows_kernel(float* __restrict__ feat, const uint8_t* __restrict__ mask, long long rows, int Dv) {
+// Zero the clip rows the ragged upload skipped (pad rows, mask == 0): one CTA per row of `row_bytes` bytes (a multiple of 2).
+__global__ void zero_pad_rows_kernel(uint8_t* __restrict__ feat, const uint8_t* __restrict__ mask, long long rows, int row_bytes) {
     const long long r = blockIdx.x;
     if (r >= rows || mask[r]) return;
-    float* q = feat + r * (long long)Dv;
-    if ((Dv & 1) == 0 && (reinterpret_cast<uintptr_t>(feat) & 7) == 0) {
+    uint8_t* q = feat + r * (long long)row_bytes;
+    if ((row_bytes & 7) == 0 && (reinterpret_cast<uintptr_t>(feat) & 7) == 0) {
         float2* p = reinterpret_cast<float2*>(q);
-        for (int c = threadIdx.x; c < Dv / 2; c += blockDim.x) p[c] = make_float2(0.f, 0.f);
+        for (int c = threadIdx.x; c < row_bytes / 8; c += blockDim.x) p[c] = make_float2(0.f, 0.f);
+    } else if ((row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 3) == 0) {
+        float* p = reinterpret_cast<float*>(q);
+        for (int c = threadIdx.x; c < row_bytes / 4; c += blockDim.x) p[c] = 0.f;
     } else {
-        for (int c = threadIdx.x; c < Dv; c += blockDim.x) q[c] = 0.f;
+        uint16_t* p = reinterpret_cast<uint16_t*>(q);
+        for (int c = threadIdx.x; c < row_bytes / 2; c += blockDim.x) p[c] = 0;
     }
 }
 }  // namespace
@@ -93,8 +97,8 @@ static bool use_memcpy_batch() {
     return v == 1;
 }
 
-int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, float* dev_feat,
-                      uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied, void* stream) {
+static int upload_clips_impl(const uint8_t* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, int elem, uint8_t* dev_feat,
+                             uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied, void* stream) {
     mesm_ctx* ctx = nullptr;
     if (!host_feat || !host_mask || !dev_feat || !dev_mask || B < 1 || L < 1 || Dv < 1) return fail(ctx, 1, "mesm_upload_clips: bad argument");
     if (num_clips) {
@@ -103,7 +107,7 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
         if (tot != B) return fail(ctx, 1, "mesm_upload_clips: sum(num_clips) != B");
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t row = (size_t)Dv * sizeof(float);
+    const size_t row = (size_t)Dv * elem;
     int64_t total = (int64_t)B * L;
     CK(cudaMemcpyAsync(dev_mask, host_mask, (size_t)B * L, cudaMemcpyHostToDevice, s));
     // valid rows are a prefix of each pair (utils/data_utils.py:78-82); a pair whose mask is not a prefix is copied up to its
@@ -116,10 +120,10 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
         if (run_rows <= 0) return cudaSuccess;
         cudaError_t e = cudaSuccess;
         if (batch) {
-            b_dst.push_back(dev_feat + run_start * Dv); b_src.push_back(const_cast<float*>(host_feat) + run_start * Dv);
+            b_dst.push_back(dev_feat + run_start * row); b_src.push_back(const_cast<uint8_t*>(host_feat) + run_start * row);
             b_size.push_back((size_t)run_rows * row);
         } else {
-            e = cudaMemcpyAsync(dev_feat + run_start * Dv, host_feat + run_start * Dv, (size_t)run_rows * row, cudaMemcpyHostToDevice, s);
+            e = cudaMemcpyAsync(dev_feat + run_start * row, host_feat + run_start * row, (size_t)run_rows * row, cudaMemcpyHostToDevice, s);
         }
         total += run_rows * (long long)row;
         run_rows = 0; run_start = -1;
@@ -150,10 +154,20 @@ int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t 
             for (size_t i = 0; i < b_dst.size(); ++i) CK(cudaMemcpyAsync(b_dst[i], b_src[i], b_size[i], cudaMemcpyHostToDevice, s));
         }
     }
-    zero_pad_rows_kernel<<<(unsigned)((long long)B * L), 128, 0, s>>>(dev_feat, dev_mask, (long long)B * L, Dv);
+    zero_pad_rows_kernel<<<(unsigned)((long long)B * L), 128, 0, s>>>(dev_feat, dev_mask, (long long)B * L, (int)row);
     CK(cudaGetLastError());
     if (bytes_copied) *bytes_copied = total;
     return 0;
+}
+
+int mesm_upload_clips(const float* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, float* dev_feat,
+                      uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied, void* stream) {
+    return upload_clips_impl((const uint8_t*)host_feat, host_mask, B, L, Dv, 4, (uint8_t*)dev_feat, dev_mask, num_clips, G, bytes_copied, stream);
+}
+
+int mesm_upload_clips_f16(const void* host_feat, const uint8_t* host_mask, int32_t B, int32_t L, int32_t Dv, void* dev_feat,
+                          uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied, void* stream) {
+    return upload_clips_impl((const uint8_t*)host_feat, host_mask, B, L, Dv, 2, (uint8_t*)dev_feat, dev_mask, num_clips, G, bytes_copied, stream);
 }
 
 size_t mesm_mha_workspace_bytes(int32_t L, int32_t S, int32_t B, int32_t E, int32_t Ev) {

@@ -23,6 +23,7 @@ struct PL {              // packed linear: Wt[Kp, ldw] (k-major), bias[N]
     const float* bias = nullptr;
     const float* colsum = nullptr;   // LayerNorm-folded layers only
     const void* Wp = nullptr;        // tcgen05 packed tiles (null for tiny layers)
+    const void* Wtm = nullptr;       // the same weights as TMA-addressable bf16 hi/lo planes (linear_tma.cu; N % 256 == 0 only)
 };
 
 struct Norm { const float* g = nullptr; const float* b = nullptr; };
@@ -63,9 +64,12 @@ struct mesm_ctx {
     std::unordered_map<std::string, Tensor> w;
     std::vector<void*> owned;
     std::vector<void*> owned_host;      // malloc'ed host objects (tensor maps)
+    std::vector<void*> owned_tma;       // TmaWeights objects (tma_free_weights)
+    const void* vid0_f16 = nullptr;     // input_vid_proj.0 (LayerNorm-folded) as fp16 hi/lo planes: 16-bit stored features
     bool finalized = false;
     int chunk_pairs = 256;
     long long last_launches = 0;
+    long long last_feature_bytes = 0;   // clip-feature bytes the last forward's first projection streamed (roofline of that stage)
 
     PL vid0, vid1, txt0, txt1;
     Norm vid1_ln, txt1_ln;
@@ -118,8 +122,12 @@ struct Lin {    // thin builder around LinearOp
     LinearOp op;
     Lin(int M, const PL& w, const float* A, int lda, float* out, int ldo) {
         op = make_linear(M, w.N, w.K, A, lda, w.Wt, w.ldw, w.bias, out, ldo);
-        op.Wp = w.Wp;
+        op.Wp = w.Wp; op.Wtm = w.Wtm;
     }
+    // A / result as pre-split 16-bit planes (linear_tma.cu); lo == nullptr: one exact fp16 plane
+    Lin& aplanes(const uint16_t* hi, const uint16_t* lo, int ld) { op.a_hi = hi; op.a_lo = lo; op.lda_p = ld; return *this; }
+    Lin& oplanes(uint16_t* hi, uint16_t* lo, int ld) { op.out_hi = hi; op.out_lo = lo; op.ldp = ld; return *this; }
+    Lin& wtm(const void* w) { op.Wtm = w; return *this; }
     Lin& bias(const float* b) { op.bias = b; return *this; }
     Lin& amap(RowMap m) { op.amap = m; return *this; }
     Lin& omap(RowMap m) { op.omap = m; return *this; }

@@ -1,6 +1,7 @@
 // Row-wise / element-wise kernels of the MESM path (all HBM- or latency-bound; vectorised, coalesced, one warp per row
 // where a row reduction is needed).
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 namespace mesm {
@@ -298,6 +299,86 @@ cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStre
     pack_table_kernel<<<B, 128, 0, s>>>(cu, Lv, t_pad, pair_group, group_start);
     LAUNCH_END();
 }
+// per-video tables of a batch whose groups share their video: t_vin[vcu[g] + i] = first pair of g * Lv + i (video row -> row
+// of the zero-padded input), t_p2v[cu[b] + i] = vcu[group(b)] + i (packed pair row -> video row)
+__global__ void video_tables_kernel(const int* __restrict__ cu, const int* __restrict__ vcu, const int* __restrict__ pair_group,
+                                    const int* __restrict__ group_start, int B, int G, int Lv, int* __restrict__ t_vin, int* __restrict__ t_p2v) {
+    const int j = blockIdx.x;
+    if (j < G) {
+        const int v0 = vcu[j], n = vcu[j + 1] - v0, src = group_start[j] * Lv;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) t_vin[v0 + i] = src + i;
+    } else {
+        const int b = j - G, c0 = cu[b], n = cu[b + 1] - c0, v0 = vcu[pair_group[b]];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) t_p2v[c0 + i] = v0 + i;
+    }
+}
+cudaError_t launch_video_tables(const int* cu, const int* vcu, const int* pair_group, const int* group_start, int B, int G, int Lv,
+                                int* t_vin, int* t_p2v, cudaStream_t s) {
+    ProfScope _ps("pack_tables", s);
+    if (B <= 0) return cudaSuccess;
+    video_tables_kernel<<<G + B, 128, 0, s>>>(cu, vcu, pair_group, group_start, B, G, Lv, t_vin, t_p2v);
+    LAUNCH_END();
+}
+
+// 16-bit stored clip features -> the TMA-addressable operand of the first projection: rows gathered through `table` (video
+// row -> row of the padded [B, Lv, Dv] fp16 input, whose 2 * Dv-byte pitch is not 16-byte aligned for the shipped Dv) are
+// copied to a compact [R, ldo] fp16 buffer (ldo % 8 == 0, tail columns zeroed) and their LayerNorm statistics (mean, rstd
+// over the Dv values, fp32, two passes) are written to rowstat.  One warp per row; the second pass re-reads the row from L1/L2.
+__global__ void __launch_bounds__(256) repack_f16_rows_kernel(const uint16_t* __restrict__ x, const int* __restrict__ table, long long r0,
+                                                               long long R, int Dv, uint16_t* __restrict__ out, int ldo, float* __restrict__ rowstat) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const long long src = table ? (long long)table[r0 + r] : r0 + r;
+    const uint16_t* xr = x + src * Dv;
+    uint16_t* orow = out + r * ldo;
+    float s = 0.f;
+    const bool pair_ok = (Dv & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;
+    const int n2 = Dv >> 1;
+    if (pair_ok) {
+        const uint32_t* x2 = reinterpret_cast<const uint32_t*>(xr);
+        for (int c = lane; c < n2; c += 32) {
+            const uint32_t u = __ldg(x2 + c);
+            const __half2 h = *reinterpret_cast<const __half2*>(&u);
+            const float2 f = __half22float2(h);
+            s += f.x + f.y;
+        }
+    } else {
+        for (int c = lane; c < Dv; c += 32) s += __half2float(__ushort_as_half(xr[c]));
+    }
+    s = warp_sum(s);
+    const float mean = s / Dv;
+    float q = 0.f;
+    if (pair_ok) {
+        const uint32_t* x2 = reinterpret_cast<const uint32_t*>(xr);
+        uint32_t* o2 = reinterpret_cast<uint32_t*>(orow);
+        for (int c = lane; c < n2; c += 32) {
+            const uint32_t u = __ldg(x2 + c);
+            o2[c] = u;
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+            const float a = f.x - mean, b = f.y - mean;
+            q = fmaf(a, a, q); q = fmaf(b, b, q);
+        }
+    } else {
+        for (int c = lane; c < Dv; c += 32) {
+            const uint16_t u = xr[c];
+            orow[c] = u;
+            const float d = __half2float(__ushort_as_half(u)) - mean;
+            q = fmaf(d, d, q);
+        }
+    }
+    for (int c = Dv + lane; c < ldo; c += 32) orow[c] = 0;
+    q = warp_sum(q);
+    if (lane == 0) { rowstat[2 * r] = mean; rowstat[2 * r + 1] = rsqrtf(q / Dv + 1e-5f); }
+}
+cudaError_t launch_repack_f16_rows(const uint16_t* x, const int* table, long long r0, long long R, int Dv, uint16_t* out, int ldo,
+                                   float* rowstat, cudaStream_t s) {
+    ProfScope _ps("repack_f16_rows", s);
+    if (R <= 0) return cudaSuccess;
+    repack_f16_rows_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, table, r0, R, Dv, out, ldo, rowstat);
+    LAUNCH_END();
+}
+
 __global__ void chunk_tables_kernel(const int* __restrict__ cu, int* __restrict__ t_c2e, int* __restrict__ t_g,
                                     const int* __restrict__ len_off, int* __restrict__ t_posV, int* __restrict__ t_posE) {
     const int b = blockIdx.x, c0 = cu[b] - cu[0], n = cu[b + 1] - cu[b];

@@ -82,6 +82,11 @@ cudaError_t launch_saliency_packed(const float* p1, const int* cu, const float* 
 // src(b) = b, or the first pair of b's video group when pair_group / group_start are given
 cudaError_t launch_pack_table(const int* cu, int B, int Lv, int* t_pad, cudaStream_t s, const int* pair_group = nullptr,
                               const int* group_start = nullptr);
+cudaError_t launch_video_tables(const int* cu, const int* vcu, const int* pair_group, const int* group_start, int B, int G, int Lv,
+                                int* t_vin, int* t_p2v, cudaStream_t s);
+// rows [r0, r0 + R) of the (gathered) fp16 input -> compact [R, ldo] fp16 rows + their LayerNorm statistics (elementwise.cu)
+cudaError_t launch_repack_f16_rows(const uint16_t* x, const int* table, long long r0, long long R, int Dv, uint16_t* out, int ldo,
+                                   float* rowstat, cudaStream_t s);
 // per chunk: t_c2e[r] = encoder-buffer row of packed clip row r; t_g[b] = encoder-buffer row of pair b's global token
 cudaError_t launch_chunk_tables(const int* cu, int Bc, int* t_c2e, int* t_g, cudaStream_t s, const int* len_off = nullptr,
                                 int* t_posV = nullptr, int* t_posE = nullptr);

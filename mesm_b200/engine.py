@@ -119,7 +119,15 @@ class Engine:
         ``shared_group_video``: the clips of a pair are read from the first pair of its video group (what
         ``prepare_batch_input(..., shared_group_video=True)`` uploads for charades / tacos batches); needs ``video_len``."""
         t_enter = time.perf_counter()
-        video_feat = _f32(video_feat, "video_feat")
+        f16 = video_feat.dtype == torch.float16          # 16-bit feature storage: used exactly (see mesm_inputs.video_feat_f16)
+        if f16:
+            if not video_feat.is_cuda:
+                raise RuntimeError("mesm_b200: `video_feat` must be a CUDA tensor (no CPU fallback)")
+            if video_len is None:
+                raise RuntimeError("mesm_b200: fp16 `video_feat` needs the host clip counts (`video_len`)")
+            video_feat = video_feat.contiguous()
+        else:
+            video_feat = _f32(video_feat, "video_feat")
         words_feat = _f32(words_feat, "words_feat")
         vmask = _u8(video_mask, "video_mask")
         B, Lv, Dv = video_feat.shape
@@ -163,7 +171,7 @@ class Engine:
                 if not torch.equal(m, ar < torch.tensor(vl, device=dev)[:, None]):
                     raise RuntimeError("mesm_b200: `video_len` does not describe `video_mask` (valid clips must be a prefix)")
         inp = MesmInputs(B, Lv, Lt, len(nc), _ptr(video_feat), _ptr(vmask), _ptr(words_feat), nc_arr, _ptr(neg_index), vl_arr,
-                         int(bool(shared_group_video)))
+                         int(bool(shared_group_video)), int(f16))
         out = MesmOutputs(**{k: _ptr(v) for k, v in o.items()})
         # a video group is never split: the internal chunk must hold the largest group
         self.lib.mesm_set_chunk_pairs(self.ctx, max(self.chunk_pairs, max(nc)))
@@ -180,6 +188,10 @@ class Engine:
     @property
     def last_launch_count(self):
         return int(self.lib.mesm_last_launch_count(self.ctx))
+
+    @property
+    def last_feature_bytes(self):
+        return int(self.lib.mesm_last_feature_bytes(self.ctx))
 
 
 # ---- span decode / NMS / span utils (context-free entry points) ------------------------------------------------------

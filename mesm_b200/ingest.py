@@ -50,7 +50,7 @@ def _hold_until_copied(tensors, non_blocking):
 
 
 def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=None, num_clips=None, non_blocking=True):
-    """Ragged upload of host ``video_feat`` f32[B,L,Dv] / ``video_mask`` bool[B,L] on the current stream.
+    """Ragged upload of host ``video_feat`` f32 (or f16: the 16-bit storage option) [B,L,Dv] / ``video_mask`` bool[B,L] on the current stream.
     Returns (dev_feat, dev_mask, bytes_copied).  Pin the host tensors for the copies to be asynchronous.
     ``num_clips`` (optional, charades / tacos batches only): the collate step replicates a group's video for each of
     its queries (dataset/base.py:307-309); only the first pair of every group is then uploaded and the rows of the
@@ -58,17 +58,18 @@ def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=No
     if video_feat.is_cuda or video_mask.is_cuda:
         raise RuntimeError("upload_clips takes host tensors")
     vf = video_feat.contiguous()
-    if vf.dtype != torch.float32:
+    f16 = vf.dtype == torch.float16                     # 16-bit feature storage: uploaded and consumed as is (half the PCIe bytes)
+    if not f16 and vf.dtype != torch.float32:
         vf = vf.float()
     vm = video_mask.contiguous()
     vm8 = vm.view(torch.uint8) if vm.dtype == torch.bool else (vm != 0).view(torch.uint8)
     B, L, Dv = vf.shape
     if out_feat is None:
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        out_feat = torch.empty(B, L, Dv, dtype=torch.float32, device=device)
+        out_feat = torch.empty(B, L, Dv, dtype=vf.dtype, device=device)
     if out_mask is None:
         out_mask = torch.empty(B, L, dtype=torch.bool, device=out_feat.device)
-    if tuple(out_feat.shape) != (B, L, Dv) or tuple(out_mask.shape) != (B, L) or not out_feat.is_contiguous():
+    if tuple(out_feat.shape) != (B, L, Dv) or tuple(out_mask.shape) != (B, L) or not out_feat.is_contiguous() or out_feat.dtype != vf.dtype:
         raise RuntimeError("upload_clips: output buffers do not match the batch shape")
     n = c_int64(0)
     nc_arr, G = None, 0
@@ -92,8 +93,9 @@ def upload_clips(video_feat, video_mask, device=None, out_feat=None, out_mask=No
             raise ValueError("upload_clips(num_clips=...): the pairs of a video group do not share one video")
         nc_arr, G = (c_int64 * len(nc))(*nc), len(nc)
     with torch.cuda.device(out_feat.device):
-        check(_lib.lib().mesm_upload_clips(ctypes.c_void_p(vf.data_ptr()), ctypes.c_void_p(vm8.data_ptr()), B, L, Dv,
-                                           _ptr(out_feat), _ptr(out_mask.view(torch.uint8)), nc_arr, G, byref(n), _stream()))
+        fn = _lib.lib().mesm_upload_clips_f16 if f16 else _lib.lib().mesm_upload_clips
+        check(fn(ctypes.c_void_p(vf.data_ptr()), ctypes.c_void_p(vm8.data_ptr()), B, L, Dv,
+                 _ptr(out_feat), _ptr(out_mask.view(torch.uint8)), nc_arr, G, byref(n), _stream()))
         # vf / vm8 may be temporaries (.contiguous(), .float(), != 0) and the caller may drop its own tensors right away
         _hold_until_copied((video_feat, video_mask, vf, vm8), non_blocking)
     return out_feat, out_mask, int(n.value)

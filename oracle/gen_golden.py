@@ -43,6 +43,9 @@ CASES = [
     ("charades_vgg_l200", "charades_vgg", [2, 1, 2], dict(lv=200)),
     ("tacos_l200", "tacos", [10, 3, 4], dict(lv=200)),
     ("charades_vgg_l600", "charades_vgg", [2, 1], dict(lv=600)),
+    # 16-bit feature storage: the reference fed the fp16-representable values, upcast to fp32
+    ("charades_csf_ragged_f16", "charades_csf", [2, 3, 1, 2], dict(f16_features=True)),
+    ("tacos_l96_f16", "tacos", [4, 3], dict(lv=96, f16_features=True)),
 ]
 NMS_THD = 0.7
 

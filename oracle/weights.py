@@ -141,7 +141,7 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0):
 
 
 def make_inputs(cfg: OracleConfig, num_clips, seed: int = 0, lv=None, lt=None, ragged_video=True, ragged_text=True,
-                min_video_frac=0.5, min_words=3, dur_range=(10.0, 150.0)):
+                min_video_frac=0.5, min_words=3, dur_range=(10.0, 150.0), f16_features=False):
     """Seeded synthetic batch shaped like ``collate``'s output (dataset/base.py:288-355).
 
     num_clips: list of queries per video group; B = sum.  All queries of a group share the video
@@ -179,6 +179,8 @@ def make_inputs(cfg: OracleConfig, num_clips, seed: int = 0, lv=None, lt=None, r
             video_mask[b, :vlens[gi]] = True
             video_len[b] = vlens[gi]
             b += 1
+    if f16_features:                 # the 16-bit feature-storage option: the model is fed the fp16-representable values
+        video_feat = video_feat.half().float()
     words = torch.randn(B, lt, cfg.t_feat_dim, generator=g)
     wl = torch.randint(min(min_words, lt), lt + 1, (B,), generator=g) if ragged_text else torch.full((B,), lt)
     wl[0] = lt

@@ -9,16 +9,19 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north star: <= 1e-3 relative (max|a-b| / max|ref|) on logits, spans, saliency
 
 
-def _run(name, chunk_pairs=256, packed=False):
+def _run(name, chunk_pairs=256, packed=False, shared=False):
     import mesm_b200
     from mesm_b200.ingest import clip_counts
     cfg, sd, inp, neg, gold, meta = load_case(name)
     eng = mesm_b200.Engine(engine_cfg(cfg), chunk_pairs=chunk_pairs)
     eng.load_state_dict(sd)
     dev = eng.device
-    out = eng.forward(inp["video_feat"].to(dev), inp["video_mask"].to(dev), inp["words_feat"].to(dev), inp["num_clips"],
+    vf = inp["video_feat"].to(dev)
+    if meta["kwargs"].get("f16_features") and packed:
+        vf = vf.half()                  # the 16-bit stored features themselves (packed rows only); padded: their fp32 upcast
+    out = eng.forward(vf, inp["video_mask"].to(dev), inp["words_feat"].to(dev), inp["num_clips"],
                       neg_index=neg.to(dev), want=("core", "aux", "rec", "taps"),
-                      video_len=clip_counts(inp["video_mask"]) if packed else None)
+                      video_len=clip_counts(inp["video_mask"]) if packed else None, shared_group_video=shared)
     torch.cuda.synchronize()
     return cfg, inp, gold, out
 
@@ -49,6 +52,20 @@ def test_forward_matches_reference_golden(name, packed):
     sal_h = out["saliency_scores"].half().float().cpu()
     ref_h = torch.from_numpy(gold["saliency_scores"]).half().float()
     assert rel_err(sal_h, ref_h, vm) <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "charades_csf_ragged", "charades_csf_ragged_f16", "tacos_l96_f16", "tacos_l200"])
+def test_per_video_projection_matches_reference_golden(name):
+    """shared_group_video: the K = v_feat_dim projection runs once per video (and, for fp16 features, on the TMA-fed kernel with
+    an exact fp16 operand plane); results = the reference's golden outputs."""
+    cfg, inp, gold, out = _run(name, packed=True, shared=True)
+    vm = inp["video_mask"]
+    for k in ("pred_logits", "pred_spans", "recon_feat", "projed_recon_feat"):
+        assert rel_err(out[k], gold[k]) <= TOL, k
+    for k in ("saliency_scores", "neg_saliency_scores"):
+        assert rel_err(out[k], gold[k], vm) <= TOL, k
+    assert rel_err(out["projed_video_feat"][:, 0], gold["projed_video_row0"]) <= TOL
+    assert rel_err(out["enhanced_video_feat"][:, 0], gold["enhanced_video_row0"]) <= TOL
 
 
 @pytest.mark.parametrize("name", ["tiny_ragged", "charades_csf_ragged", "tiny_qvh_groups", "tacos_l96"])

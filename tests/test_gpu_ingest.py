@@ -158,3 +158,39 @@ def test_pinned_source_may_be_reused_right_after_the_call():
     out = mesm_b200.prepare_batch_input(dict(video_feat=vf.clone(), video_mask=mask), "cuda", non_blocking=False)
     assert torch.cuda.current_stream().query()
     assert torch.equal(out["video_feat"].cpu(), vf)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_fp16_feature_storage_upload_and_forward(shared):
+    """16-bit feature storage: fp16 host features cross PCIe as they are (half the bytes), bit-exact on the device,
+    and the forward on them equals the reference fed the same values upcast to fp32 (golden charades_csf_ragged_f16)."""
+    import mesm_b200
+    from mesm_b200.model import build_model
+    from tests.helpers import engine_cfg, load_case, rel_err
+    cfg, sd, inp, neg, gold, meta = load_case("charades_csf_ragged_f16")
+    model = build_model(engine_cfg(cfg))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    B, L, Dv = inp["video_feat"].shape
+    h16 = inp["video_feat"].half()
+    assert torch.equal(h16.float(), inp["video_feat"])                    # the fixture's features are fp16-representable
+    f, mm, n = mesm_b200.upload_clips(h16.pin_memory(), inp["video_mask"].pin_memory(), num_clips=inp["num_clips"] if shared else None)
+    torch.cuda.synchronize()
+    assert f.dtype == torch.float16
+    rows = int(inp["video_mask"].sum()) if not shared else int(inp["video_mask"][torch.cumsum(inp["num_clips"], 0) - inp["num_clips"]].sum())
+    assert n == rows * Dv * 2 + B * L
+    if not shared:
+        assert torch.equal(f.cpu(), h16)
+    batch = dict(video_feat=h16.pin_memory(), video_mask=inp["video_mask"].pin_memory(), words_id=inp["words_feat"], words_mask=None,
+                 words_weight=torch.ones(B, inp["words_feat"].shape[1]), num_clips=inp["num_clips"], duration=inp["duration"])
+    mesm_b200.prepare_batch_input(batch, "cuda", non_blocking=True, shared_group_video=shared)
+    assert batch["video_feat"].dtype == torch.float16 and mesm_b200.prepare_batch_input.last_h2d_bytes < B * L * Dv * 2 + 10 ** 6
+    out = model(**batch, dataset_name=cfg.dataset_name, is_training=False, neg_index=neg.cuda())
+    torch.cuda.synchronize()
+    vm = inp["video_mask"]
+    for k in ("pred_logits", "pred_spans", "recon_feat"):
+        assert rel_err(out[k], gold[k]) <= 1e-3, k
+    for k in ("saliency_scores", "neg_saliency_scores"):
+        assert rel_err(out[k], gold[k], vm) <= 1e-3, k
+    assert rel_err(out["projed_video_feat"][:, 0], gold["projed_video_row0"]) <= 1e-3
+    assert model._eng.last_feature_bytes == rows * Dv * 2

@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(mesm_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     l = _lib.lib()                       # dlopen + getattr of every symbol
-    assert l.mesm_abi_version() == 2
+    assert l.mesm_abi_version() == 3
 
 
 def test_no_device_means_loud_failure():
