@@ -402,6 +402,8 @@ def main():
     # ------------------------------------------------------------------ our arm ----------------------------------------
     import mesm_b200
     from mesm_b200 import _lib
+    # host placement before any pinned allocation: this rank's threads and staging buffers on its GPU's NUMA node
+    numa = {"bound": False, "why": "MESM_NO_NUMA_BIND"} if os.environ.get("MESM_NO_NUMA_BIND") else mesm_b200.bind_to_gpu_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -642,7 +644,7 @@ def main():
 
     line = {"metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "layout": layout, "clocks": clk.summary(),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "layout": layout, "numa": numa, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
                     "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest two sub-batches ahead on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}

@@ -5,5 +5,6 @@ Layout: ``csrc/`` CUDA kernels + C ABI (include/mesm_b200.h) -> ``libmesm_b200.s
 """
 from .engine import Engine, decode_nms, temporal_nms_lists, align_scores  # noqa: F401
 from .ingest import prepare_batch_input, upload_clips  # noqa: F401
+from .numa import bind_to_gpu_node  # noqa: F401
 
 __all__ = ["Engine", "decode_nms", "temporal_nms_lists", "align_scores", "prepare_batch_input", "upload_clips"]
