@@ -561,13 +561,17 @@ def main():
     # compute stream's grids, or the copy engine idles until it has run)
     comp, copy = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     shared = (not padded and vlen_host is not None and not os.environ.get("MESM_E2E_NO_SHARED") and dname != "qvhighlights")
-    dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
-    hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
-    hkeep = [torch.empty(Bs, 10, dtype=torch.int32).pin_memory() for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    # NB device buffers: with two, the copy of sub-batch i+2 can only start when the scoring of sub-batch i has finished, so the copy
+    # engine idles whenever a copy is shorter than a scoring period and stalls the GPU whenever it is longer; a third buffer lets the
+    # copy stream run continuously (at N = 8 the host bridges of this box leave some GPUs only ~23 GB/s, profiles/r2_h2d_probe_n8.md)
+    NB = int(os.environ.get("MESM_E2E_BUFFERS", "3"))
+    dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(NB)]
+    hres = [torch.empty(Bs, 10, 3, dtype=torch.float64).pin_memory() for _ in range(NB)]
+    hkeep = [torch.empty(Bs, 10, dtype=torch.int32).pin_memory() for _ in range(NB)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    freed = [torch.cuda.Event() for _ in range(NB)]
     h2d_box = [0]
-    vl_box = [None if vlen_host is None else sb["video_len"]] * 2
+    vl_box = [None if vlen_host is None else sb["video_len"]] * NB
 
     def e2e_stream(total):
         # Host order: scoring of sub-batch i is enqueued first, then the ingest of sub-batch i+2 into the buffer it frees.
@@ -576,46 +580,45 @@ def main():
 
         def prefetch(i):
             with torch.cuda.stream(copy):
-                copy.wait_event(freed[i % 2])                  # the compute that last read this buffer has finished
+                copy.wait_event(freed[i % NB])                  # the compute that last read this buffer has finished
                 if padded:
                     for k, v in host.items():
-                        dbuf[i % 2][k].copy_(v, non_blocking=True)
+                        dbuf[i % NB][k].copy_(v, non_blocking=True)
                     h2d_box[0] = sum(v.numel() * v.element_size() for v in host.values())
                 else:
-                    staged = mesm_b200.prepare_batch_input(dict(host, num_clips=sb["num_clips"]), dev, non_blocking=True, out=dbuf[i % 2],
+                    staged = mesm_b200.prepare_batch_input(dict(host, num_clips=sb["num_clips"]), dev, non_blocking=True, out=dbuf[i % NB],
                                                            shared_group_video=shared)
                     h2d_box[0] = mesm_b200.prepare_batch_input.last_h2d_bytes
-                    vl_box[i % 2] = None if vlen_host is None else staged["video_len"]
-                ready[i % 2].record(copy)
+                    vl_box[i % NB] = None if vlen_host is None else staged["video_len"]
+                ready[i % NB].record(copy)
 
         trace = [] if os.environ.get("MESM_E2E_TRACE") else None
         t_host0 = time.perf_counter()
-        prefetch(0)
-        if total > 1:
-            prefetch(1)
+        for j in range(min(NB, total)):
+            prefetch(j)
         th = th1 = time.perf_counter()
         for i in range(total):
-            d = dbuf[i % 2]
+            d = dbuf[i % NB]
             tf0 = time.perf_counter()
             with torch.cuda.stream(comp):
-                comp.wait_event(ready[i % 2])
+                comp.wait_event(ready[i % NB])
                 o = model(d["video_feat"], d["video_mask"], d["words_feat"], None, None, sb["num_clips"],
-                          dataset_name=dname, is_training=False, neg_index=d["neg_index"], video_len=vl_box[i % 2],
+                          dataset_name=dname, is_training=False, neg_index=d["neg_index"], video_len=vl_box[i % NB],
                           shared_group_video=shared)
                 mesm_b200.align_scores(o["projed_video_feat"], d["clip_mask"], o["expanded_words_feat"], o["expanded_words_mask"], 0.5)
                 w, od, kp, ct = mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], d["duration"], cfg["clip_len"],
                                                      cfg["max_ts_val"], NMS_THD, 10, 10)
                 if wlc["dense_nms"]:
                     mesm_b200.temporal_nms_lists(d["dense_windows"], d["dense_offsets"], NMS_THD, 10)
-                hres[i % 2].copy_(w, non_blocking=True)
-                hkeep[i % 2].copy_(kp, non_blocking=True)
-                freed[i % 2].record(comp)
+                hres[i % NB].copy_(w, non_blocking=True)
+                hkeep[i % NB].copy_(kp, non_blocking=True)
+                freed[i % NB].record(comp)
                 if trace is not None:
                     e = torch.cuda.Event(enable_timing=True); e.record(comp)
                     trace.append((e, tf0 - t_host0, th1 - th, time.perf_counter() - tf0, model._eng.last_enqueue_s))
             th = time.perf_counter()
-            if i + 2 < total:
-                prefetch(i + 2)
+            if i + NB < total:
+                prefetch(i + NB)
             th1 = time.perf_counter()
         comp.synchronize()
         copy.synchronize()
@@ -626,7 +629,7 @@ def main():
                       f"launch enqueue {trace[j][4][1] * 1e3:.2f})", file=sys.stderr)
 
     d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
-    e2e_stream(2 * nsub)             # warm-up: both buffers, the allocator's steady state and the copy path
+    e2e_stream(max(2 * nsub, NB))    # warm-up: every buffer, the allocator's steady state and the copy path
     torch.cuda.synchronize()
     gc.collect()
     if dist:
@@ -646,7 +649,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "layout": layout, "numa": numa, "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
-                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest two sub-batches ahead on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
+                    "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest up to {NB} sub-batches ahead ({NB} device buffers) on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
