@@ -179,29 +179,45 @@ int fail(mesm_ctx* c, int code, const std::string& msg) {
 // FFN block of a layer: out = LN2(res + W2 PReLU(W1 x + b1) + b2).  One fused tcgen05 kernel when the shape allows
 // (MESM_FFN_FUSED=0 keeps the two-GEMM path, which also serves small row counts).
 cudaError_t ffn_block(const AttnFfn& L, int R, const float* x, const float* res, float* H, float* out, int ldo, RowMap omap,
-                      cudaStream_t s) {
+                      cudaStream_t s, Planes xp = Planes(), Planes outp = Planes()) {
     static int fused = -1;
     if (fused < 0) { const char* e = getenv("MESM_FFN_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
     FfnArgs a;
     a.X = x; a.ldx = D; a.R = res; a.ldr = D; a.out = out; a.ldo = ldo; a.omap = omap; a.M = R;
     a.W1f = L.ffn_w1; a.W2f = L.ffn_w2; a.maps = L.ffn_maps; a.b1 = L.l1.bias; a.b2 = L.l2.bias; a.ln_g = L.n2.g; a.ln_b = L.n2.b; a.prelu = L.prelu;
+    a.x_hi = xp.hi; a.x_lo = xp.lo; a.out_hi = outp.hi; a.out_lo = outp.lo;
     if (fused && ffn_fused_eligible(a)) {
         ProfScope _ps("ffn_fused", s, 4.0 * R * (double)D * FF, R);
         return launch_ffn_fused(a, s);
     }
+    if (xp || outp) return cudaErrorInvalidValue;              // the plane flow is only set up where the fused kernel runs
     MESM_CHECK(Lin(R, L.l1, x, D, H, FF).act(ACT_PRELU, L.prelu).run(s));
     MESM_CHECK(Lin(R, L.l2, H, FF, out, ldo).omap(omap).res(res, D).ln(L.n2).run(s));
     return cudaSuccess;
+}
+
+// A/B switches of the plane flow (developer): MESM_FFN_X=f32 keeps the FFN's X operand fp32 (converted in the kernel),
+// MESM_FFN_OUTP=0 stops the FFN from storing its result as planes (the next layer then falls back to fp32 operands)
+static bool ffn_x_f32() { static int v = -1; if (v < 0) { const char* e = getenv("MESM_FFN_X"); v = (e && e[0] == 'f') ? 1 : 0; } return v == 1; }
+static bool ffn_outp_off() { static int v = -1; if (v < 0) { const char* e = getenv("MESM_FFN_OUTP"); v = (e && e[0] == '0') ? 1 : 0; } return v == 1; }
+
+// the plane flow needs the fused FFN (M > 128 rows), its weight images and the TMA weight planes of the layer
+static bool planes_ok(const AttnFfn& L, int R, const PlaneIO* pio) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MESM_PLANES"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on && pio && pio->ao && pio->y1 && R > 128 && L.ffn_maps && L.out.Wtm && L.q.Wtm && L.qk.Wtm && L.v.Wtm;
 }
 
 // T2V layer (model/transformer.py:508-540).  txt rows: [Bc*Lk] through tmap; vid rows [Bc*Lq] contiguous.
 cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const float* pos_txt, int Lk, const float* vid,
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
                       const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q, const int* cu,
-                      int Rv_packed, int q_pad_ld, const float* posW, const int* t_pos) {
+                      int Rv_packed, int q_pad_ld, const float* posW, const int* t_pos, PlaneIO* pio) {
     const int Rt = Bc * Lk, Rv = cu ? Rv_packed : Bc * Lq;
+    const bool pl = planes_ok(L, Rv, pio) && ldo == D;
+    if (pio) pio->wrote_out = pl && pio->out;
     if (pos_txt) {
-        PL kw = L.kv; kw.N = D;
+        PL kw = L.kv; kw.N = D; kw.Wtm = nullptr;
         MESM_CHECK(Lin(Rt, kw, txt, D, t.KV, 2 * D).amap(tmap).apos(pos_txt).run(s));
         PL vw = L.v;
         MESM_CHECK(Lin(Rt, vw, txt, D, t.KV + D, 2 * D).amap(tmap).run(s));
@@ -211,6 +227,7 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     if (!reuse_q) {                                                                     // Q depends on the clips only
         Lin q(Rv, L.q, vid, D, t.Q, D);
         if (posW) q.res(posW, D, table_map(t_pos)); else q.apos(pos_vid);             // (x + pos) Wq = x Wq + (pos Wq)[table]
+        if (pl && pio->in && posW) q.aplanes(pio->in.hi, pio->in.lo, D);              // input already pre-split: TMA-fed kernel
         MESM_CHECK(q.run(s));
     }
     MhaRowsArgs a;
@@ -218,7 +235,17 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     a.k_pad = k_pad; a.q_pad = q_pad; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = Lq; a.Lk = Lk; a.b0 = b0; a.Btot = Btot;
     a.q_scale = kScale32;
     a.q_cu = cu; a.q_enc = 0; a.q_pad_ld = q_pad_ld;         // packed clips: pair b's queries are rows cu[b]-cu[0] ...
+    if (pl) { a.out = nullptr; a.out_hi = pio->ao.hi; a.out_lo = pio->ao.lo; }      // attention output straight into operand planes
     MESM_CHECK(launch_mha_rows(a, s));
+    if (pl) {
+        // out-proj (+ residual, pre-LN copy, LN1) on the TMA-fed kernel; LN1's result only exists as the FFN's operand planes
+        const bool xf = ffn_x_f32();
+        MESM_CHECK(Lin(Rv, L.out, nullptr, D, xf ? t.Y1 : nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(vid, D).pre_ln(t.X1).ln(L.n1)
+                       .oplanes(xf ? nullptr : pio->y1.hi, xf ? nullptr : pio->y1.lo, D).run(s));
+        if (ffn_outp_off()) pio->wrote_out = false;
+        MESM_CHECK(ffn_block(L, Rv, xf ? t.Y1 : nullptr, t.X1, t.H, out, ldo, omap, s, xf ? Planes() : pio->y1, pio->wrote_out ? pio->out : Planes()));
+        return cudaSuccess;
+    }
     MESM_CHECK(Lin(Rv, L.out, t.AO, D, t.Y1, D).res(vid, D).pre_ln(t.X1).ln(L.n1).run(s));
     MESM_CHECK(ffn_block(L, Rv, t.Y1, t.X1, t.H, out, ldo, omap, s));
     return cudaSuccess;
@@ -227,20 +254,37 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
 // Encoder layer (model/transformer.py:637-650) on the [Bc, L1, 256] buffer (L1 = Lv + 1, global token first).
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
                       const EncBuffers& t, float* out, cudaStream_t s, const int* cu, int R_packed, const float* posW,
-                      const int* t_pos) {
+                      const int* t_pos, PlaneIO* pio) {
     const int R = cu ? R_packed : Bc * L1;
+    const bool pl = planes_ok(L, R, pio) && pio->in && posW;
+    if (pio) pio->wrote_out = pl && pio->out;
     {
         Lin qk(R, L.qk, src, D, t.QKV, 3 * D);
         if (posW) qk.res(posW, 2 * D, table_map(t_pos)); else qk.apos(pos);
+        if (pl) qk.aplanes(pio->in.hi, pio->in.lo, D);
         MESM_CHECK(qk.run(s));
     }
-    MESM_CHECK(Lin(R, L.v, src, D, t.QKV + 2 * D, 3 * D).run(s));
+    {
+        Lin v(R, L.v, src, D, t.QKV + 2 * D, 3 * D);
+        if (pl) v.aplanes(pio->in.hi, pio->in.lo, D);
+        MESM_CHECK(v.run(s));
+    }
     MhaRowsArgs a;
     a.q = t.QKV; a.ldq = 3 * D; a.k = t.QKV + D; a.ldk = 3 * D; a.v = t.QKV + 2 * D; a.ldv = 3 * D;
     a.k_pad = pad; a.q_pad = nullptr; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = L1; a.Lk = L1; a.b0 = 0; a.Btot = Bc;
     a.q_scale = kScale32;
     a.q_cu = cu; a.q_enc = 1; a.k_cu = cu; a.k_enc = 1;      // packed encoder rows (global token + this pair's clips)
+    if (pl) { a.out = nullptr; a.out_hi = pio->ao.hi; a.out_lo = pio->ao.lo; }
     MESM_CHECK(launch_mha_rows(a, s));
+    if (pl) {
+        // LN1's result is both the FFN's operand (planes) and its residual (fp32)
+        const bool xf = ffn_x_f32();
+        MESM_CHECK(Lin(R, L.out, nullptr, D, t.Y1, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(src, D).ln(L.n1)
+                       .oplanes(xf ? nullptr : pio->y1.hi, xf ? nullptr : pio->y1.lo, D).run(s));
+        if (ffn_outp_off()) pio->wrote_out = false;
+        MESM_CHECK(ffn_block(L, R, xf ? t.Y1 : nullptr, t.Y1, t.H, out, D, identity_map(), s, xf ? Planes() : pio->y1, pio->wrote_out ? pio->out : Planes()));
+        return cudaSuccess;
+    }
     MESM_CHECK(Lin(R, L.out, t.AO, D, t.Y1, D).res(src, D).ln(L.n1).run(s));
     MESM_CHECK(ffn_block(L, R, t.Y1, t.Y1, t.H, out, D, identity_map(), s));
     return cudaSuccess;
@@ -264,7 +308,7 @@ cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, 
                         const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
                         long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
                         long long refs_layer_stride, cudaStream_t s, const int* cu, int Re_packed, const float* const* posWkp,
-                        const int* t_posE) {
+                        const int* t_posE, Planes Ep) {
     const int nq = c->cfg.num_queries, nl = c->cfg.dec_layers, L1 = Lv + 1;
     const int R = Bc * nq, Re = cu ? Re_packed : Bc * L1;
     MESM_CHECK(launch_fill(d.tgtA, (long long)R * D, 0.f, s));                         // tgt = 0 (transformer.py:201)
@@ -299,14 +343,25 @@ cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, 
         // cross-attention into the encoder memory
         if (lid == 0) {
             MESM_CHECK(Lin(R, L.ca_qc, d.t1, D, d.qca, D).second(d.qpos, D, L.ca_qp).bias(L.ca_q_bias0).run(s));
-            if (posWkp) MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).res(posWkp[0], D, table_map(t_posE)).run(s));   // k_content + k_pos
+            if (posWkp) {                                                                  // k_content + k_pos
+                Lin kc(Re, L.ca_kc, E, D, d.Kc, D);
+                kc.res(posWkp[0], D, table_map(t_posE));
+                if (Ep && L.ca_kc.Wtm) kc.aplanes(Ep.hi, Ep.lo, D);
+                MESM_CHECK(kc.run(s));
+            }
             else MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).second(posE, D, L.ca_kp).bias(L.ca_k_bias0).run(s));
         } else {
             MESM_CHECK(Lin(R, L.ca_qc, d.t1, D, d.qca, D).run(s));
-            MESM_CHECK(Lin(Re, L.ca_kc, E, D, d.Kc, D).run(s));
+            Lin kc(Re, L.ca_kc, E, D, d.Kc, D);
+            if (Ep && L.ca_kc.Wtm) kc.aplanes(Ep.hi, Ep.lo, D);
+            MESM_CHECK(kc.run(s));
         }
         if (!posWkp) MESM_CHECK(Lin(Re, L.ca_kp, posE, D, d.Kp, D).run(s));          // else: rows of the position table product
-        MESM_CHECK(Lin(Re, L.ca_v, E, D, d.Vd, D).run(s));
+        {
+            Lin cv(Re, L.ca_v, E, D, d.Vd, D);
+            if (Ep && L.ca_v.Wtm) cv.aplanes(Ep.hi, Ep.lo, D);
+            MESM_CHECK(cv.run(s));
+        }
         MESM_CHECK(Lin(R, L.ca_sine, d.sine_s, D, d.sinep, D).run(s));
         a.q = d.qca; a.q2 = d.sinep; a.ldq2 = D; a.k = d.Kc; a.k2 = posWkp ? posWkp[lid] : d.Kp; a.ldk2 = D; a.v = d.Vd; a.k_pad = padV;
         a.k2_table = posWkp ? t_posE : nullptr;
@@ -620,6 +675,7 @@ struct FwdPlan {
     DecBuffers dec;
     float *rS, *rS2, *rq, *rqk, *rpool, *rao, *rX1, *rY1, *rH, *rtmp;
     float *PT, *PWq, *PWqk, *PWkp;
+    Planes xaP, xbP, enhP, EP, E2P, aoP, y1P;            // pre-split activations of the chunk (PlaneIO, ctx.h)
     size_t total = 0;
 };
 
@@ -651,6 +707,7 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.xa = ar.get<float>(Rv * D); p.xb = ar.get<float>(Rv * D); p.enh = ar.get<float>(Rv * D); p.Qenh0 = ar.get<float>(Rv * D);
     p.E = ar.get<float>(Re * D); p.E2 = ar.get<float>(Re * D); p.P1 = ar.get<float>(Re * D); p.P2 = ar.get<float>((size_t)Bc * D);
     p.padV = ar.get<uint8_t>(Rv); p.padE = ar.get<uint8_t>(Re);
+    for (Planes* pp : {&p.xaP, &p.xbP, &p.enhP, &p.EP, &p.E2P, &p.aoP, &p.y1P}) { pp->hi = ar.get<uint16_t>(Re * D); pp->lo = ar.get<uint16_t>(Re * D); }
     p.t2v.KV = ar.get<float>(Rk * 2 * D); p.t2v.Q = ar.get<float>(Re * D); p.t2v.AO = ar.get<float>(Re * D);
     p.t2v.X1 = ar.get<float>(Re * D); p.t2v.Y1 = ar.get<float>(Re * D); p.t2v.H = ar.get<float>(Re * FF);
     p.encb.QKV = ar.get<float>(Re * 3 * D); p.encb.AO = p.t2v.AO; p.encb.Y1 = p.t2v.Y1; p.encb.H = p.t2v.H;
@@ -913,6 +970,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         if (packed && !neg) CK(launch_chunk_tables(cu, Bc, p.t_c2e, p.t_g, s, ptab ? d_lenoff : nullptr, p.t_posV, p.t_posE));
         PosArgs pa; pa.vmask = vmask; pa.B = Bc; pa.Lv = Lv; pa.gtok = ctx->gtok; pa.gpos = ctx->gpos; pa.cu = cu;
         pa.posV = p.posV; pa.posE = p.posE; pa.encbuf = p.E; pa.padV = p.padV; pa.padE = p.padE;
+        pa.enc_hi = p.EP.hi; pa.enc_lo = p.EP.lo;
         if (ptab) { pa.posV = nullptr; pa.posE = nullptr; }                                        // positions come from the table
         if (neg) { pa.posV = nullptr; pa.posE = nullptr; pa.padV = nullptr; pa.padE = nullptr; }   // positions / pads kept from the main pass
         CK(launch_pos_embed(pa, s));
@@ -923,13 +981,18 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         const float* x = projV;
         float* enh_out = (!neg && out->enhanced_video_feat) ? out->enhanced_video_feat + (size_t)b0 * Lv * D : nullptr;
         float* enh = (enh_out && !packed) ? enh_out : p.enh;
+        Planes xP;                                      // planes of `x` (empty: the producer of x wrote fp32 only)
         for (size_t l = 0; l < ctx->enh.size(); ++l) {
-            float* dst = (l + 1 == ctx->enh.size()) ? enh : (l % 2 == 0 ? p.xa : p.xb);
+            const bool lastl = (l + 1 == ctx->enh.size());
+            float* dst = lastl ? enh : (l % 2 == 0 ? p.xa : p.xb);
+            PlaneIO pio;
+            pio.in = xP; pio.out = lastl ? p.enhP : (l % 2 == 0 ? p.xaP : p.xbP); pio.ao = p.aoP; pio.y1 = p.y1P;
             T2VBuffers tb = p.t2v;
             if (l == 0) tb.Q = p.Qenh0;                 // layer 0's Q = (projV + pos) Wq is identical in the negative pass
             CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, tb,
-                         dst, D, identity_map(), s, l == 0 && neg, cu, Rv, Lv, PWq_enh[l], p.t_posV));
+                         dst, D, identity_map(), s, l == 0 && neg, cu, Rv, Lv, PWq_enh[l], p.t_posV, &pio));
             x = dst;
+            xP = pio.wrote_out ? pio.out : Planes();
         }
         if (ctx->enh.empty() && enh_out && !packed)
             CK(cudaMemcpyAsync(enh, projV, (size_t)Rv * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -940,25 +1003,39 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         }
         // ---- aligner (model/model.py:230-234; neg: 290-294): keys = recon token + words; last layer writes the
         //      encoder buffer [Bc, Lv+1, 256] behind the global token ----
+        Planes xinP = ctx->enh.empty() ? Planes() : xP;
         for (size_t l = 0; l < ctx->aln.size(); ++l) {
             const bool last = (l + 1 == ctx->aln.size());
             float* dst = last ? p.E : (l % 2 == 0 ? p.xa : p.xb);
+            PlaneIO pio;
+            pio.in = xinP; pio.out = last ? p.EP : (l % 2 == 0 ? p.xaP : p.xbP); pio.ao = p.aoP; pio.y1 = p.y1P;
             CK(t2v_layer(ctx->aln[l], words_c, identity_map(), nullptr, Lk, xin, p.posV, Lv, Bc, b0, B, p.padV_all, epad_all,
-                         p.t2v, dst, D, last ? c2e : identity_map(), s, false, cu, Rv, Lv, PWq_aln[l], p.t_posV));
+                         p.t2v, dst, D, last ? c2e : identity_map(), s, false, cu, Rv, Lv, PWq_aln[l], p.t_posV, &pio));
             xin = dst;
+            xinP = pio.wrote_out ? pio.out : Planes();
         }
+        Planes EcurP = ctx->aln.empty() ? Planes() : xinP, EnextP = p.E2P;      // planes of the encoder buffer (empty: fp32 only)
         if (ctx->aln.empty())
             CK(launch_copy_rows(xin, D, identity_map(), p.E, D, c2e, Rv, s));
         // ---- transformer encoder (model/transformer.py:185-197) ----
         float* Ecur = p.E; float* Enext = p.E2;
         for (size_t l = 0; l < ctx->enc.size(); ++l) {
-            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re, PWqk[l], p.t_posE));
+            PlaneIO pio;
+            pio.in = EcurP; pio.out = EnextP; pio.ao = p.aoP; pio.y1 = p.y1P;
+            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re, PWqk[l], p.t_posE, &pio));
             std::swap(Ecur, Enext);
+            const Planes done = pio.wrote_out ? pio.out : Planes();
+            EnextP = (pio.out.hi == p.E2P.hi) ? p.EP : p.E2P;
+            EcurP = done;
         }
         // ---- saliency head (model/model.py:301-302) ----
         float* sal = neg ? out->neg_saliency_scores : out->saliency_scores;
         if (sal) {
-            CK(Lin(Re, ctx->sal1, Ecur, D, p.P1, D).run(s));
+            {
+                Lin s1(Re, ctx->sal1, Ecur, D, p.P1, D);
+                if (EcurP && ctx->sal1.Wtm) s1.aplanes(EcurP.hi, EcurP.lo, D);
+                CK(s1.run(s));
+            }
             if (packed) {
                 CK(Lin(Bc, ctx->sal2, Ecur, D, p.P2, D).amap(table_map(p.t_g)).run(s));
                 CK(launch_saliency_packed(p.P1, cu, p.P2, Bc, Lv, sal + (size_t)b0 * Lv, s));
@@ -986,7 +1063,7 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
                                         out->aux_logits ? out->aux_logits + (size_t)b0 * nq * 2 : nullptr,
                                         out->aux_spans ? out->aux_spans + (size_t)b0 * nq * 2 : nullptr, (long long)B * nq * 2,
                                         out->hs ? out->hs + (size_t)b0 * nq * D : nullptr, (long long)B * nq * D, nullptr, 0, s,
-                                        cu, Re, ptab ? PWkp.data() : nullptr, p.t_posE);
+                                        cu, Re, ptab ? PWkp.data() : nullptr, p.t_posE, EcurP);
             CK(e);
         }
         return 0;

@@ -8,6 +8,7 @@
 //   recon_pool        SS-MESM single-query attention evaluated on the *unprojected* clip rows
 //                     (scores = (Wk_h^T q_h) . x_k, output = Wv_h (sum_k p_k x_k) + b): no K/V projection of the clips.
 #include "kernels.h"
+#include "tc_common.cuh"
 #include <math_constants.h>
 #include <cstdlib>
 
@@ -112,9 +113,24 @@ __global__ void __launch_bounds__(MR_ROWS, 5) mha_rows_kernel(const MhaRowsArgs 
         }
     }
     const float inv = 1.f / l;                 // l == 0 (all keys masked) -> inf*0 = NaN like the reference
-    float4* op = reinterpret_cast<float4*>(a.out + qrow * a.ldo + h * 32);
+    if (a.out) {
+        float4* op = reinterpret_cast<float4*>(a.out + qrow * a.ldo + h * 32);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) op[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+    }
+    if (a.out_hi) {                            // pre-split planes for the output projection (row pitch 256 elements)
+        uint4* ph = reinterpret_cast<uint4*>(a.out_hi + qrow * D + h * 32);
+        uint4* pl = reinterpret_cast<uint4*>(a.out_lo + qrow * D + h * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 hh, ll;
+            tc::split_bf16x2(o[8 * j] * inv, o[8 * j + 1] * inv, hh.x, ll.x);
+            tc::split_bf16x2(o[8 * j + 2] * inv, o[8 * j + 3] * inv, hh.y, ll.y);
+            tc::split_bf16x2(o[8 * j + 4] * inv, o[8 * j + 5] * inv, hh.z, ll.z);
+            tc::split_bf16x2(o[8 * j + 6] * inv, o[8 * j + 7] * inv, hh.w, ll.w);
+            ph[j] = hh; pl[j] = ll;
+        }
+    }
 }
 
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_simt) {

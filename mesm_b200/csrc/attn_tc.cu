@@ -270,9 +270,17 @@ uint32_t vh2[2], vl2[2];
                 for (int i = 0; i < 8; ++i) {
                     const int r = 4 * i + rsub;
                     const int qo = tile * 128 + q4 * 32 + r;
-                    if (qo < Lq)
-                        *reinterpret_cast<float4*>(a.out + (qbase + qo) * a.ldo + h * 32 + c4) =
-                            *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+                    if (qo < Lq) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+                        if (a.out) *reinterpret_cast<float4*>(a.out + (qbase + qo) * a.ldo + h * 32 + c4) = t4;
+                        if (a.out_hi) {
+                            uint2 hh, ll;
+                            split_bf16x2(t4.x, t4.y, hh.x, ll.x);
+                            split_bf16x2(t4.z, t4.w, hh.y, ll.y);
+                            *reinterpret_cast<uint2*>(a.out_hi + (qbase + qo) * D + h * 32 + c4) = hh;
+                            *reinterpret_cast<uint2*>(a.out_lo + (qbase + qo) * D + h * 32 + c4) = ll;
+                        }
+                    }
                 }
             }
         }
@@ -614,9 +622,17 @@ __global__ void __launch_bounds__(ATP_THREADS, 1) attn_tcp_kernel(const MhaRowsA
                     for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + rsub;
                         const int qo = wt * 128 + q4 * 32 + r;
-                        if (qo < Lq)
-                            *reinterpret_cast<float4*>(a.out + (qbase + qo) * a.ldo + h * 32 + c4) =
-                                *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+                        if (qo < Lq) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(&T[r * 36 + c4]);
+                            if (a.out) *reinterpret_cast<float4*>(a.out + (qbase + qo) * a.ldo + h * 32 + c4) = t4;
+                            if (a.out_hi) {
+                                uint2 hh, ll;
+                                split_bf16x2(t4.x, t4.y, hh.x, ll.x);
+                                split_bf16x2(t4.z, t4.w, hh.y, ll.y);
+                                *reinterpret_cast<uint2*>(a.out_hi + (qbase + qo) * D + h * 32 + c4) = hh;
+                                *reinterpret_cast<uint2*>(a.out_lo + (qbase + qo) * D + h * 32 + c4) = ll;
+                            }
+                        }
                     }
                     __syncwarp();                    // scratch is rewritten by the next head's epilogue
                 }
@@ -652,7 +668,7 @@ bool attn_tc_eligible(const MhaRowsArgs& a) {
     // gain; measured 13.9 ms vs 9.5 ms per bench step for the fp32 thread-per-row kernel
     if (a.Lk <= 64) return false;
     auto al = [](const float* p, int ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); };
-    return al(a.q, a.ldq) && al(a.k, a.ldk) && al(a.v, a.ldv) && al(a.out, a.ldo);
+    return al(a.q, a.ldq) && al(a.k, a.ldk) && al(a.v, a.ldv) && (a.out ? al(a.out, a.ldo) : a.out_hi != nullptr);
 }
 
 cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s) {

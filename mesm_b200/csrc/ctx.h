@@ -152,6 +152,12 @@ struct Lin {    // thin builder around LinearOp
 constexpr float kScale32 = 0.17677669529663687f;   // 32^-0.5
 constexpr float kScale64 = 0.125f;                 // 64^-0.5
 
+// Pre-split activations (bf16 hi / lo planes, [rows, 256], pitch 256) around one layer call: the layer input as planes (A operand of
+// its Q / QK / V projections on linear_tma.cu), where to store its output as planes (same row mapping as the fp32 output), and the two
+// plane scratch buffers every layer needs (attention output, LayerNorm-1 output).  Empty members fall back to the fp32 operands.
+struct Planes { uint16_t* hi = nullptr; uint16_t* lo = nullptr; explicit operator bool() const { return hi != nullptr; } };
+struct PlaneIO { Planes in, out, ao, y1; bool wrote_out = false; /* set by the layer: `out` now holds its result */ };
+
 struct T2VBuffers { float *KV, *Q, *AO, *X1, *Y1, *H; };
 struct EncBuffers { float *QKV, *AO, *Y1, *H; };
 struct DecBuffers {
@@ -163,13 +169,13 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
                       const float* pos_vid, int Lq, int Bc, int b0, int Btot, const uint8_t* q_pad, const uint8_t* k_pad,
                       const T2VBuffers& t, float* out, int ldo, RowMap omap, cudaStream_t s, bool reuse_q = false,
                       const int* cu = nullptr, int Rv_packed = 0, int q_pad_ld = 0, const float* posW = nullptr,
-                      const int* t_pos = nullptr);
+                      const int* t_pos = nullptr, PlaneIO* pio = nullptr);
 // posW / t_pos: the position term of a projection as a gathered residual - row r of the GEMM adds posW[t_pos[r]], where
 // posW = (position table) . W^T was computed once per distinct (clip count, clip index); replaces the (x + pos) K-sweep
 // cu != nullptr (device, first pair of the chunk): packed variable-length rows, see pair_rows() in common.cuh
 cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, const uint8_t* pad, int L1, int Bc,
                       const EncBuffers& t, float* out, cudaStream_t s, const int* cu = nullptr, int R_packed = 0,
-                      const float* posW = nullptr, const int* t_pos = nullptr);
+                      const float* posW = nullptr, const int* t_pos = nullptr, PlaneIO* pio = nullptr);
 size_t dec_alloc(Arena& ar, DecBuffers& d, int Bc, int nq, int L1, int nl);
 cudaError_t launch_colsum(const float* Wt, int Kp, int ldw, int N, float* out, cudaStream_t s);
 cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, float* Wt, int ldw, int Kp, cudaStream_t s);
@@ -177,6 +183,6 @@ cudaError_t run_decoder(const mesm_ctx* c, const float* qembed, const float* E, 
                         const DecBuffers& d, float* logits_out, float* spans_out, float* aux_logits, float* aux_spans,
                         long long aux_layer_stride, float* hs_out, long long hs_layer_stride, float* refs_out,
                         long long refs_layer_stride, cudaStream_t s, const int* cu = nullptr, int Re_packed = 0,
-                        const float* const* posWkp = nullptr, const int* t_posE = nullptr);
+                        const float* const* posWkp = nullptr, const int* t_posE = nullptr, Planes Ep = Planes());
 
 }  // namespace mesm

@@ -1,6 +1,7 @@
 // Row-wise / element-wise kernels of the MESM path (all HBM- or latency-bound; vectorised, coalesced, one warp per row
 // where a row reduction is needed).
 #include "kernels.h"
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -86,6 +87,12 @@ __global__ void __launch_bounds__(256) pos_embed_kernel(const PosArgs a) {
     long long vrow0; int Lv;                                   // this pair's clip rows in the (possibly packed) buffers
     pair_rows(a.cu, 0, b, a.Lv, vrow0, Lv);
     const long long erow0 = vrow0 + b;                         // its encoder rows: global token first (uniform: b * (Lv + 1))
+    if (a.enc_hi && threadIdx.x < D) {                         // the global token also as bf16 hi / lo planes of the encoder buffer
+        const float g = a.gtok[threadIdx.x];
+        const __nv_bfloat16 h = __float2bfloat16_rn(g);
+        a.enc_hi[erow0 * D + threadIdx.x] = __bfloat16_as_ushort(h);
+        a.enc_lo[erow0 * D + threadIdx.x] = __bfloat16_as_ushort(__float2bfloat16_rn(g - __bfloat162float(h)));
+    }
     if (!a.posV && !a.posE && !a.padV && !a.padE) {          // only the global token row of the encoder buffer
         if (a.encbuf) a.encbuf[erow0 * D + threadIdx.x] = a.gtok[threadIdx.x];
         return;

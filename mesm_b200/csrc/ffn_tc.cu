@@ -19,6 +19,7 @@
 //   E1, then the final epilogue (+b2, +R, LayerNorm, coalesced stores through shared memory).
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "tma_host.h"
 #include <cstdlib>
 #include <cuda.h>
 
@@ -54,6 +55,9 @@ struct FfnOp {
     int M;
     const uint8_t* W1f; const uint8_t* W2f;
     CUtensorMap tm1, tm2;                    // the packed weight images as [rows of 128 B] tensors: one 16 KB slot = a 128 x 128 B box
+    CUtensorMap tmXh, tmXl;                  // X as pre-split bf16 hi / lo planes [M, 256] (box 32 x 128, SWIZZLE_64B); used when x_planes
+    int x_planes;                            // 1: X arrives through the TMA engine, no conversion in the kernel
+    uint16_t* out_hi; uint16_t* out_lo;      // optional: the result also as planes, same row mapping and pitch as `out` (ldo == 256)
     const float* b1; const float* b2; const float* ln_g; const float* ln_b; const float* prelu;
     int dbg;                                 // probe only: bit 0 skips the G1 MMAs, bit 1 the G2 MMAs (timing experiments)
 };
@@ -74,6 +78,10 @@ __device__ __forceinline__ void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint6
 __device__ __forceinline__ void tma_load_slot(uint32_t dst, const CUtensorMap* tm, int row, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_peer + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }   // full: one arrival per CTA, both in the leader
-        for (int k = 0; k < 8; ++k) mbar_init(bar_xfull + 8 * k, 16);          // 8 converter warps of each CTA (used in the leader)
+        for (int k = 0; k < 8; ++k) mbar_init(bar_xfull + 8 * k, op.x_planes ? 2 : 16);   // the TMA producer / the 8 converter warps of each CTA (used in the leader)
         mbar_init(bar_hacc_full, 1); mbar_init(bar_hbf_free, 1); mbar_init(bar_yfull, 1);
         mbar_init(bar_hacc_free, 16); mbar_init(bar_hbf_full, 16);             // the E1 warps of both CTAs (used in the leader)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -131,6 +139,16 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
         if (lane == 0) {
             int g = 0;
             const uint32_t full_leader = map_to_cta(bar_full, 0);
+            if (op.x_planes) {
+                // X: 8 K blocks x (hi | lo) = sixteen 8 KB boxes straight into the resident operand image; both CTAs of the pair
+                // complete their halves on the LEADER's barrier of the block (rows past M are zero-filled by the TMA engine)
+                const uint32_t xfull_leader = map_to_cta(bar_xfull, 0);
+                for (int kb = 0; kb < 8; ++kb) {
+                    mbar_arrive_expect_tx_remote(xfull_leader + 8 * kb, XBLK);
+                    tma_load_x(sbase + kb * XBLK, &op.tmXh, kb * 32, m0, xfull_leader + 8 * kb);
+                    tma_load_x(sbase + kb * XBLK + 8192, &op.tmXl, kb * 32, m0, xfull_leader + 8 * kb);
+                }
+            }
             for (int e = 0; e < 2 * NCH; ++e) {
                 bool g2; int j;
                 segment(e, g2, j);
@@ -247,7 +265,8 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
             }
         }
         // ---- X: fp32 rows -> bf16 hi/lo, K-major SWIZZLE_64B blocks of 32 columns, resident for the whole tile ----
-        {
+        //      (skipped when the producer of X stored it pre-split: warp 0 then loads the planes with the TMA engine)
+        if (!op.x_planes) {
             const int cv = tcid & 7, r0 = tcid >> 3;        // 8 threads per row, 32 rows per pass, 4 passes
             const int sbyte0 = sw64(r0, cv * 4);
             const uint32_t xfull_leader = map_to_cta(bar_xfull, 0);
@@ -360,7 +379,15 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const long long o = rowoff[trow0 + 4 * i + rsub];
-                    if (o >= 0) *reinterpret_cast<float4*>(op.out + o + nn) = x[i];
+                    if (o < 0) continue;
+                    if (op.out) *reinterpret_cast<float4*>(op.out + o + nn) = x[i];
+                    if (op.out_hi) {
+                        uint2 hh, ll;
+                        split_bf16x2(x[i].x, x[i].y, hh.x, ll.x);
+                        split_bf16x2(x[i].z, x[i].w, hh.y, ll.y);
+                        *reinterpret_cast<uint2*>(op.out_hi + o + nn) = hh;
+                        *reinterpret_cast<uint2*>(op.out_lo + o + nn) = ll;
+                    }
                 }
             }
         };
@@ -486,22 +513,8 @@ cudaError_t launch_pack_ffn(const float* W1, const float* W2, void* W1f, void* W
 }
 
 namespace {
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {          // resolved through the runtime: the library does not link libcuda
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
 bool make_slot_map(CUtensorMap* tm, const void* base, size_t bytes) {
-    EncodeTiledFn enc = encode_tiled();
+    EncodeTiledFn enc = tma_encode_fn();
     if (!enc) return false;
     const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 128)};
     const cuuint64_t gstr[1] = {128};
@@ -524,7 +537,10 @@ bool ffn_fused_eligible(const FfnArgs& a) {
     if (!a.maps) return false;
     if (!a.W1f || !a.W2f || a.M <= ffn::BM) return false;
     auto al16 = [](const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); };
-    return al16(a.X, a.ldx) && al16(a.R, a.ldr) && al16(a.out, a.ldo) && a.b1 && a.b2 && a.ln_g && a.ln_b && a.prelu;
+    if (a.x_hi ? !a.x_lo : !a.X) return false;
+    if (a.out_hi && (a.ldo != ffn::DM || !a.out_lo)) return false;        // planes share the row offsets of `out`
+    if (!a.out && !a.out_hi) return false;
+    return (a.x_hi || al16(a.X, a.ldx)) && al16(a.R, a.ldr) && (!a.out || al16(a.out, a.ldo)) && a.b1 && a.b2 && a.ln_g && a.ln_b && a.prelu;
 }
 
 cudaError_t launch_ffn_fused(const FfnArgs& a, cudaStream_t s) {
@@ -538,6 +554,15 @@ cudaError_t launch_ffn_fused(const FfnArgs& a, cudaStream_t s) {
     op.W1f = (const uint8_t*)a.W1f; op.W2f = (const uint8_t*)a.W2f;
     op.tm1 = static_cast<const CUtensorMap*>(a.maps)[0]; op.tm2 = static_cast<const CUtensorMap*>(a.maps)[1];
     op.b1 = a.b1; op.b2 = a.b2; op.ln_g = a.ln_g; op.ln_b = a.ln_b; op.prelu = a.prelu;
+    op.out_hi = a.out_hi; op.out_lo = a.out_lo;
+    op.x_planes = a.x_hi != nullptr;
+    if (op.x_planes) {
+        if (!tma_map_2d_16bit(&op.tmXh, a.x_hi, ffn::DM, (unsigned long long)a.M, ffn::DM * 2, 32, ffn::BM, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tma_map_2d_16bit(&op.tmXl, a.x_lo, ffn::DM, (unsigned long long)a.M, ffn::DM * 2, 32, ffn::BM, CU_TENSOR_MAP_SWIZZLE_64B))
+            return cudaErrorInvalidValue;
+    } else {
+        op.tmXh = op.tm1; op.tmXl = op.tm1;
+    }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MESM_FFN_DBG"); dbg = e ? atoi(e) : 0; } op.dbg = dbg; }
     const unsigned mt = (unsigned)((a.M + ffn::BM - 1) / ffn::BM);
     cudaLaunchConfig_t cfg = {};

@@ -19,6 +19,8 @@ struct MhaRowsArgs {
     const int* q_cu = nullptr; int q_enc = 0;
     const int* k_cu = nullptr; int k_enc = 0;
     int q_pad_ld = 0;          // 0 = Lq
+    // optional: the result as bf16 hi / lo planes [rows, 256] (the A operand of the output projection on linear_tma.cu); `out` may then be null
+    uint16_t* out_hi = nullptr; uint16_t* out_lo = nullptr;
 };
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_simt = false);      // dispatcher: tcgen05 kernel when eligible
 bool attn_tc_eligible(const MhaRowsArgs& a);
@@ -62,6 +64,7 @@ struct PosArgs {
     const float* gtok; const float* gpos;
     float* posV; float* posE; float* encbuf; uint8_t* padV; uint8_t* padE;
     const int* cu = nullptr;        // packed layout (pair_rows): clip rows at cu[b]-cu[0], encoder rows at cu[b]-cu[0]+b
+    uint16_t* enc_hi = nullptr; uint16_t* enc_lo = nullptr;     // optional planes of encbuf: the global-token row is written there too
 };
 cudaError_t launch_pos_embed(const PosArgs& a, cudaStream_t s);
 
@@ -112,6 +115,10 @@ struct FfnArgs {
     const void* W1f; const void* W2f;        // launch_pack_ffn images of linear1 / linear2
     const void* maps;                        // ffn_make_maps(W1f, W2f)
     const float* b1; const float* b2; const float* ln_g; const float* ln_b; const float* prelu;
+    // pre-split planes (optional): X as bf16 hi / lo [M, 256] (then X may be null: no conversion in the kernel, TMA loads), and the
+    // result also as planes with the row mapping of `out` (needs ldo == 256; `out` may be null)
+    const uint16_t* x_hi = nullptr; const uint16_t* x_lo = nullptr;
+    uint16_t* out_hi = nullptr; uint16_t* out_lo = nullptr;
 };
 size_t ffn_packed_bytes();
 cudaError_t launch_pack_ffn(const float* W1, const float* W2, void* W1f, void* W2f, cudaStream_t s);
