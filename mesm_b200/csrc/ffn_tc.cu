@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
                 const bool ok = m < op.M;
                 rowoff[tcid] = ok ? op.omap(m) * (long long)op.ldo : -1;
                 rowoff[128 + tcid] = ok ? (long long)m * op.ldr : -1;
+                if (ok) {                                  // the residual row is read by the final epilogue ~90 k cycles from now: bring it
+                    const float* r = op.R + (long long)m * op.ldr;      // into L2 (19 MB chip-wide) so that those loads do not pay HBM latency
+#pragma unroll
+                    for (int c = 0; c < DM; c += 32) prefetch_l2(r + c);
+                }
             }
         }
         // ---- X: fp32 rows -> bf16 hi/lo, K-major SWIZZLE_64B blocks of 32 columns, resident for the whole tile ----

@@ -7,7 +7,7 @@
 // the time (profiles/r1_linear_tc_ncu.md).  Here the producers of an activation store it pre-split (hi = bf16(x),
 // lo = bf16(x - hi): the same 4 bytes per element as fp32) and this kernel moves BOTH operands with the TMA engine:
 //   warp 0      : one thread issues cp.async.bulk.tensor loads of the A planes (box 32 x 128, SWIZZLE_64B) and of the weight
-//                 planes (box 32 x 256) into a 3-stage ring; the other lanes prefetch the residual rows of the tile into L2
+//                 planes (box 32 x 256) into a 3-stage ring
 //   warp 1      : one thread issues the MMAs (M128 N256 K16; bf16x3: Ahi.Whi + Alo.Whi + Ahi.Wlo; or, for an exact single
 //                 fp16 A plane - the 16-bit stored clip features - A.Whi + A.Wlo) and commits stages / accumulators
 //   warps 2..9  : epilogue out of TMEM (LayerNorm fold / bias / scale / activation / residual / LayerNorm / stores as fp32
@@ -25,15 +25,16 @@ namespace mesm {
 namespace tma {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 32, NST = 3;
+constexpr int BM = 128, BN = 256, BK = 32;
 constexpr int A_TILE = BM * BK * 2;                       // 8 KB: one plane of the A block
 constexpr int W_TILE = BN * BK * 2;                       // 16 KB: one plane of the weight block
-constexpr int STG = 2 * A_TILE + 2 * W_TILE;              // 48 KB
+// operand ring: 3 stages of 48 KB (two A planes + two W planes) for split bf16 operands, 4 stages of 40 KB for a single fp16 A plane
+constexpr int RING_BYTES = 4 * (A_TILE + 2 * W_TILE);     // 160 KB (>= 3 * 48 KB)
 constexpr int NEPI = 256;                                 // epilogue threads (8 warps)
 constexpr int THREADS = 64 + NEPI;
-constexpr int OFF_T = NST * STG;                          // per-warp 32 x 36 fp32 transpose scratch
+constexpr int OFF_T = RING_BYTES;                         // per-warp 32 x 36 fp32 transpose scratch
 constexpr int T_BYTES = 8 * 32 * 36 * 4;
-constexpr int OFF_BAR = OFF_T + T_BYTES;                  // full[3] empty[3] tfull[2] tempty[2] tmem_ptr
+constexpr int OFF_BAR = OFF_T + T_BYTES;                  // full[4] empty[4] tfull[2] tempty[2] tmem_ptr
 constexpr int OFF_LNX = OFF_BAR + 128;                    // [2][128]
 constexpr int OFF_VEC = OFF_LNX + 1024;                   // [4][256]: bias, colsum, ln_g, ln_b of the N tile
 constexpr int OFF_ROWOFF = OFF_VEC + 4096;                // [3][128] long long: out, out2, residual row offsets
@@ -59,8 +60,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_full = smem_base + OFF_BAR, bar_empty = bar_full + 24, bar_tfull = bar_full + 48, bar_tempty = bar_full + 64;
+    const uint32_t bar_full = smem_base + OFF_BAR, bar_empty = bar_full + 32, bar_tfull = bar_full + 64, bar_tempty = bar_full + 80;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
+    const int NST = P.npass == 3 ? 3 : 4;                 // ring depth / stage size of this launch's operand format
+    const int A_BYTES = P.npass == 3 ? 2 * A_TILE : A_TILE, STG = A_BYTES + 2 * W_TILE;
     float* ln_x = reinterpret_cast<float*>(smem + OFF_LNX);
     float* vec_s = reinterpret_cast<float*>(smem + OFF_VEC);
     long long* rowoff = reinterpret_cast<long long*>(smem + OFF_ROWOFF);
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
     const int nkb = P.nkb;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, NEPI / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&P.tmA0); tma_prefetch_desc(&P.tmW0); tma_prefetch_desc(&P.tmW1);
@@ -91,22 +94,12 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
-        // ===================== TMA producer (lane 0) + L2 prefetch of the tile's residual rows (all lanes) =====================
+        // ===================== TMA producer (lane 0) =====================
         int g = 0;
         for (int ti = 0; ti < nmine; ++ti) {
             const int t = (int)blockIdx.x + ti * (int)gridDim.x;
             const int mt = t / P.ntn, nt = t - mt * P.ntn;
             const int m0 = mt * BM, n0 = nt * BN;
-            if (op.residual) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int m = m0 + lane + 32 * i;
-                    if (m < op.M) {
-                        const float* r = op.residual + op.rmap(m) * (long long)op.ldr + n0;
-                        for (int c = 0; c < BN; c += 32) prefetch_l2(r + c);
-                    }
-                }
-            }
             if (lane == 0) {
                 // every tile walks the K blocks in its own rotation: the CTAs start together and would otherwise all ask L2
                 // for the same weight lines at the same moment
@@ -117,11 +110,11 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
                     mbar_wait_spin(bar_empty + 8 * s, ph ^ 1, 1000 + kb);
                     int kk = kb + krot; kk = kk >= nkb ? kk - nkb : kk;
                     const uint32_t dst = smem_base + s * STG, full = bar_full + 8 * s;
-                    mbar_arrive_expect_tx(full, (P.npass == 3 ? 2 : 1) * A_TILE + 2 * W_TILE);
+                    mbar_arrive_expect_tx(full, STG);
                     tma_load_2d(dst, &P.tmA0, kk * BK, m0, full);
                     if (P.npass == 3) tma_load_2d(dst + A_TILE, &P.tmA1, kk * BK, m0, full);
-                    tma_load_2d(dst + 2 * A_TILE, &P.tmW0, kk * BK, n0, full);
-                    tma_load_2d(dst + 2 * A_TILE + W_TILE, &P.tmW1, kk * BK, n0, full);
+                    tma_load_2d(dst + A_BYTES, &P.tmW0, kk * BK, n0, full);
+                    tma_load_2d(dst + A_BYTES + W_TILE, &P.tmW1, kk * BK, n0, full);
                 }
             }
             __syncwarp();
@@ -142,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
                     mbar_wait_spin(bar_full + 8 * s, ph, 2000 + kb);
                     tc_fence_after();
                     const uint32_t a_hi = smem_base + s * STG, a_lo = a_hi + A_TILE;
-                    const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + W_TILE;
+                    const uint32_t w_hi = a_hi + A_BYTES, w_lo = w_hi + W_TILE;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint32_t koff = k * 32;          // 16 elements = 32 bytes along K inside the 64-byte swizzle row
@@ -193,6 +186,18 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int m = m0 + row;
             const bool mok = m < op.M;
+            if (op.residual) {
+                // this thread's residual row segment (its TMEM lane x this warp's column half) into L2 now: the loads of
+                // rows_pass follow within a few thousand cycles.  (Prefetching from the producer warp, two tiles ahead as
+                // linear_tc does, was useless here: ~150 MB stream through L2 in between and the lines were fetched twice -
+                // ncu: 920 MB of DRAM reads for 614 MB of operands.)
+                const long long ro = rowoff[256 + row];
+                if (ro >= 0) {
+                    const float* r = op.residual + ro + n0 + half * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (n0 + half * 128 + c * 32 < op.N) prefetch_l2(r + c * 32);
+                }
+            }
             float mean_in = 0.f, rstd_in = 1.f;
             if (op.rowstat && mok) { mean_in = __ldg(op.rowstat + 2 * m); rstd_in = __ldg(op.rowstat + 2 * m + 1); }
             if (lane == 0) mbar_wait(bar_tfull + 8 * acc, aph, 5000 + ti);
