@@ -152,6 +152,20 @@ int mesm_upload_clips_f16(const void* host_feat, const uint8_t* host_mask, int32
                           void* dev_feat, uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied,
                           void* stream);
 
+/* ---- feature-ingest front-end: replaces get_video_feat (dataset/charades.py:108-119, dataset/qvhighlights.py:201-211) +
+ * sample_video_feat (dataset/base.py:100-114) + add_tef (dataset/base.py:225-230) for ONE video.  raw: HOST array of S device
+ * pointers to the raw per-source clip features [raw_len[s], dims[s]] (fp32, or fp16 when raw_f16; the reference upcasts on load);
+ * normalize = the config's normalize_video (per-source L2 normalisation over the feature dim, eps 1e-12); sources are truncated
+ * to the shortest one, concatenated, mean-pooled to max_video_l clips when longer, and the two tef columns are appended
+ * (use_tef).  out: dev [mesm_video_feat_rows(...), sum(dims) + 2 * use_tef] fp32, or fp16 when out_f16 (the 16-bit storage
+ * option of mesm_forward).  qvhighlights truncates the raw arrays to max_video_l rows before anything else: pass
+ * min(raw_len, max_video_l) there. */
+int32_t mesm_video_feat_rows(const int32_t* raw_len, int32_t S, int32_t max_video_l);
+size_t  mesm_video_feat_workspace_bytes(const int32_t* raw_len, int32_t S, int32_t max_video_l);
+int     mesm_build_video_feat(const void* const* raw, const int32_t* raw_len, const int32_t* dims, int32_t S, int32_t raw_f16,
+                              int32_t normalize, int32_t max_video_l, int32_t use_tef, void* out, int32_t out_f16, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- span decode + post-processing + temporal NMS ------------------------------------------------------------- */
 /* replaces eval.py:64-66,84-91 (softmax fg score, span_cxw_to_xx * duration, stable sort, 4-decimal rounding),
  * PostProcessorDETR as configured at eval.py:111-115 (utils/post_processing.py:22-47) and, when nms_thd != -1,
@@ -198,6 +212,17 @@ int mesm_temporal_iou(const float* spans1, int32_t N, const float* spans2, int32
                       float* giou, void* stream);
 /* span_cxw_to_xx (26-42) when to_xx != 0 else span_xx_to_cxw (5-23), n rows of 2. */
 int mesm_span_convert(const float* in, float* out, int64_t n, int to_xx, void* stream);
+
+/* ---- eval-time saliency criterion: replaces Criterion.loss_saliency (model/criterion.py:139-221), which train.py's per-epoch
+ * evaluation applies to the forward's outputs (eval.py:101-105).  saliency_scores / neg_saliency_scores dev [B,L] (MESM.forward),
+ * video_mask dev [B,L] (1 = valid), label dev [B,L] fp32 = targets["saliency_label"] or targets["clip_mask"].float() (:155-158),
+ * rank_coef = the config's value (12 in every shipped config); num_pairs > 0 adds the triplet term of `use_triplet` configs with
+ * pos_idx / neg_idx dev int64 [B,num_pairs] and saliency_margin.  out4 (dev) = {loss_saliency, loss_neg_pair,
+ * loss_rank_contrastive, loss_triplet}. */
+size_t mesm_saliency_loss_workspace_bytes(int32_t B);
+int mesm_saliency_loss(const float* saliency_scores, const float* neg_saliency_scores, const uint8_t* video_mask, const float* label,
+                       int32_t B, int32_t L, float rank_coef, const int64_t* pos_idx, const int64_t* neg_idx, int32_t num_pairs,
+                       float saliency_margin, float* out4, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- segment-sentence alignment scores: replaces model/criterion.py:241-266 (up to cos_sim / tau) --------------- */
 int mesm_align_scores(const float* projed_video_feat,    /* dev [B,Lv,256] */

@@ -3,8 +3,9 @@
 Layout: ``csrc/`` CUDA kernels + C ABI (include/mesm_b200.h) -> ``libmesm_b200.so``; ``_lib`` ctypes binding;
 ``engine`` context owner; ``model`` / ``utils`` drop-in mirrors of the reference's Python interface.
 """
-from .engine import Engine, decode_nms, temporal_nms_lists, align_scores  # noqa: F401
-from .ingest import prepare_batch_input, upload_clips  # noqa: F401
+from .engine import Engine, decode_nms, temporal_nms_lists, align_scores, loss_saliency  # noqa: F401
+from .ingest import prepare_batch_input, upload_clips, build_video_feat  # noqa: F401
 from .numa import bind_to_gpu_node  # noqa: F401
 
-__all__ = ["Engine", "decode_nms", "temporal_nms_lists", "align_scores", "prepare_batch_input", "upload_clips"]
+__all__ = ["Engine", "decode_nms", "temporal_nms_lists", "align_scores", "loss_saliency", "prepare_batch_input", "upload_clips",
+           "build_video_feat", "bind_to_gpu_node"]

@@ -57,6 +57,10 @@ SYMBOLS = {
                                   POINTER(c_int64), c_void_p]),
     "mesm_upload_clips_f16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_int32,
                                       POINTER(c_int64), c_void_p]),
+    "mesm_video_feat_rows": (c_int32, [POINTER(c_int32), c_int32, c_int32]),
+    "mesm_video_feat_workspace_bytes": (c_size_t, [POINTER(c_int32), c_int32, c_int32]),
+    "mesm_build_video_feat": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
     "mesm_decode_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, POINTER(MesmDecodeParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mesm_temporal_nms": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),
@@ -66,6 +70,9 @@ SYMBOLS = {
     "mesm_align_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "mesm_align_workspace_bytes": (c_size_t, [c_int32]),
+    "mesm_saliency_loss_workspace_bytes": (c_size_t, [c_int32]),
+    "mesm_saliency_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_int32,
+                                   c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mesm_mha_noproj": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mesm_mha_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),

@@ -243,3 +243,28 @@ def align_scores(projed_video_feat, clip_mask, expanded_words_feat, expanded_wor
         check(lib.mesm_align_scores(_ptr(pv), _ptr(cm), _ptr(ew), _ptr(em), B, Lv, Lw, float(tau), _ptr(S), _ptr(ws),
                                     ws.numel(), _stream()))
     return S
+
+
+def loss_saliency(outputs, targets, rank_coef=12, use_triplet=False, saliency_margin=0.2):
+    """Criterion.loss_saliency (model/criterion.py:139-221) on the forward's outputs, as train.py's per-epoch evaluation calls it
+    (eval.py:101-105).  ``outputs``: dict with saliency_scores / neg_saliency_scores [B,L]; ``targets``: the batch dict
+    (video_mask, saliency_label or clip_mask, and pos_idx / neg_idx when ``use_triplet``).  Returns {"loss_saliency": 0-d tensor}
+    plus the three terms it is the sum of."""
+    lib = _lib.lib()
+    sal = _f32(outputs["saliency_scores"], "saliency_scores"); neg = _f32(outputs["neg_saliency_scores"], "neg_saliency_scores")
+    vm = _u8(targets["video_mask"], "video_mask")
+    label = targets["saliency_label"] if "saliency_label" in targets else targets["clip_mask"]
+    label = _f32(label.to(sal.device), "saliency_label")
+    B, L = sal.shape
+    pos = neg_i = None
+    P = 0
+    if use_triplet:
+        pos = targets["pos_idx"].to(device=sal.device, dtype=torch.int64).contiguous()
+        neg_i = targets["neg_idx"].to(device=sal.device, dtype=torch.int64).contiguous()
+        P = pos.shape[1]
+    out = torch.empty(4, dtype=torch.float32, device=sal.device)
+    ws = torch.empty(lib.mesm_saliency_loss_workspace_bytes(B), dtype=torch.uint8, device=sal.device)
+    with torch.cuda.device(sal.device):
+        check(lib.mesm_saliency_loss(_ptr(sal), _ptr(neg), _ptr(vm), _ptr(label), B, L, float(rank_coef), _ptr(pos), _ptr(neg_i), P,
+                                     float(saliency_margin), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return {"loss_saliency": out[0], "loss_neg_pair": out[1], "loss_rank_contrastive": out[2], "loss_triplet": out[3]}

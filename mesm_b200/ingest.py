@@ -155,3 +155,30 @@ def prepare_batch_input(batched_data, device, non_blocking=False, out=None, shar
         batched_data["norm_span"] = span_xx_to_cxw(batched_data["norm_moment"])
     prepare_batch_input.last_h2d_bytes = total
     return batched_data
+
+
+def build_video_feat(raw_sources, max_video_l, normalize_video=True, use_tef=True, out_dtype=torch.float32, device=None):
+    """The dataset-side front-end of ONE video on the device: get_video_feat (dataset/charades.py:108-119) + sample_video_feat
+    (dataset/base.py:100-114) + add_tef (dataset/base.py:225-230).  ``raw_sources``: list of raw per-source clip features
+    [L_s, D_s], all fp32 or all fp16 (host or device).  Returns [L, sum(D_s) + 2] in ``out_dtype`` (torch.float16 = the 16-bit
+    storage option ``MESM.forward`` consumes directly).  For qvhighlights pass the raw arrays truncated to ``max_video_l`` rows
+    (dataset/qvhighlights.py:205)."""
+    from ctypes import c_int32, c_void_p
+    lib = _lib.lib()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    f16 = raw_sources[0].dtype == torch.float16
+    srcs = [r.to(device=device, dtype=torch.float16 if f16 else torch.float32).contiguous() for r in raw_sources]
+    S = len(srcs)
+    lens = (c_int32 * S)(*[int(r.shape[0]) for r in srcs])
+    dims = (c_int32 * S)(*[int(r.shape[1]) for r in srcs])
+    ptrs = (c_void_p * S)(*[r.data_ptr() for r in srcs])
+    L = int(lib.mesm_video_feat_rows(lens, S, int(max_video_l)))
+    W = sum(int(r.shape[1]) for r in srcs) + (2 if use_tef else 0)
+    if out_dtype not in (torch.float32, torch.float16):
+        raise ValueError("out_dtype must be torch.float32 or torch.float16")
+    out = torch.empty(L, W, dtype=out_dtype, device=device)
+    ws = torch.empty(int(lib.mesm_video_feat_workspace_bytes(lens, S, int(max_video_l))), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        check(lib.mesm_build_video_feat(ptrs, lens, dims, S, int(f16), int(bool(normalize_video)), int(max_video_l), int(bool(use_tef)),
+                                        _ptr(out), int(out_dtype == torch.float16), _ptr(ws), ws.numel(), _stream()))
+    return out

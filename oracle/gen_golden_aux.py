@@ -1,0 +1,92 @@
+"""Golden fixtures of the path's neighbours: the eval-time saliency criterion and the feature-ingest front-end.
+
+Runs ONLY in the build container (needs /root/reference).  TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.gen_golden_aux
+
+* criterion: the reference's own ``Criterion.loss_saliency`` (model/criterion.py:139-221) called unbound on seeded tensors
+  (charades-style 0/1 clip-mask labels; QVHighlights-style integer saliency labels + the triplet term).
+* front-end: ``dataset`` is not importable offline (h5py / ftfy), so the three functions are evaluated from their SOURCE TEXT:
+  the bodies of ``sample_video_feat`` / ``add_tef`` (dataset/base.py:100-114, 225-230) are exec'ed from the reference file, and
+  ``get_video_feat`` (dataset/charades.py:108-119) is restated around the same ``F.normalize`` / ``torch.cat`` calls.
+"""
+import os
+import re
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("MESM_REFERENCE", "/root/reference")
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def criterion_cases():
+    sys.path.insert(0, REF)
+    from model.criterion import Criterion
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    for name, B, L, qvh in (("charades", 37, 61, False), ("qvh", 24, 75, True), ("one_row", 1, 9, False)):
+        lens = torch.randint(max(2, L // 2), L + 1, (B,), generator=g)
+        lens[0] = L
+        mask = torch.arange(L)[None] < lens[:, None]
+        sal = torch.randn(B, L, generator=g) * 2
+        neg = torch.randn(B, L, generator=g) * 2
+        if qvh:
+            label = (torch.randint(0, 13, (B, L), generator=g) * (torch.rand(B, L, generator=g) < 0.3)).float() * mask
+            label[3] = 0                                           # a row without positives
+            pos_idx = torch.stack([torch.randint(0, int(n), (2,), generator=g) for n in lens])
+            neg_idx = torch.stack([torch.randint(0, int(n), (2,), generator=g) for n in lens])
+            targets = dict(video_mask=mask, saliency_label=label, pos_idx=pos_idx, neg_idx=neg_idx)
+        else:
+            label = ((torch.rand(B, L, generator=g) < 0.3) & mask)
+            targets = dict(video_mask=mask, clip_mask=label)
+        fake = types.SimpleNamespace(rank_coef=12, use_triplet=qvh, saliency_margin=0.2)
+        ref = Criterion.loss_saliency(fake, dict(saliency_scores=sal, neg_saliency_scores=neg), targets, None)["loss_saliency"]
+        out.update({f"crit_{name}_sal": sal.numpy(), f"crit_{name}_neg": neg.numpy(), f"crit_{name}_mask": mask.numpy(),
+                    f"crit_{name}_label": (targets.get("saliency_label", targets.get("clip_mask"))).float().numpy(),
+                    f"crit_{name}_loss": np.float32(ref)})
+        if qvh:
+            out.update({f"crit_{name}_pos_idx": pos_idx.numpy(), f"crit_{name}_neg_idx": neg_idx.numpy()})
+        print(f"criterion {name}: loss_saliency = {float(ref):.6f}")
+    return out
+
+
+def _method_source(path, name):
+    src = open(path).read()
+    m = re.search(r"^    def %s\(self.*?(?=^    def |^\S|\Z)" % name, src, re.S | re.M)
+    return textwrap.dedent(m.group(0))
+
+
+def frontend_cases():
+    ns = {"torch": torch}
+    exec(_method_source(os.path.join(REF, "dataset", "base.py"), "sample_video_feat"), ns)
+    exec(_method_source(os.path.join(REF, "dataset", "base.py"), "add_tef"), ns)
+    from oracle.weights import FRONTEND_CASES, make_raw_features
+    out = {}
+    for name in FRONTEND_CASES:
+        raws, max_l = make_raw_features(name)
+        feats = [F.normalize(torch.from_numpy(r.numpy().astype(np.float32)), dim=1) for r in raws]      # charades.py:112-116
+        min_len = min(len(e) for e in feats)
+        feat = torch.cat([e[:min_len] for e in feats], dim=1)     # :117-119
+        fake = types.SimpleNamespace(max_video_l=max_l)
+        feat = ns["sample_video_feat"](fake, feat)                # base.py:168
+        feat = ns["add_tef"](fake, feat.shape[0], feat)           # base.py:169-171
+        out[f"fe_{name}_out"] = feat.numpy()
+        print(f"front-end {name}: raw {[tuple(r.shape) for r in raws]} -> {tuple(feat.shape)}")
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "criterion_saliency.npz"), **criterion_cases())
+    np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **frontend_cases())
+    print("written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

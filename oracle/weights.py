@@ -207,3 +207,21 @@ def make_neg_index(num_clips, seed: int = 0):
             cand = torch.cat([torch.arange(0, int(start[gi])), torch.arange(int(end[gi]), B)])
             out.append(cand[int(torch.randint(0, len(cand), (1,), generator=g))])
     return torch.stack(out)
+
+
+# raw per-source clip features of the feature-ingest front-end fixtures (tests/golden/frontend.npz): name -> (clip counts per
+# source, feature dims per source, max_video_l, stored as fp16)
+FRONTEND_CASES = {
+    "csf_short": ((21, 23), (512, 2304), 75, False),        # shipped C+SF dims, shorter than max_video_l: no pooling
+    "csf_pool": ((160, 157), (64, 200), 75, True),          # mean-pool down-sampling (dataset/base.py:100-114), 16-bit storage
+    "vgg_pool": ((333,), (300,), 200, True),
+    "c3d_exact": ((200,), (128,), 200, False),              # length == max_video_l
+}
+
+
+def make_raw_features(name):
+    """Seeded raw (un-normalised) per-source features of a front-end fixture: list of [L_s, D_s] tensors (fp16 or fp32)."""
+    lens, dims, max_l, f16 = FRONTEND_CASES[name]
+    g = torch.Generator().manual_seed(_key_seed(7, "frontend:" + name))
+    raws = [torch.randn(n, d, generator=g) * (1 + i) for i, (n, d) in enumerate(zip(lens, dims))]
+    return [r.half() if f16 else r for r in raws], max_l
