@@ -459,9 +459,162 @@ __global__ void __launch_bounds__(256) recon_pool_kernel(const ReconPoolArgs a) 
     op[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
 }
 
+// Tiled variant (round 2).  The kernel above keeps one warp per head walking the keys one at a time: every key costs a 1 KB row
+// load per head (8x per pair, twice: scores and pooling) and a serial 5-step warp reduction.  Here the CTA stages 32 clip rows
+// ONCE in shared memory for all 8 heads and both uses, computes the 8 x 32 scores with the Wk^T q vectors in registers (warp w:
+// 4 keys; lane: 8 columns x 8 heads = 64 FMAs per key, then a 9-shuffle transpose-reduce instead of 8 x 5), runs the softmax
+// online per tile (warp h = head h), and pools with thread = column, 8 heads in registers.
+constexpr int RP_TK = 32, RP_LD = 260;
+__global__ void __launch_bounds__(256) recon_pool_tiled_kernel(const ReconPoolArgs a) {
+    extern __shared__ float smem[];
+    float* xt = smem;                                   // [32][260]  clip rows of the tile (row stride 260: LDS.128 conflict-free)
+    float* sc = xt + RP_TK * RP_LD;                     // [32 keys][8 heads] scores, then probabilities
+    int* krow = reinterpret_cast<int*>(sc + RP_TK * 8); // [max_keys] global row of key k (-1 = padded)
+    __shared__ int s_nkeys, s_bp[8], s_qpo[8], s_glp[8];
+    __shared__ float s_alpha[8], s_l[8];
+    const int bl = blockIdx.x, b = a.b0 + blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = a.pair_group[b], slot = a.pair_slot[b];
+    const int Lv = a.Lv;
+    if (a.qvh) {
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int p = a.group_start[g]; p < a.group_start[g + 1]; ++p)
+                for (int i = 0; i < Lv; ++i)
+                    if (a.vmask[(long long)p * Lv + i]) krow[n++] = a.x_start ? a.x_start[p] + i : (p - a.b0) * Lv + i;
+            s_nkeys = n;
+        }
+    } else {
+        for (int i = threadIdx.x; i < Lv; i += blockDim.x) krow[i] = a.vmask[(long long)b * Lv + i] ? (a.x_start ? a.x_start[b] + i : bl * Lv + i) : -1;
+        if (threadIdx.x == 0) s_nkeys = Lv;
+    }
+    if (threadIdx.x < 8) {                              // quirk partner of (pair, head h): see the header comment of this section
+        const int h = threadIdx.x;
+        const int bp = (int)(((long long)b * NH + h) % a.Btot);
+        const int gp = a.pair_group[bp];
+        s_bp[h] = bp;
+        s_qpo[h] = slot >= (a.group_start[gp + 1] - a.group_start[gp]) ? 1 : 0;
+        s_glp[h] = a.qvh ? a.group_len[gp] : 0;
+    }
+    __syncthreads();
+    const int nk = s_nkeys;
+    float qk[8][8];                                     // (Wk_h^T q_h)[lane * 8 + j] for the 8 heads
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        const float4* qp = reinterpret_cast<const float4*>(a.qk + ((long long)bl * NH + h) * D + lane * 8);
+        const float4 t0 = qp[0], t1 = qp[1];
+        qk[h][0] = t0.x; qk[h][1] = t0.y; qk[h][2] = t0.z; qk[h][3] = t0.w; qk[h][4] = t1.x; qk[h][5] = t1.y; qk[h][6] = t1.z; qk[h][7] = t1.w;
+    }
+    float acc[8];                                       // pooled[h][c], c = threadIdx.x
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc[h] = 0.f;
+    float m_run = -CUDART_INF_F, l_run = 0.f;           // online softmax state of head w (uniform over the warp)
+    const int c = threadIdx.x;
+
+    for (int k0 = 0; k0 < nk; k0 += RP_TK) {
+        const int tk = min(RP_TK, nk - k0);
+        {   // stage the tile: thread -> (row t >> 3, float4 columns (t & 7) + 8 i)
+            const int r = threadIdx.x >> 3;
+            const int gr = (r < tk) ? krow[k0 + r] : -1;
+            const float4* src = gr >= 0 ? reinterpret_cast<const float4*>(a.x + (long long)gr * a.ldx) : nullptr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c4 = (threadIdx.x & 7) + 8 * i;
+                const float4 v = src ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(&xt[r * RP_LD + c4 * 4]) = v;
+            }
+        }
+        __syncthreads();
+        // ---- scores: warp w -> keys 4w .. 4w+3 of the tile, all 8 heads ----
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+            const int kk = 4 * w + u;
+            if (kk >= tk) break;                        // warp-uniform
+            const float4 x0 = *reinterpret_cast<const float4*>(&xt[kk * RP_LD + lane * 8]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&xt[kk * RP_LD + lane * 8 + 4]);
+            float p[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                float d = qk[h][0] * x0.x;
+                d = fmaf(qk[h][1], x0.y, d); d = fmaf(qk[h][2], x0.z, d); d = fmaf(qk[h][3], x0.w, d);
+                d = fmaf(qk[h][4], x1.x, d); d = fmaf(qk[h][5], x1.y, d); d = fmaf(qk[h][6], x1.z, d); d = fmaf(qk[h][7], x1.w, d);
+                p[h] = d;
+            }
+            // transpose-reduce: 8 partials x 32 lanes -> every lane ends with the full sum of head (bit4, bit3, bit2 of its lane id)
+            {
+                const bool up = (lane & 16) != 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float send = up ? p[i] : p[i + 4]; const float recv = __shfl_xor_sync(0xffffffffu, send, 16); p[i] = (up ? p[i + 4] : p[i]) + recv; }
+            }
+            {
+                const bool up = (lane & 8) != 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { const float send = up ? p[i] : p[i + 2]; const float recv = __shfl_xor_sync(0xffffffffu, send, 8); p[i] = (up ? p[i + 2] : p[i]) + recv; }
+            }
+            {
+                const bool up = (lane & 4) != 0;
+                const float send = up ? p[0] : p[1];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                p[0] = (up ? p[1] : p[0]) + recv;
+            }
+            p[0] += __shfl_xor_sync(0xffffffffu, p[0], 2);
+            p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+            if ((lane & 3) == 0) {
+                const int h = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const int k = k0 + kk;
+                bool masked = krow[k] < 0;
+                if (!masked && s_qpo[h]) masked = a.qvh ? (k >= s_glp[h]) : (a.vmask[(long long)s_bp[h] * Lv + k] == 0);
+                sc[kk * 8 + h] = masked ? -CUDART_INF_F : p[0];
+            }
+        }
+        __syncthreads();
+        // ---- online softmax of head w over the tile's keys (lane = key) ----
+        {
+            const float sv = lane < tk ? sc[lane * 8 + w] : -CUDART_INF_F;
+            const float tm = warp_max(sv);
+            float alpha = 1.f, pv = 0.f;
+            if (tm != -CUDART_INF_F) {
+                const float mn = fmaxf(m_run, tm);
+                alpha = __expf(m_run - mn);             // first tile: exp(-inf) = 0
+                pv = sv == -CUDART_INF_F ? 0.f : __expf(sv - mn);
+                l_run = l_run * alpha + warp_sum(pv);
+                m_run = mn;
+            }
+            if (lane < tk) sc[lane * 8 + w] = pv;
+            if (lane == 0) s_alpha[w] = alpha;
+        }
+        __syncthreads();
+        // ---- pooling: thread = column c, 8 heads in registers ----
+#pragma unroll
+        for (int h = 0; h < 8; ++h) acc[h] *= s_alpha[h];
+        for (int kk = 0; kk < tk; ++kk) {
+            const float x = xt[kk * RP_LD + c];
+            const float4 p0 = *reinterpret_cast<const float4*>(&sc[kk * 8]);
+            const float4 p1 = *reinterpret_cast<const float4*>(&sc[kk * 8 + 4]);
+            acc[0] = fmaf(p0.x, x, acc[0]); acc[1] = fmaf(p0.y, x, acc[1]); acc[2] = fmaf(p0.z, x, acc[2]); acc[3] = fmaf(p0.w, x, acc[3]);
+            acc[4] = fmaf(p1.x, x, acc[4]); acc[5] = fmaf(p1.y, x, acc[5]); acc[6] = fmaf(p1.z, x, acc[6]); acc[7] = fmaf(p1.w, x, acc[7]);
+        }
+        __syncthreads();                                // the next tile overwrites xt / sc
+    }
+    if (lane == 0) s_l[w] = l_run;
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 8; ++h) a.pooled[((long long)bl * NH + h) * D + c] = acc[h] * (1.f / s_l[h]);     // l == 0 -> NaN like the reference
+}
+
 cudaError_t launch_recon_pool(const ReconPoolArgs& a, cudaStream_t s) {
     ProfScope _ps("recon_pool", s);
     if (a.B <= 0) return cudaSuccess;
+    static int tiled = -1;
+    if (tiled < 0) { const char* e = getenv("MESM_RECON_TILED"); tiled = (e && e[0] == '0') ? 0 : 1; }
+    if (tiled && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
+        const size_t smem = (size_t)(RP_TK * RP_LD + RP_TK * 8) * sizeof(float) + (size_t)a.max_keys * sizeof(int);
+        if (smem <= 200 * 1024) {
+            if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(recon_pool_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            recon_pool_tiled_kernel<<<a.B, 256, smem, s>>>(a);
+            g_stats.launches++;
+            return cudaGetLastError();
+        }
+    }
     const size_t smem = (size_t)a.max_keys * (8 * sizeof(float) + sizeof(int));
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) MESM_CHECK(cudaFuncSetAttribute(recon_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
