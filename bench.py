@@ -311,6 +311,59 @@ def gpu_eager_pairs_per_s(name, cfg, state_dict, wl_full, pairs, device, steps=3
     return res, B, ref
 
 
+def latency_b32(dev, feature_f16):
+    """Small-batch latency (BASELINE configs[0] shape: QVHighlights C+SF, batch 32): one forward + decode/NMS, host call to results
+    ready, eager (185+ launches enqueued from Python / ctypes) vs one CUDA-graph replay (Engine.capture)."""
+    import mesm_b200
+    from mesm_b200.model import build_model
+    qcfg, qwl = model_cfg("qvh"), BENCH_CONFIGS["qvh"]["wl"]
+    torch.manual_seed(0)
+    m = build_model(qcfg).to(dev)
+    b = make_workload(qcfg, 32, 99, dev, qwl)
+    vf = b["video_feat"].half() if feature_f16 else b["video_feat"]
+    vl = b["video_len"]
+
+    def eager():
+        o = m(vf, b["video_mask"], b["words_feat"], None, None, b["num_clips"], dataset_name="qvhighlights", is_training=False,
+              neg_index=b["neg_index"], video_len=vl)
+        return mesm_b200.decode_nms(o["pred_logits"], o["pred_spans"], b["duration"], qcfg["clip_len"], qcfg["max_ts_val"], NMS_THD, 10, 10)
+
+    for _ in range(5):
+        eager()
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        w = eager()
+        w[0][0, 0, 0].item()                       # results on the host
+        lat.append(time.perf_counter() - t0)
+    lat.sort()
+    eng = m._eng
+    cap = eng.capture(vf, b["video_mask"], b["words_feat"], b["num_clips"], neg_index=b["neg_index"], want=("core", "rec", "aux"), video_len=vl,
+                      decode=dict(duration=b["duration"], clip_len=qcfg["clip_len"], max_ts_val=qcfg["max_ts_val"], nms_thd=NMS_THD))
+    ref = eager()
+    out = cap.replay()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out["windows"], ref[0]) and torch.equal(out["keep"], ref[2]))
+    glat = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        o = cap.replay()
+        o["windows"][0, 0, 0].item()
+        glat.append(time.perf_counter() - t0)
+    glat.sort()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        cap.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"shape": "QVHighlights C+SF, batch 32, forward (incl. negative branch) + decode/NMS, host call -> first result on the host",
+            "eager_ms_median": 1e3 * lat[len(lat) // 2], "eager_ms_min": 1e3 * lat[0],
+            "graph_ms_median": 1e3 * glat[len(glat) // 2], "graph_ms_min": 1e3 * glat[0],
+            "graph_device_ms_back_to_back": e0.elapsed_time(e1) / 50, "graph_kernels": cap.launches, "graph_equals_eager": same}
+
+
 def _f32_features(b):
     """The reference legs take fp32 tensors: the stored fp16 values upcast (exactly the values our arm computes on)."""
     if b["video_feat"].dtype == torch.float16:
@@ -672,6 +725,10 @@ def main():
             del qref, qsd, qb
         except Exception as e:                      # noqa: BLE001
             line["cpu_baseline"]["c1_qvh_b32"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            line["latency_b32"] = latency_b32(dev, f16)
+        except Exception as e:                      # noqa: BLE001
+            line["latency_b32"] = {"error": f"{type(e).__name__}: {e}"}
         if args.eager_pairs > 0:
             try:
                 res, Be, gref = gpu_eager_pairs_per_s(args.config, cfg, sd_cpu, wl, min(args.eager_pairs, B), dev)

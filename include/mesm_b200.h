@@ -213,6 +213,17 @@ int mesm_temporal_iou(const float* spans1, int32_t N, const float* spans2, int32
 /* span_cxw_to_xx (26-42) when to_xx != 0 else span_xx_to_cxw (5-23), n rows of 2. */
 int mesm_span_convert(const float* in, float* out, int64_t n, int to_xx, void* stream);
 
+/* ---- moment-retrieval metrics: the per-query work of eval_moment_retrieval (eval.py:233-263): compute_mr_r1 (eval.py:397-425),
+ * compute_average_precision_detection (eval.py:323-394), interpolated_precision_recall (utils/data_utils.py:166-182), for every
+ * ground-truth length range of get_data_by_range (eval.py:428-461) at once.  windows dev [B,nq,3] fp64 = the ranked output of
+ * mesm_decode_nms (the first max_pred_windows rows are scored, eval.py:266); gt_windows dev [total,2] fp64 with gt_offsets dev
+ * [B+1] (<= 32 windows per query); length_ranges dev [n_ranges,2] (min_l, max_l], min_l < 0 = keep everything (the "full" range);
+ * iou_thds dev [n_thds <= 16].  Outputs (dev): in_range [n_ranges,B] (the query has a ground-truth window in the range),
+ * top1_iou [n_ranges,B] (max IoU of the first window with the in-range ground truth), ap [n_ranges,B,n_thds]. */
+int mesm_mr_metrics(const double* windows, int32_t B, int32_t nq, int32_t max_pred_windows, const double* gt_windows,
+                    const int64_t* gt_offsets, const double* length_ranges, int32_t n_ranges, const double* iou_thds, int32_t n_thds,
+                    uint8_t* in_range, double* top1_iou, double* ap, void* stream);
+
 /* ---- eval-time saliency criterion: replaces Criterion.loss_saliency (model/criterion.py:139-221), which train.py's per-epoch
  * evaluation applies to the forward's outputs (eval.py:101-105).  saliency_scores / neg_saliency_scores dev [B,L] (MESM.forward),
  * video_mask dev [B,L] (1 = valid), label dev [B,L] fp32 = targets["saliency_label"] or targets["clip_mask"].float() (:155-158),

@@ -70,6 +70,8 @@ SYMBOLS = {
     "mesm_align_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "mesm_align_workspace_bytes": (c_size_t, [c_int32]),
+    "mesm_mr_metrics": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
     "mesm_saliency_loss_workspace_bytes": (c_size_t, [c_int32]),
     "mesm_saliency_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_int32,
                                    c_float, c_void_p, c_void_p, c_size_t, c_void_p]),

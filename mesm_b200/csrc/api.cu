@@ -502,6 +502,7 @@ void mesm_destroy(mesm_ctx* ctx) {
     for (void* p : ctx->owned_host) free(p);
     for (void* p : ctx->owned_tma) tma_free_weights(p);
     for (auto& kv : ctx->w) cudaFree(kv.second.p);
+    for (int* p : ctx->graph_tabs) cudaFreeHost(p);
     for (int i = 0; i < mesm_ctx::kTabSlots; ++i) {
         if (ctx->h_tab[i]) cudaFreeHost(ctx->h_tab[i]);
         if (ctx->tab_event[i]) cudaEventDestroy(ctx->tab_event[i]);
@@ -754,16 +755,29 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
     if (in->neg_index && G < 2) return fail(ctx, 1, "the negative branch needs >= 2 video groups (sample_outclass_neg raises in the reference)");
     const bool packed = in->video_len != nullptr;       // variable-length clip rows: no work on the zero padding
     const size_t tab_ints = (size_t)3 * B + (G + 1) + 1 + 3 * (size_t)Lv + 1 + (G + 1);
+    // Stream capture (CUDA graphs, Engine.capture): the kernel that pulls the host tables is replayed with the graph, so the
+    // tables of a captured forward get a pinned buffer of their own that lives as long as the context (relaxed capture mode
+    // permits the allocation); the ring and its events serve eager forwards only.
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(s, &cap_status));
+    const bool capturing = cap_status == cudaStreamCaptureStatusActive;
     const int ts = ctx->tab_turn;                    // this forward's slot of the pinned-table ring
-    ctx->tab_turn = (ts + 1) % mesm_ctx::kTabSlots;
-    if (ctx->tab_event_pending[ts]) { CK(cudaEventSynchronize(ctx->tab_event[ts])); ctx->tab_event_pending[ts] = false; }   // its last reader has run
-    if (ctx->h_tab_cap[ts] < tab_ints) {
-        if (ctx->h_tab[ts]) cudaFreeHost(ctx->h_tab[ts]);
-        ctx->h_tab[ts] = nullptr; ctx->h_tab_cap[ts] = 0;
-        CK(cudaMallocHost((void**)&ctx->h_tab[ts], tab_ints * 2 * sizeof(int)));
-        ctx->h_tab_cap[ts] = tab_ints * 2;
+    int* h_table = nullptr;
+    if (capturing) {
+        CK(cudaMallocHost((void**)&h_table, tab_ints * sizeof(int)));
+        ctx->graph_tabs.push_back(h_table);
+    } else {
+        ctx->tab_turn = (ts + 1) % mesm_ctx::kTabSlots;
+        if (ctx->tab_event_pending[ts]) { CK(cudaEventSynchronize(ctx->tab_event[ts])); ctx->tab_event_pending[ts] = false; }   // its last reader has run
+        if (ctx->h_tab_cap[ts] < tab_ints) {
+            if (ctx->h_tab[ts]) cudaFreeHost(ctx->h_tab[ts]);
+            ctx->h_tab[ts] = nullptr; ctx->h_tab_cap[ts] = 0;
+            CK(cudaMallocHost((void**)&ctx->h_tab[ts], tab_ints * 2 * sizeof(int)));
+            ctx->h_tab_cap[ts] = tab_ints * 2;
+        }
+        h_table = ctx->h_tab[ts];
     }
-    int* h_group = ctx->h_tab[ts]; int* h_slot = h_group + B; int* h_gstart = h_slot + B; int* h_cu = h_gstart + (G + 1);
+    int* h_group = h_table; int* h_slot = h_group + B; int* h_gstart = h_slot + B; int* h_cu = h_gstart + (G + 1);
     h_cu[0] = 0;
     for (int b = 0; b < B; ++b) {
         const int n = packed ? in->video_len[b] : Lv;
@@ -834,8 +848,10 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         CK(cudaHostGetDevicePointer((void**)&h_dev, h_group, 0));
         CK(launch_pull_ints(h_dev, d_group, (long long)tab_ints, s));
     }
-    CK(cudaEventRecord(ctx->tab_event[ts], s));
-    ctx->tab_event_pending[ts] = true;
+    if (!capturing) {
+        CK(cudaEventRecord(ctx->tab_event[ts], s));
+        ctx->tab_event_pending[ts] = true;
+    }
     if (cf.qvh_grouping) CK(launch_group_len(in->video_mask, Lv, d_gstart, G, d_glen, s));
     // t_pad: packed clip row -> this pair's row in the zero-padded [B, Lv] layout (outputs); t_in: the row its features are
     // read from (the same, or the group's first pair when the collate-replicated video was uploaded once per group)

@@ -90,6 +90,7 @@ struct mesm_ctx {
     cudaEvent_t tab_event[kTabSlots] = {nullptr, nullptr, nullptr};
     bool tab_event_pending[kTabSlots] = {false, false, false};
     int tab_turn = 0;
+    std::vector<int*> graph_tabs;      // pinned tables of forwards recorded into CUDA graphs (one per capture, kept until destroy)
 };
 
 

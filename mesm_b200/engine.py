@@ -185,6 +185,17 @@ class Engine:
             o["expanded_words_mask"] = o["expanded_words_mask"].view(torch.bool)
         return o
 
+    def capture(self, video_feat, video_mask, words_feat, num_clips, neg_index=None, want=("core",), video_len=None,
+                shared_group_video=False, decode=None, warmup=2):
+        """Record ``forward`` (and, with ``decode=dict(duration=..., clip_len=..., max_ts_val=..., nms_thd=...)``, the span decode /
+        NMS) for THIS batch signature into a CUDA graph and return a ``CapturedForward``: ``replay()`` re-runs the ~190 launches
+        as one graph launch on the current contents of the (static) input tensors - refresh them in place with ``copy_``.  The
+        ragged structure (num_clips, video_len) is part of the signature.  For small batches the per-launch CPU cost dominates the
+        eager call; a replay removes it (bench.py: latency_b32)."""
+        return CapturedForward(self, dict(video_feat=video_feat, video_mask=video_mask, words_feat=words_feat, num_clips=num_clips,
+                                          neg_index=neg_index, want=want, video_len=video_len, shared_group_video=shared_group_video),
+                               decode, warmup)
+
     @property
     def last_launch_count(self):
         return int(self.lib.mesm_last_launch_count(self.ctx))
@@ -192,6 +203,39 @@ class Engine:
     @property
     def last_feature_bytes(self):
         return int(self.lib.mesm_last_feature_bytes(self.ctx))
+
+
+class CapturedForward:
+    """A forward (+ decode) recorded into a CUDA graph by ``Engine.capture``."""
+
+    def __init__(self, eng, kw, decode, warmup):
+        self.eng, self.kw, self.decode = eng, kw, decode
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):               # warm-up outside the capture: workspace, function attributes, lazy module loads
+            for _ in range(max(1, warmup)):
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # relaxed: mesm_forward allocates the pinned table of a captured forward inside the capture (a host allocation, not recorded)
+        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+            self.out = self._run()
+        self.launches = eng.last_launch_count + (1 if decode else 0)
+
+    def _run(self):
+        o = self.eng.forward(**self.kw)
+        if self.decode:
+            d = self.decode
+            o["windows"], o["order"], o["keep"], o["keep_count"] = decode_nms(
+                o["pred_logits"], o["pred_spans"], d["duration"], d["clip_len"], d["max_ts_val"], d.get("nms_thd", -1.0),
+                d.get("max_before_nms", 10), d.get("max_after_nms", 10))
+        return o
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
 
 
 # ---- span decode / NMS / span utils (context-free entry points) ------------------------------------------------------

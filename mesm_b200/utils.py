@@ -105,3 +105,50 @@ class PostProcessorDETR:
             l["pred_relevant_windows"] = rows[k:k + n]
             k += n
         return lines
+
+
+def eval_moment_retrieval(windows, gt_windows, gt_offsets, dataset_name="charades", max_pred_windows=10):
+    """eval_moment_retrieval (eval.py:233-263) on the device: MR-mAP and MR-R1 per ground-truth length range.
+
+    windows: f64[B,nq,3] ranked [st,ed,score] (``decode_nms``); gt_windows f64[total,2] + gt_offsets i64[B+1] (CUDA tensors): the
+    ``relevant_windows`` of query b are rows gt_offsets[b]:gt_offsets[b+1].  Returns the reference's nested dict
+    {range: {"MR-mAP": {thd: %, "average": %}, "MR-R1": {thd: %, "miou": %}}} with its 2-decimal percent formatting; ranges
+    without any query are skipped like eval.py:249-250."""
+    import numpy as np
+    lib = _lib.lib()
+    dev = windows.device
+    if dataset_name in ("tacos",):
+        ranges, names, max_len = [[0, 10], [10, 30], [30, 150], [150, 600], [0, 600]], ["short", "middle", "long", "superlong", "full"], 600
+        r1_thds = np.array([0.1, 0.3, 0.5, 0.7])
+    else:
+        ranges, names, max_len = [[0, 10], [10, 30], [30, 150], [0, 150]], ["short", "middle", "long", "full"], 150
+        r1_thds = np.concatenate([np.array([0.3]), np.linspace(0.5, 0.95, 10)])
+    ap_thds = [float(f"{e:.2f}") for e in np.linspace(0.5, 0.95, 10)]
+    r1_thds = [float(f"{e:.2f}") for e in r1_thds]
+    rg = torch.tensor([[-1.0, 0.0] if (a == 0 and b == max_len) else [float(a), float(b)] for a, b in ranges], dtype=torch.float64, device=dev)
+    B, nq = windows.shape[0], windows.shape[1]
+    nr, nt = len(ranges), len(ap_thds)
+    w = windows.to(torch.float64).contiguous()
+    in_range = torch.empty(nr, B, dtype=torch.uint8, device=dev)
+    top1 = torch.empty(nr, B, dtype=torch.float64, device=dev)
+    ap = torch.empty(nr, B, nt, dtype=torch.float64, device=dev)
+    thd_t = torch.tensor(ap_thds, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.mesm_mr_metrics(_ptr(w), B, nq, int(max_pred_windows), _ptr(gt_windows.to(torch.float64).contiguous()),
+                                  _ptr(gt_offsets.to(torch.int64).contiguous()), _ptr(rg), nr, _ptr(thd_t), nt, _ptr(in_range), _ptr(top1),
+                                  _ptr(ap), _stream()))
+    fmt = lambda v: float(f"{100 * v:.2f}")
+    out = {}
+    in_range, top1, ap = in_range.bool().cpu().numpy(), top1.cpu().numpy(), ap.cpu().numpy()
+    for r, name in enumerate(names):
+        sel = in_range[r]
+        if not sel.any():
+            continue
+        ap_thd = ap[r][sel].mean(0)
+        m_ap = dict(zip([str(e) for e in ap_thds], ap_thd))
+        m_ap["average"] = np.mean(ap_thd)
+        iou = top1[r][sel]
+        m_r1 = {str(t): fmt(np.mean(iou >= t)) for t in r1_thds}
+        m_r1["miou"] = fmt(iou.mean())
+        out[name] = {"MR-mAP": {k: fmt(v) for k, v in m_ap.items()}, "MR-R1": m_r1}
+    return out

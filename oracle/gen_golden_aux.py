@@ -81,8 +81,63 @@ def frontend_cases():
     return out
 
 
+def _function_source(path, name):
+    src = open(path).read()
+    m = re.search(r"^def %s\(.*?(?=^def |^if __name__|\Z)" % name, src, re.S | re.M)
+    return m.group(0)
+
+
+def metrics_cases():
+    """eval_moment_retrieval (eval.py:233-263) and everything below it, exec'ed from the reference's eval.py (the module itself
+    imports runner / dataset, which need ftfy / h5py).  One harness change: compute_mr_ap's multiprocessing pool is switched off
+    (num_workers=8 -> 1) because exec'ed functions cannot be pickled; the per-query code is untouched."""
+    import copy
+    import json
+    import time
+    from collections import OrderedDict, defaultdict
+    sys.path.insert(0, REF)
+    from utils import compute_temporal_iou_batch_cross, compute_temporal_iou_batch_paired, get_window_len, interpolated_precision_recall
+    ns = dict(np=np, copy=copy, time=time, defaultdict=defaultdict, OrderedDict=OrderedDict, mp=None,
+              compute_temporal_iou_batch_cross=compute_temporal_iou_batch_cross, compute_temporal_iou_batch_paired=compute_temporal_iou_batch_paired,
+              get_window_len=get_window_len, interpolated_precision_recall=interpolated_precision_recall)
+    path = os.path.join(REF, "eval.py")
+    for fn in ("eval_moment_retrieval", "compute_mr_ap", "compute_average_precision_detection_wrapper", "compute_average_precision_detection",
+               "compute_mr_r1", "get_data_by_range"):
+        exec(_function_source(path, fn).replace("num_workers=8", "num_workers=1"), ns)
+    out, expect = {}, {}
+    rng = np.random.default_rng(5)
+    for name, dataset, B, max_ts, ngt in (("charades", "charades", 300, 60.0, 1), ("qvh", "qvhighlights", 200, 150.0, 4), ("tacos", "tacos", 250, 600.0, 1)):
+        nq = 10
+        st = rng.uniform(0, max_ts * 0.8, (B, nq)).round(2)
+        ed = np.minimum(st + rng.uniform(0.5, max_ts * 0.5, (B, nq)).round(2), max_ts)
+        sc = -np.sort(-rng.uniform(0, 1, (B, nq)).round(4), axis=1)
+        sc[::9, 3] = sc[::9, 2]                                      # equal scores
+        win = np.stack([st, ed, sc], -1)
+        n_gt = rng.integers(1, ngt + 1, B)
+        gts, offs = [], [0]
+        for b in range(B):
+            g0 = rng.uniform(0, max_ts * 0.7, n_gt[b]).round(2)
+            g1 = np.minimum(g0 + rng.choice([3.0, 8.0, 20.0, 45.0, 200.0], n_gt[b]) * rng.uniform(0.5, 1.5, n_gt[b]), max_ts).round(2)
+            if b % 4 == 0:                                           # make the top-1 prediction overlap a ground-truth window
+                win[b, 0, 0], win[b, 0, 1] = g0[0] + 0.5, g1[0]
+            if b % 6 == 0 and nq > 2:
+                win[b, 2, :2] = win[b, 0, :2]                        # duplicate prediction: only one may match (lock_gt)
+            gts.append(np.stack([g0, g1], 1))
+            offs.append(offs[-1] + n_gt[b])
+        sub = [dict(qid=b, pred_relevant_windows=win[b].tolist()) for b in range(B)]
+        gt = [dict(qid=b, relevant_windows=gts[b].tolist()) for b in range(B)]
+        res = ns["eval_moment_retrieval"](sub, gt, verbose=False, dataset_name=dataset)
+        out.update({f"met_{name}_windows": win, f"met_{name}_gt": np.concatenate(gts), f"met_{name}_gt_off": np.asarray(offs, dtype=np.int64)})
+        expect[name] = dict(dataset_name=dataset, metrics=res)
+        print(f"metrics {name}: full R1@0.5 {res['full']['MR-R1']['0.5']} mAP {res['full']['MR-mAP']['average']} ranges {sorted(res)}")
+    with open(os.path.join(GOLD, "metrics_expected.json"), "w") as f:
+        json.dump(expect, f, indent=1)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **metrics_cases())
     np.savez_compressed(os.path.join(GOLD, "criterion_saliency.npz"), **criterion_cases())
     np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **frontend_cases())
     print("written to", GOLD)

@@ -47,3 +47,22 @@ def test_feature_frontend_matches_reference(golden_dir, name):
     h = mesm_b200.build_video_feat([r.cuda() for r in raws], max_l, out_dtype=torch.float16)      # 16-bit storage of the same rows
     assert h.dtype == torch.float16 and float((h.float().cpu() - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
     assert torch.equal(h, out.half())
+
+
+@pytest.mark.parametrize("name", ["charades", "qvh", "tacos"])
+def test_moment_retrieval_metrics_match_reference(golden_dir, name):
+    """eval_moment_retrieval (eval.py:233-263: MR-R1 / MR-mAP per ground-truth length range, multi-window ground truth, duplicate
+    predictions, equal scores) - the reference's own functions produced tests/golden/metrics_expected.json."""
+    import json
+    from mesm_b200 import utils as U
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    exp = json.load(open(os.path.join(golden_dir, "metrics_expected.json")))[name]
+    res = U.eval_moment_retrieval(torch.from_numpy(g[f"met_{name}_windows"]).cuda(), torch.from_numpy(g[f"met_{name}_gt"]).cuda(),
+                                  torch.from_numpy(g[f"met_{name}_gt_off"]).cuda(), dataset_name=exp["dataset_name"])
+    ref = exp["metrics"]
+    assert sorted(res) == sorted(ref)
+    for rng_name in ref:
+        for fam in ("MR-mAP", "MR-R1"):
+            assert sorted(res[rng_name][fam]) == sorted(ref[rng_name][fam]), (rng_name, fam)
+            for k, v in ref[rng_name][fam].items():
+                assert res[rng_name][fam][k] == v, (rng_name, fam, k, res[rng_name][fam][k], v)       # 2-decimal percents: exact
