@@ -276,6 +276,7 @@ cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, cons
     a.k_pad = pad; a.q_pad = nullptr; a.out = t.AO; a.ldo = D; a.B = Bc; a.Lq = L1; a.Lk = L1; a.b0 = 0; a.Btot = Bc;
     a.q_scale = kScale32;
     a.q_cu = cu; a.q_enc = 1; a.k_cu = cu; a.k_enc = 1;      // packed encoder rows (global token + this pair's clips)
+    a.split_ws = t.split; a.split_rows = R;                  // more keys than one 224-key tile (max_video_l = 600): key-split passes
     if (pl) { a.out = nullptr; a.out_hi = pio->ao.hi; a.out_lo = pio->ao.lo; }
     MESM_CHECK(launch_mha_rows(a, s));
     if (pl) {
@@ -714,6 +715,7 @@ void plan_forward(const mesm_ctx* c, Arena& ar, FwdPlan& p, int B, int Lv, int L
     p.t2v.KV = ar.get<float>(Rk * 2 * D); p.t2v.Q = ar.get<float>(Re * D); p.t2v.AO = ar.get<float>(Re * D);
     p.t2v.X1 = ar.get<float>(Re * D); p.t2v.Y1 = ar.get<float>(Re * D); p.t2v.H = ar.get<float>(Re * FF);
     p.encb.QKV = ar.get<float>(Re * 3 * D); p.encb.AO = p.t2v.AO; p.encb.Y1 = p.t2v.Y1; p.encb.H = p.t2v.H;
+    p.encb.split = attn_split_floats((long long)Re, L1) ? ar.get<float>(attn_split_floats((long long)Re, L1)) : nullptr;
     dec_alloc(ar, p.dec, Bc, cf.num_queries, L1, cf.dec_layers);
     p.rS = ar.get<float>((size_t)B * D); p.rS2 = ar.get<float>((size_t)B * D); p.rq = ar.get<float>((size_t)B * D);
     p.rqk = ar.get<float>((size_t)B * NH * D); p.rpool = ar.get<float>((size_t)B * NH * D); p.rao = ar.get<float>((size_t)B * D);

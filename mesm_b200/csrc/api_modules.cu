@@ -248,6 +248,7 @@ size_t mesm_transformer_workspace_bytes(const mesm_ctx* ctx, int32_t B, int32_t 
     const size_t Re = (size_t)B * (L + 1);
     ar.get<float>(Re * D); ar.get<float>(Re * D); ar.get<float>(Re * D); ar.get<uint8_t>(Re);
     ar.get<float>(Re * 3 * D); ar.get<float>(Re * D); ar.get<float>(Re * D); ar.get<float>(Re * FF);
+    if (attn_split_floats((long long)Re, L + 1)) ar.get<float>(attn_split_floats((long long)Re, L + 1));
     DecBuffers d;
     dec_alloc(ar, d, B, ctx->cfg.num_queries, L + 1, ctx->cfg.dec_layers);
     return ar.off + 4096;
@@ -274,6 +275,7 @@ int mesm_transformer(mesm_ctx* ctx, const float* src, const uint8_t* pad, const 
     uint8_t* padE = ar.get<uint8_t>(Re);
     EncBuffers eb;
     eb.QKV = ar.get<float>(Re * 3 * D); eb.AO = ar.get<float>(Re * D); eb.Y1 = ar.get<float>(Re * D); eb.H = ar.get<float>(Re * FF);
+    if (attn_split_floats((long long)Re, L1)) eb.split = ar.get<float>(attn_split_floats((long long)Re, L1));
     DecBuffers d;
     dec_alloc(ar, d, B, nq, L1, ctx->cfg.dec_layers);
     build_enc_kernel<<<dim3(L1, B), D, 0, s>>>(src, pos_embed, pad, global_token, global_token_pos, B, L, E, posE, padE);
@@ -309,11 +311,20 @@ int mesm_debug_attention(const float* qkv, const uint8_t* k_pad, int32_t B, int3
     a.q = qkv; a.ldq = 3 * D; a.k = qkv + D; a.ldk = 3 * D; a.v = qkv + 2 * D; a.ldv = 3 * D;
     a.k_pad = k_pad; a.q_pad = nullptr; a.out = out; a.ldo = D; a.B = B; a.Lq = L; a.Lk = L; a.b0 = 0; a.Btot = B;
     a.q_scale = kScale32;
+    float* split = nullptr;
+    if (use_tc == 2) {                 // key-split tensor-core path (more than 224 keys)
+        const size_t nf = attn_split_floats((long long)B * L, L);
+        if (!nf) return fail(ctx, 3, "key-split needs more than 224 keys");
+        CK(cudaMalloc((void**)&split, nf * sizeof(float)));
+        a.split_ws = split; a.split_rows = (long long)B * L;
+    }
     for (int i = 0; i < iters; ++i) {
-        if (use_tc) { if (!attn_tc_eligible(a)) return fail(ctx, 3, "not eligible"); CK(launch_attn_tc(a, s)); }
+        if (use_tc == 2) { if (!attn_tc_split_eligible(a)) { cudaFree(split); return fail(ctx, 3, "not eligible"); } CK(launch_attn_tc_split(a, a.split_rows, s)); }
+        else if (use_tc) { if (!attn_tc_eligible(a)) return fail(ctx, 3, "not eligible"); CK(launch_attn_tc(a, s)); }
         else { CK(launch_mha_rows(a, s, true)); }
     }
     CK(cudaStreamSynchronize(s));
+    cudaFree(split);
     if (watchdog8) { unsigned long long tmp[64]; tc_read_watchdog(tmp); for (int i = 0; i < 8; ++i) watchdog8[i] = tmp[i]; }
     return 0;
 }

@@ -139,6 +139,10 @@ cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_sim
         static int force = -1;
         if (force < 0) { const char* e = getenv("MESM_FORCE_SIMT"); const char* e2 = getenv("MESM_FORCE_SIMT_ATTN"); force = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
         if (!force && !force_simt && attn_tc_eligible(a)) return launch_attn_tc(a, s);
+        if (!force && !force_simt && attn_tc_split_eligible(a)) {
+            // rows of the query side = rows of the output: uniform B * Lq, packed: the caller passes it through split_rows
+            return launch_attn_tc_split(a, a.split_rows, s);
+        }
     }
     ProfScope _ps(a.q_pad ? "mha_rows t2v" : "mha_rows self", s);
     const int threads = MR_ROWS;

@@ -54,7 +54,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const MhaRowsArg
     long long kbase, qbase; int Lq, Lk;                                 // rows of this pair (packed layouts: per-pair counts)
     pair_rows(a.q_cu, a.q_enc, b, a.Lq, qbase, Lq);
     pair_rows(a.k_cu, a.k_enc, b, a.Lk, kbase, Lk);
-    const long long kpad_own = a.k_cu ? kbase : (long long)bg * Lk;
+    long long kpad_own = a.k_cu ? kbase : (long long)bg * Lk;
+    if (a.k_count > 0) {                                                // key-split pass: this launch sees one chunk of the keys
+        const int n = min(a.k_count, Lk - a.k_begin);
+        kbase += a.k_begin; kpad_own += a.k_begin;
+        Lk = n;
+        if (n <= 0) {                                                   // this pair has no key in the chunk: weight 0 in the merge
+            for (int i = threadIdx.x; i < Lq; i += blockDim.x) {
+                a.split_stats[((qbase + i) * NH + h) * 2] = -CUDART_INF_F;
+                a.split_stats[((qbase + i) * NH + h) * 2 + 1] = 0.f;
+            }
+            return;
+        }
+    }
     const int q_pad_ld = a.q_pad_ld ? a.q_pad_ld : a.Lq;
     const int Lkp = (Lk + 31) & ~31;
     const int ntiles = (Lq + 127) >> 7;
@@ -259,7 +271,14 @@ uint32_t vh2[2], vl2[2];
             if (wact) {
                 float o[32];
                 tmem_ld32(trow + AT_OCOL, o);
-                const float inv = 1.f / sum;
+                float inv = 1.f / sum;
+                if (a.split_stats) {
+                    if (sum == 0.f) inv = 0.f;                             // every key of the chunk masked for this row: weight 0 in the merge
+                    if (qi < Lq) {
+                        a.split_stats[((qbase + qi) * NH + h) * 2] = mx;
+                        a.split_stats[((qbase + qi) * NH + h) * 2 + 1] = sum;
+                    }
+                }
                 float* T = reinterpret_cast<float*>(smem + AT_P + wt * 32768) + q4 * (32 * 36);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -661,6 +680,79 @@ int tc_read_attn_trace(long long* out128) {
 }
 
 void tc_read_watchdog(unsigned long long* out64) { cudaMemcpyFromSymbol(out64, tc::g_tc_watchdog, 512); unsigned long long z[64] = {0}; cudaMemcpyToSymbol(tc::g_tc_watchdog, z, 512); }
+
+// merge of the key-split passes: out[row, head, :] = sum_c w_c O_c / sum_c w_c,  w_c = rowsum_c * exp(rowmax_c - max_c rowmax_c)
+__global__ void attn_combine_kernel(const float* __restrict__ parts, const float* __restrict__ stats, int nchunks, long long rows,
+                                    long long part_stride, long long stat_stride, float* __restrict__ out, int ldo,
+                                    uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;         // (row, head, 4 dims)
+    if (idx >= rows * NH * 8) return;
+    const int c4 = (int)(idx & 7) * 4, h = (int)((idx >> 3) & 7);
+    const long long row = idx >> 6;
+    float m = -CUDART_INF_F;
+    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, stats[c * stat_stride + (row * NH + h) * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+        const float mc = stats[c * stat_stride + (row * NH + h) * 2], lc = stats[c * stat_stride + (row * NH + h) * 2 + 1];
+        if (lc == 0.f) continue;
+        const float w = lc * __expf(mc - m);
+        const float4 o = *reinterpret_cast<const float4*>(parts + c * part_stride + row * D + h * 32 + c4);
+        acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
+        wsum += w;
+    }
+    const float inv = 1.f / wsum;                                                   // all chunks empty -> NaN like the reference
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    if (out) *reinterpret_cast<float4*>(out + row * ldo + h * 32 + c4) = acc;
+    if (out_hi) {
+        uint2 hh, ll;
+        tc::split_bf16x2(acc.x, acc.y, hh.x, ll.x);
+        tc::split_bf16x2(acc.z, acc.w, hh.y, ll.y);
+        *reinterpret_cast<uint2*>(out_hi + row * D + h * 32 + c4) = hh;
+        *reinterpret_cast<uint2*>(out_lo + row * D + h * 32 + c4) = ll;
+    }
+}
+
+size_t attn_split_floats(long long rows, int Lk) {
+    if (Lk <= tc::AT_LKP_MAX) return 0;
+    const int nch = (Lk + tc::AT_LKP_MAX - 1) / tc::AT_LKP_MAX;
+    return (size_t)nch * ((size_t)rows * D + (size_t)rows * NH * 2);
+}
+
+// Self-attention over more keys than one tile holds: one attn_tc pass per 224-key chunk, then the exact merge above.
+cudaError_t launch_attn_tc_split(const MhaRowsArgs& a, long long rows, cudaStream_t s) {
+    const int nch = (a.Lk + tc::AT_LKP_MAX - 1) / tc::AT_LKP_MAX;
+    float* parts = a.split_ws;
+    float* stats = parts + (size_t)nch * rows * D;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MESM_CHECK(cudaFuncSetAttribute(tc::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::AT_SMEM));
+        attr_set = true;
+    }
+    {
+        ProfScope _ps("attn_tc self (key-split)", s);
+        for (int c = 0; c < nch; ++c) {
+            MhaRowsArgs p = a;
+            p.out = parts + (size_t)c * rows * D; p.ldo = D; p.out_hi = nullptr; p.out_lo = nullptr;
+            p.k_begin = c * tc::AT_LKP_MAX; p.k_count = tc::AT_LKP_MAX;
+            p.split_stats = stats + (size_t)c * rows * NH * 2;
+            dim3 grid(NH, a.B);
+            tc::attn_tc_kernel<<<grid, tc::AT_THREADS, tc::AT_SMEM, s>>>(p);
+            g_stats.launches++;
+        }
+    }
+    ProfScope _ps2("attn_combine", s);
+    const long long n = rows * NH * 8;
+    attn_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(parts, stats, nch, rows, rows * D, rows * NH * 2, a.out, a.ldo, a.out_hi, a.out_lo);
+    g_stats.launches++;
+    return cudaGetLastError();
+}
+
+bool attn_tc_split_eligible(const MhaRowsArgs& a) {
+    if (a.Lk <= tc::AT_LKP_MAX || a.q_pad || !a.split_ws || a.k_count) return false;       // self-attention only (no quirk partner mask)
+    auto al = [](const float* p, int ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); };
+    return al(a.q, a.ldq) && al(a.k, a.ldk) && al(a.v, a.ldv) && (a.out ? al(a.out, a.ldo) : a.out_hi != nullptr);
+}
 
 bool attn_tc_eligible(const MhaRowsArgs& a) {
     if (a.Lk > tc::AT_LKP_MAX || a.Lk < 1) return false;

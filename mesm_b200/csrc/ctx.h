@@ -160,7 +160,7 @@ struct Planes { uint16_t* hi = nullptr; uint16_t* lo = nullptr; explicit operato
 struct PlaneIO { Planes in, out, ao, y1; bool wrote_out = false; /* set by the layer: `out` now holds its result */ };
 
 struct T2VBuffers { float *KV, *Q, *AO, *X1, *Y1, *H; };
-struct EncBuffers { float *QKV, *AO, *Y1, *H; };
+struct EncBuffers { float *QKV, *AO, *Y1, *H; float* split = nullptr; /* key-split attention scratch (attn_split_floats), Lv + 1 > 224 only */ };
 struct DecBuffers {
     float *tgtA, *tgtB, *ref, *refs, *sine, *sine_s, *h1, *h2, *qpos, *ptrans, *anc, *qsa, *ksa, *vsa, *ao, *t1, *qca,
         *sinep, *t2, *hff, *d2, *hs, *Kc, *Kp, *Vd, *tmpref;

@@ -21,7 +21,18 @@ struct MhaRowsArgs {
     int q_pad_ld = 0;          // 0 = Lq
     // optional: the result as bf16 hi / lo planes [rows, 256] (the A operand of the output projection on linear_tma.cu); `out` may then be null
     uint16_t* out_hi = nullptr; uint16_t* out_lo = nullptr;
+    // Key-split pass (tcgen05 kernel, self-attention with more keys than one 224-key tile, e.g. the shipped max_video_l = 600):
+    // only keys [k_begin, k_begin + k_count) of every pair are visited, the output is the chunk's own softmax-normalised result and
+    // split_stats[(row * 8 + head) * 2 + {0, 1}] = (row maximum, row sum of exp) lets launch_attn_combine merge the chunks exactly.
+    int k_begin = 0, k_count = 0;
+    float* split_stats = nullptr;
+    // caller-provided scratch for the key-split path: nchunks x (rows x 256 + rows x 16) floats (see attn_split_floats)
+    float* split_ws = nullptr;
+    long long split_rows = 0;   // total query rows of the launch (uniform: B * Lq; packed: the packed row count)
 };
+bool attn_tc_split_eligible(const MhaRowsArgs& a);
+cudaError_t launch_attn_tc_split(const MhaRowsArgs& a, long long rows, cudaStream_t s);
+size_t attn_split_floats(long long rows, int Lk);         // 0 when one key tile suffices
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_simt = false);      // dispatcher: tcgen05 kernel when eligible
 bool attn_tc_eligible(const MhaRowsArgs& a);
 cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s);

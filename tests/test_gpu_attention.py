@@ -48,6 +48,19 @@ def test_attention_kernels_match_reference(B, L):
         assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
 
 
+@pytest.mark.parametrize("B,L", [(3, 601), (2, 449), (5, 225), (4, 300)])
+def test_attention_key_split_matches_reference(B, L):
+    """More keys than one 224-key tile (the shipped max_video_l = 600 -> 601 encoder keys): one tcgen05 pass per key chunk + exact
+    merge of the chunk softmaxes (launch_attn_tc_split)."""
+    qkv, pad = _inputs(B, L, seed=L)
+    ref = _reference(qkv, pad, B, L)
+    out, wd = _run(qkv, pad, B, L, 2)
+    assert wd[0] == 0, wd
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 3e-5
+    simt, _ = _run(qkv, pad, B, L, 0)
+    assert float((simt.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
 def test_attention_tc_stress_no_stalled_barrier():
     """Many CTAs, two per SM, ragged key masks: the watchdog must stay silent and every launch must give the same bits."""
     B, L = 384, 195
