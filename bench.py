@@ -572,7 +572,7 @@ def main():
     # dominant kernel = the fused FFN (ffn_pair_kernel): 8 T2V launches on the clip rows + 4 encoder launches on clip rows + B per step
     ffn_n, ffn_ms = rep_rows.get("ffn_fused", (0, 0.0))
     if ffn_n:
-        ffn_flops = 4.0 * 256 * 1024 * (8.0 * clip_rows + 4.0 * (clip_rows + B)) * (ffn_n / 12.0)
+        ffn_flops = 4.0 * 256 * 1024 * (8.0 * clip_rows + 4.0 * (clip_rows + B))      # 12 layer passes over the step's rows (however chunked)
         ach = ffn_flops / (ffn_ms * 1e-3) / 1e12
         tr = traffic_tab.get("ffn_pair_kernel", {}).get("dram_bytes_per_row")
         roof = {"bound": "tensor", "kernel": "ffn_pair_kernel (fused FFN block, tcgen05 CTA pairs; bf16x3 = 3 MMAs per algorithmic MAC)",

@@ -70,9 +70,9 @@ class Engine:
         if not self.ctx:
             raise RuntimeError("mesm_create failed: " + self.lib.mesm_last_error(None).decode())
         # Pairs per internal chunk.  Large chunks keep the GEMM grids many waves deep (the tiles of a wave drift out of
-        # phase, so one CTA's epilogue overlaps its neighbour's K loop); 0 = auto: ~800 k clip rows per chunk (~20 GB of
+        # phase, so one CTA's epilogue overlaps its neighbour's K loop); 0 = auto: ~900 k padded clip rows per chunk (~25 GB of
         # workspace at d = 256), i.e. the whole 4096-pair Charades batch.
-        self.chunk_pairs = int(chunk_pairs) if chunk_pairs else max(64, 800_000 // max(1, int(c.max_video_l)))
+        self.chunk_pairs = int(chunk_pairs) if chunk_pairs else max(64, 900_000 // max(1, int(c.max_video_l)))
         self.lib.mesm_set_chunk_pairs(self.ctx, self.chunk_pairs)
         self._ws = None
         self._keep = []          # tensors that must outlive the asynchronous call that uses them
