@@ -152,6 +152,24 @@ int mesm_upload_clips_f16(const void* host_feat, const uint8_t* host_mask, int32
                           void* dev_feat, uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied,
                           void* stream);
 
+/* ---- CLIP text tower: replaces CLIPTextEncoder.forward (model/text_encoder.py:240-354), called by MESM.CLIP_encode_text
+ * (model/model.py:103-109).  State-dict keys as in the reference: token_embedding.weight [vocab,width], positional_embedding
+ * [context,width], transformer.resblocks.N.{ln_1,ln_2}.{weight,bias}, .attn.in_proj_{weight [3w,w],bias}, .attn.out_proj.*,
+ * .mlp.c_fc.* [4w,w], .mlp.c_proj.* [w,4w], ln_final.*, text_projection [width,embed_dim].  The reference computes in fp16; this
+ * runs fp32-in / fp32-out (bf16x3 products), text dev int64 [B,context]; last_hidden_state dev [B,context,width],
+ * pooler_output dev [B,embed_dim] (may be NULL) = ln_final(x)[b, argmax(text[b])] @ text_projection. */
+typedef struct mesm_clip mesm_clip;
+mesm_clip*  mesm_clip_create(int32_t width, int32_t heads, int32_t layers, int32_t context_length, int32_t vocab_size,
+                             int32_t embed_dim, int32_t device);
+void        mesm_clip_destroy(mesm_clip* c);
+const char* mesm_clip_last_error(const mesm_clip* c);
+int    mesm_clip_load_weight(mesm_clip* c, const char* key, const float* data, const int64_t* shape, int ndim, int is_device,
+                             void* stream);
+int    mesm_clip_finalize(mesm_clip* c, void* stream);
+size_t mesm_clip_workspace_bytes(const mesm_clip* c, int32_t B);
+int    mesm_clip_forward(mesm_clip* c, const int64_t* text, int32_t B, float* last_hidden_state, float* pooler_output,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- feature-ingest front-end: replaces get_video_feat (dataset/charades.py:108-119, dataset/qvhighlights.py:201-211) +
  * sample_video_feat (dataset/base.py:100-114) + add_tef (dataset/base.py:225-230) for ONE video.  raw: HOST array of S device
  * pointers to the raw per-source clip features [raw_len[s], dims[s]] (fp32, or fp16 when raw_f16; the reference upcasts on load);

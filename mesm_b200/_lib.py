@@ -57,6 +57,13 @@ SYMBOLS = {
                                   POINTER(c_int64), c_void_p]),
     "mesm_upload_clips_f16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_int32,
                                       POINTER(c_int64), c_void_p]),
+    "mesm_clip_create": (c_void_p, [c_int32] * 7),
+    "mesm_clip_destroy": (None, [c_void_p]),
+    "mesm_clip_last_error": (c_char_p, [c_void_p]),
+    "mesm_clip_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_int, c_void_p]),
+    "mesm_clip_finalize": (c_int, [c_void_p, c_void_p]),
+    "mesm_clip_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
+    "mesm_clip_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mesm_video_feat_rows": (c_int32, [POINTER(c_int32), c_int32, c_int32]),
     "mesm_video_feat_workspace_bytes": (c_size_t, [POINTER(c_int32), c_int32, c_int32]),
     "mesm_build_video_feat": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, c_int32, c_int32, c_int32,

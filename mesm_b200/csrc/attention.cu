@@ -213,7 +213,7 @@ __global__ void mha_small_kernel(const MhaSmallArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i0 + u < L) Sc[(i0 + u) * S + j] = masked ? -CUDART_INF_F : acc[u];
+                if (i0 + u < L) Sc[(i0 + u) * S + j] = (masked || (a.causal && j > i0 + u)) ? -CUDART_INF_F : acc[u];
         }
     }
     __syncthreads();
@@ -357,7 +357,7 @@ cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s) {
     if (a.B <= 0 || a.L <= 0) return cudaSuccess;
     static int cross_on = -1;
     if (cross_on < 0) { const char* e = getenv("MESM_DEC_CROSS"); cross_on = (e && e[0] == '0') ? 0 : 1; }
-    if (cross_on && dec_cross_eligible(a)) {
+    if (cross_on && !a.causal && dec_cross_eligible(a)) {
         ProfScope _ps("dec_cross", s);
         const size_t smem = (size_t)(10 * 512 + 8 * 10 * 32) * sizeof(float);
         dec_cross_kernel<10><<<a.B, 256, smem, s>>>(a);

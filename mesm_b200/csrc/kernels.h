@@ -52,6 +52,7 @@ struct MhaSmallArgs {
     // indexed (k_cu[b]-k_cu[0]) + j.  S stays the maximum over the pairs (shared-memory sizing).
     const int* k_cu = nullptr; int k_enc = 0;
     const int* k2_table = nullptr;   // k2 row of key row r is k2_table[r] (position-term table) instead of r
+    int causal = 0;                  // 1: key j is masked for query i when j > i (CLIP text tower, model/text_encoder.py:321-327)
 };
 cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s);
 

@@ -8,6 +8,7 @@
     model/transformer.py:119  Transformer      Transformer        -> mesm_transformer
     model/attention.py:61     MultiheadAttention MultiheadAttention -> mesm_mha_noproj
     model/position_encoding.py:35 PositionEmbeddingSine (parameter-free; the fused forward computes it on the fly)
+    model/text_encoder.py:240 CLIPTextEncoder  CLIPTextEncoder    -> mesm_clip_forward
     runner.py:255-298         build_model      build_model
 
 The nn.Modules below only *hold parameters* under the reference's names; no torch op touches the hot path.  Inference
@@ -171,7 +172,8 @@ class _EngineBacked(nn.Module):
         if eng is None or self.__dict__.get("_eng_sig") != sig:
             if eng is None or str(eng.device) != str(device):
                 eng = Engine(self._engine_cfg(), device=device, chunk_pairs=self.__dict__.get("chunk_pairs", 0))
-            eng.load_state_dict({self._prefix + k: v for k, v in self.state_dict().items()})
+            # (checkpoints omit text_encoder.*, utils/model_utils.py:20-36; a CLIP / GloVe front-end keeps its own weights)
+            eng.load_state_dict({self._prefix + k: v for k, v in self.state_dict().items() if not k.startswith("text_encoder.")})
             self.__dict__["_eng"] = eng
             self.__dict__["_eng_sig"] = (str(device), self._weights_signature())
         return eng
@@ -361,6 +363,107 @@ class GloveTextEncoder(nn.Module):
         return self.emb(word_ids)
 
 
+class _ClipBlock(nn.Module):
+    """ResidualAttentionBlock (model/text_encoder.py:165-186), parameters only."""
+
+    def __init__(self, d_model):
+        super().__init__()
+        self.attn = _PackedMHA(d_model)
+        self.ln_1 = nn.LayerNorm(d_model)
+        self.mlp = nn.Sequential()
+        self.mlp.add_module("c_fc", nn.Linear(d_model, d_model * 4))
+        self.mlp.add_module("c_proj", nn.Linear(d_model * 4, d_model))
+        self.ln_2 = nn.LayerNorm(d_model)
+
+
+class _ClipTransformer(nn.Module):
+    def __init__(self, width, layers, heads):
+        super().__init__()
+        self.width, self.layers, self.heads = width, layers, heads
+        self.resblocks = nn.Sequential(*[_ClipBlock(width) for _ in range(layers)])
+
+
+class CLIPTextEncoder(nn.Module):
+    """Drop-in for model/text_encoder.py:240-354 (same constructor, state_dict keys and output dict).  forward(text int64 [B, 77])
+    -> dict(last_hidden_state [B, 77, width], pooler_output [B, embed_dim]); the whole tower runs in libmesm_b200.so
+    (mesm_clip_forward) in fp32 with bf16x3 products - the reference computes the same graph in fp16."""
+
+    def __init__(self, embed_dim, context_length, vocab_size, transformer_width, transformer_heads, transformer_layers):
+        super().__init__()
+        self.context_length, self.vocab_size, self.embed_dim = context_length, vocab_size, embed_dim
+        self.transformer = _ClipTransformer(transformer_width, transformer_layers, transformer_heads)
+        self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+        self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width))
+        self.ln_final = nn.LayerNorm(transformer_width)
+        self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
+        self.initialize_parameters()
+
+    def initialize_parameters(self):            # model/text_encoder.py:297-319
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        w, n = self.transformer.width, self.transformer.layers
+        proj_std, attn_std, fc_std = (w ** -0.5) * ((2 * n) ** -0.5), w ** -0.5, (2 * w) ** -0.5
+        for block in self.transformer.resblocks:
+            nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(block.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=w ** -0.5)
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def _ctx(self, device):
+        lib = _lib.lib()
+        sig = tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
+        if getattr(self, "_clip", None) is None or self._clip_sig != sig or self._clip_dev != device:
+            if getattr(self, "_clip", None):
+                lib.mesm_clip_destroy(self._clip)
+            t = self.transformer
+            with torch.cuda.device(device):
+                c = lib.mesm_clip_create(t.width, t.heads, t.layers, self.context_length, self.vocab_size, self.embed_dim, device.index or 0)
+                if not c:
+                    raise RuntimeError("mesm_clip_create failed: " + lib.mesm_clip_last_error(None).decode())
+                keep = []
+                for k, v in self.state_dict().items():
+                    w = v.detach().to(device=device, dtype=torch.float32).contiguous()
+                    keep.append(w)
+                    shape = (ctypes.c_int64 * max(w.dim(), 1))(*w.shape)
+                    if lib.mesm_clip_load_weight(c, k.encode(), _ptr(w), shape, w.dim(), 1, _stream()) != 0:
+                        raise RuntimeError(lib.mesm_clip_last_error(c).decode())
+                if lib.mesm_clip_finalize(c, _stream()) != 0:
+                    raise RuntimeError(lib.mesm_clip_last_error(c).decode())
+            self.__dict__["_clip"], self.__dict__["_clip_sig"], self.__dict__["_clip_dev"] = c, sig, device
+        return self._clip
+
+    def __del__(self):
+        try:
+            if getattr(self, "_clip", None):
+                _lib.lib().mesm_clip_destroy(self._clip)
+        except Exception:
+            pass
+
+    @torch.no_grad()
+    def forward(self, text):
+        if not text.is_cuda:
+            raise RuntimeError("mesm_b200: `text` must be a CUDA tensor (no CPU fallback)")
+        lib = _lib.lib()
+        dev = text.device
+        c = self._ctx(dev)
+        text = text.to(torch.int64).contiguous()
+        B = text.shape[0]
+        if text.shape[1] != self.context_length:
+            raise RuntimeError("CLIPTextEncoder: text must be [B, context_length]")
+        x = torch.empty(B, self.context_length, self.transformer.width, dtype=torch.float32, device=dev)
+        pooled = torch.empty(B, self.embed_dim, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = torch.empty(lib.mesm_clip_workspace_bytes(c, B), dtype=torch.uint8, device=dev)
+            if lib.mesm_clip_forward(c, _ptr(text), B, _ptr(x), _ptr(pooled), _ptr(ws), ws.numel(), _stream()) != 0:
+                raise RuntimeError(lib.mesm_clip_last_error(c).decode())
+        return dict(last_hidden_state=x, pooler_output=pooled)
+
+
 def sample_outclass_neg(num_clips, generator=None):
     """Vectorised equivalent of utils/data_utils.py:113-124: per pair a uniformly random pair of another video group.
     (Same distribution; the reference's per-pair torch.randperm stream is not reproduced — inject ``neg_index`` for
@@ -393,9 +496,8 @@ class MESM(_EngineBacked):
         if use_txt_pos or not normalize_txt or span_loss_type != "l1" or n_input_proj != 2:
             raise NotImplementedError("only the settings of the shipped configs are implemented "
                                       "(use_txt_pos=False, normalize_txt=True, span_loss_type='l1', n_input_proj=2)")
-        if text_encoder is not None and not isinstance(text_encoder, GloveTextEncoder):
-            raise NotImplementedError("text_encoder must be None (word features in `words_id`) or a GloveTextEncoder; the CLIP "
-                                      "text tower is in front of this path (SURVEY §8f)")
+        if text_encoder is not None and not isinstance(text_encoder, (GloveTextEncoder, CLIPTextEncoder)):
+            raise NotImplementedError("text_encoder must be None (word features in `words_id`), a GloveTextEncoder or a CLIPTextEncoder")
         self.text_encoder = text_encoder
         self.enhance_encoder = enhance_encoder
         self.t2v_encoder = t2v_encoder
@@ -444,7 +546,7 @@ class MESM(_EngineBacked):
 
     # sub-engines of the child modules are not used by the fused forward: one context holds the whole state_dict
     def _weights_signature(self):
-        return (self._dataset_name,) + super()._weights_signature()
+        return (self._dataset_name,) + tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if not n.startswith("text_encoder."))
 
     def _engine_cfg(self):
         tr = self.transformer
@@ -472,6 +574,9 @@ class MESM(_EngineBacked):
         self._dataset_name = "qvhighlights" if name == "qvhighlights" else "charades"
         if isinstance(self.text_encoder, GloveTextEncoder):          # model/model.py:136-143 up to the normalise
             words_feat = self.text_encoder(words_id).masked_fill(words_mask.unsqueeze(-1) == False, 0)  # noqa: E712
+        elif isinstance(self.text_encoder, CLIPTextEncoder):         # CLIP_encode_text, model/model.py:103-125 up to the normalise
+            words_feat = self.text_encoder(words_id)["last_hidden_state"][:, :self.max_words_l, :]
+            words_feat = words_feat.masked_fill(words_mask[:, :self.max_words_l].unsqueeze(-1) == False, 0)  # noqa: E712
         else:
             words_feat = words_id
         eng = self._engine(video_feat.device)

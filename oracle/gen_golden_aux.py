@@ -135,8 +135,30 @@ def metrics_cases():
     return out
 
 
+def clip_cases():
+    """The reference's CLIPTextEncoder (model/text_encoder.py:240-354) on seeded weights / tokens: once as shipped (fp16 weights via
+    convert_weights, fp16 activations) and once with its `dtype` property overridden to float32 (the same graph in fp32: what the
+    fp16 run approximates).  The first 32 token rows (max_words_l) and the pooled output are stored."""
+    import copy
+    sys.path.insert(0, REF)
+    from model.text_encoder import CLIPTextEncoder, convert_weights
+    from oracle.weights import CLIP_TEXT_CFG, make_clip_state_dict, make_clip_tokens
+    sd, text = make_clip_state_dict(3), make_clip_tokens(5, 4)
+    ref16 = CLIPTextEncoder(**CLIP_TEXT_CFG).eval()
+    ref16.load_state_dict(sd, strict=True)
+    ref32 = type("CLIPTextEncoderF32", (CLIPTextEncoder,), {"dtype": property(lambda self: torch.float32)})(**CLIP_TEXT_CFG).eval()
+    ref32.load_state_dict(sd, strict=True)
+    convert_weights(ref16)
+    o32, o16 = ref32(text), ref16(text)
+    d = (o16["last_hidden_state"].float() - o32["last_hidden_state"]).abs().max() / o32["last_hidden_state"].abs().max()
+    print(f"clip text tower: fp16 run vs fp32 run of the reference module: {float(d):.2e} relative")
+    return dict(clip_hidden_f32=o32["last_hidden_state"][:, :32].numpy(), clip_pooled_f32=o32["pooler_output"].numpy(),
+                clip_hidden_f16=o16["last_hidden_state"][:, :32].numpy(), clip_pooled_f16=o16["pooler_output"].numpy())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "clip_text.npz"), **clip_cases())
     np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **metrics_cases())
     np.savez_compressed(os.path.join(GOLD, "criterion_saliency.npz"), **criterion_cases())
     np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **frontend_cases())

@@ -225,3 +225,42 @@ def make_raw_features(name):
     g = torch.Generator().manual_seed(_key_seed(7, "frontend:" + name))
     raws = [torch.randn(n, d, generator=g) * (1 + i) for i, (n, d) in enumerate(zip(lens, dims))]
     return [r.half() if f16 else r for r in raws], max_l
+
+
+CLIP_TEXT_CFG = dict(embed_dim=512, context_length=77, vocab_size=1000, transformer_width=512, transformer_heads=8, transformer_layers=12)
+
+
+def make_clip_state_dict(seed=0, cfg=None):
+    """Seeded state_dict of a CLIPTextEncoder (model/text_encoder.py:240-354; the shipped ViT-B/32 text tower shape with a small
+    vocabulary), per-key generators like make_state_dict; std per tensor kind as initialize_parameters (:297-319) so that the
+    activations have realistic magnitudes."""
+    c = cfg or CLIP_TEXT_CFG
+    W, n = c["transformer_width"], c["transformer_layers"]
+    spec = [("token_embedding.weight", (c["vocab_size"], W), 0.02), ("positional_embedding", (c["context_length"], W), 0.01),
+            ("ln_final.weight", (W,), None), ("ln_final.bias", (W,), 0.02), ("text_projection", (W, c["embed_dim"]), W ** -0.5)]
+    for l in range(n):
+        p = f"transformer.resblocks.{l}."
+        spec += [(p + "attn.in_proj_weight", (3 * W, W), W ** -0.5), (p + "attn.in_proj_bias", (3 * W,), 0.02),
+                 (p + "attn.out_proj.weight", (W, W), (W ** -0.5) * ((2 * n) ** -0.5)), (p + "attn.out_proj.bias", (W,), 0.02),
+                 (p + "ln_1.weight", (W,), None), (p + "ln_1.bias", (W,), 0.02), (p + "ln_2.weight", (W,), None), (p + "ln_2.bias", (W,), 0.02),
+                 (p + "mlp.c_fc.weight", (4 * W, W), (2 * W) ** -0.5), (p + "mlp.c_fc.bias", (4 * W,), 0.02),
+                 (p + "mlp.c_proj.weight", (W, 4 * W), (W ** -0.5) * ((2 * n) ** -0.5)), (p + "mlp.c_proj.bias", (W,), 0.02)]
+    sd = {}
+    for k, shape, std in spec:
+        g = torch.Generator().manual_seed(_key_seed(seed, "clip:" + k))
+        sd[k] = (1.0 + 0.1 * torch.randn(shape, generator=g)) if std is None else torch.randn(shape, generator=g) * std
+    return sd
+
+
+def make_clip_tokens(B=5, seed=0, cfg=None):
+    """Token ids [B, 77]: sot, words, eot = the largest id of the row (text.argmax picks it, :346), zero padding."""
+    c = cfg or CLIP_TEXT_CFG
+    g = torch.Generator().manual_seed(_key_seed(seed, "clip:tokens"))
+    V, L = c["vocab_size"], c["context_length"]
+    text = torch.zeros(B, L, dtype=torch.int64)
+    for b in range(B):
+        n = int(torch.randint(3, 31, (1,), generator=g))
+        text[b, 0] = V - 2
+        text[b, 1:n + 1] = torch.randint(1, V - 2, (n,), generator=g)
+        text[b, n + 1] = V - 1
+    return text

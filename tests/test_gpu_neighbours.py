@@ -66,3 +66,48 @@ def test_moment_retrieval_metrics_match_reference(golden_dir, name):
             assert sorted(res[rng_name][fam]) == sorted(ref[rng_name][fam]), (rng_name, fam)
             for k, v in ref[rng_name][fam].items():
                 assert res[rng_name][fam][k] == v, (rng_name, fam, k, res[rng_name][fam][k], v)       # 2-decimal percents: exact
+
+
+def test_clip_text_tower_matches_reference(golden_dir):
+    """CLIPTextEncoder (model/text_encoder.py:240-354; 12 x 512, 8 heads, 77 tokens, causal): our fp32 / bf16x3 run against the
+    reference module evaluated in fp32 (tight) and as shipped in fp16 (the reference's own rounding: 1.7e-3 from its fp32 run)."""
+    from mesm_b200.model import CLIPTextEncoder
+    from oracle.weights import CLIP_TEXT_CFG, make_clip_state_dict, make_clip_tokens
+    g = np.load(os.path.join(golden_dir, "clip_text.npz"))
+    enc = CLIPTextEncoder(**CLIP_TEXT_CFG)
+    enc.load_state_dict(make_clip_state_dict(3), strict=True)
+    enc = enc.cuda().eval()
+    out = enc(make_clip_tokens(5, 4).cuda())
+    h, p = out["last_hidden_state"][:, :32].cpu(), out["pooler_output"].cpu()
+    assert out["last_hidden_state"].shape == (5, 77, 512) and not torch.isnan(out["last_hidden_state"]).any()
+    rel = lambda a, b: float((a.double() - torch.from_numpy(b).double()).abs().max() / np.abs(b).max())
+    assert rel(h, g["clip_hidden_f32"]) < 1e-4 and rel(p, g["clip_pooled_f32"]) < 1e-4
+    assert rel(h, g["clip_hidden_f16"].astype(np.float32)) < 5e-3 and rel(p, g["clip_pooled_f16"].astype(np.float32)) < 5e-3
+
+
+def test_mesm_forward_with_clip_text_encoder():
+    """MESM with a CLIPTextEncoder (the C+SF configs): words_id are token ids; equals feeding the tower's masked hidden states as word
+    features (CLIP_encode_text, model/model.py:103-125)."""
+    from mesm_b200.model import CLIPTextEncoder, build_model
+    from oracle.config import CONFIGS
+    from oracle.weights import CLIP_TEXT_CFG, make_clip_state_dict, make_clip_tokens, make_inputs, make_state_dict
+    from tests.helpers import engine_cfg
+    cfg = CONFIGS["qvhighlights"]
+    nc = [2, 1, 2]
+    inp = make_inputs(cfg, nc, 2)
+    m = build_model(engine_cfg(cfg))
+    m.load_state_dict(make_state_dict(cfg, 1), strict=True)
+    enc = CLIPTextEncoder(**CLIP_TEXT_CFG)
+    enc.load_state_dict(make_clip_state_dict(3), strict=True)
+    m = m.cuda().eval()
+    enc = enc.cuda().eval()
+    text = make_clip_tokens(5, 4).cuda()
+    wmask = (text != 0)
+    feats = enc(text)["last_hidden_state"][:, :cfg.max_words_l].masked_fill(~wmask[:, :cfg.max_words_l, None], 0)
+    a = m(inp["video_feat"].cuda(), inp["video_mask"].cuda(), feats, None, None, inp["num_clips"], dataset_name="qvhighlights", is_training=False,
+          neg_index=torch.tensor([2, 3, 0, 0, 1]).cuda())
+    m.text_encoder = enc
+    b = m(inp["video_feat"].cuda(), inp["video_mask"].cuda(), text, wmask, None, inp["num_clips"], dataset_name="qvhighlights", is_training=False,
+          neg_index=torch.tensor([2, 3, 0, 0, 1]).cuda())
+    for k in ("pred_logits", "pred_spans", "saliency_scores"):
+        assert torch.equal(a[k], b[k]), k
