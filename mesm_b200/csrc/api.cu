@@ -179,18 +179,19 @@ int fail(mesm_ctx* c, int code, const std::string& msg) {
 // FFN block of a layer: out = LN2(res + W2 PReLU(W1 x + b1) + b2).  One fused tcgen05 kernel when the shape allows
 // (MESM_FFN_FUSED=0 keeps the two-GEMM path, which also serves small row counts).
 cudaError_t ffn_block(const AttnFfn& L, int R, const float* x, const float* res, float* H, float* out, int ldo, RowMap omap,
-                      cudaStream_t s, Planes xp = Planes(), Planes outp = Planes()) {
+                      cudaStream_t s, Planes xp = Planes(), Planes outp = Planes(), const float* ln1_stats = nullptr, bool res_ln1 = false) {
     static int fused = -1;
     if (fused < 0) { const char* e = getenv("MESM_FFN_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
     FfnArgs a;
     a.X = x; a.ldx = D; a.R = res; a.ldr = D; a.out = out; a.ldo = ldo; a.omap = omap; a.M = R;
     a.W1f = L.ffn_w1; a.W2f = L.ffn_w2; a.maps = L.ffn_maps; a.b1 = L.l1.bias; a.b2 = L.l2.bias; a.ln_g = L.n2.g; a.ln_b = L.n2.b; a.prelu = L.prelu;
     a.x_hi = xp.hi; a.x_lo = xp.lo; a.out_hi = outp.hi; a.out_lo = outp.lo;
+    if (ln1_stats) { a.ln1_stats = ln1_stats; a.ln1_g = L.n1.g; a.ln1_b = L.n1.b; a.res_ln1 = res_ln1 ? 1 : 0; }   // x (and res) are PRE-LayerNorm-1 rows
     if (fused && ffn_fused_eligible(a)) {
         ProfScope _ps("ffn_fused", s, 4.0 * R * (double)D * FF, R);
         return launch_ffn_fused(a, s);
     }
-    if (xp || outp) return cudaErrorInvalidValue;              // the plane flow is only set up where the fused kernel runs
+    if (xp || outp || ln1_stats) return cudaErrorInvalidValue;  // the plane flow is only set up where the fused kernel runs
     MESM_CHECK(Lin(R, L.l1, x, D, H, FF).act(ACT_PRELU, L.prelu).run(s));
     MESM_CHECK(Lin(R, L.l2, H, FF, out, ldo).omap(omap).res(res, D).ln(L.n2).run(s));
     return cudaSuccess;
@@ -201,6 +202,9 @@ cudaError_t ffn_block(const AttnFfn& L, int R, const float* x, const float* res,
 // launches): a tile's start-up is bound by the HBM burst of a whole wave asking for its X rows at once, not by the conversion.
 // MESM_FFN_OUTP=0 stops the FFN from storing its result as planes (the next layer then falls back to fp32 operands).
 static bool ffn_x_f32() { static int v = -1; if (v < 0) { const char* e = getenv("MESM_FFN_X"); v = (e && e[0] == 'p') ? 0 : 1; } return v == 1; }
+// MESM_FFN_LN1=0: the output projection normalises (LN1) and stores the result for the FFN, as in round 1; default: it stores only the
+// pre-LN rows and their (mean, rstd), and the fused FFN applies LayerNorm-1 while it converts its X operand
+static bool ffn_ln1_fused() { static int v = -1; if (v < 0) { const char* e = getenv("MESM_FFN_LN1"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 static bool ffn_outp_off() { static int v = -1; if (v < 0) { const char* e = getenv("MESM_FFN_OUTP"); v = (e && e[0] == '0') ? 1 : 0; } return v == 1; }
 
 // the plane flow needs the fused FFN (M > 128 rows), its weight images and the TMA weight planes of the layer
@@ -242,10 +246,18 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
     if (pl) {
         // out-proj (+ residual, pre-LN copy, LN1) on the TMA-fed kernel; LN1's result only exists as the FFN's operand planes
         const bool xf = ffn_x_f32();
+        if (ffn_outp_off()) pio->wrote_out = false;
+        const Planes outp = pio->wrote_out ? pio->out : Planes();
+        if (xf && ffn_ln1_fused()) {
+            // out-proj (+ residual) stores src2 = vid + attn (pre-LN) and its row statistics; LN1 happens inside the FFN's converter:
+            // LN1's output never exists in HBM (1 KB/row written + read back per layer in round 1)
+            MESM_CHECK(Lin(Rv, L.out, nullptr, D, nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(vid, D).pre_ln(t.X1).ln_stats(t.H).run(s));
+            MESM_CHECK(ffn_block(L, Rv, t.X1, t.X1, nullptr, out, ldo, omap, s, Planes(), outp, t.H, false));
+            return cudaSuccess;
+        }
         MESM_CHECK(Lin(Rv, L.out, nullptr, D, xf ? t.Y1 : nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(vid, D).pre_ln(t.X1).ln(L.n1)
                        .oplanes(xf ? nullptr : pio->y1.hi, xf ? nullptr : pio->y1.lo, D).run(s));
-        if (ffn_outp_off()) pio->wrote_out = false;
-        MESM_CHECK(ffn_block(L, Rv, xf ? t.Y1 : nullptr, t.X1, t.H, out, ldo, omap, s, xf ? Planes() : pio->y1, pio->wrote_out ? pio->out : Planes()));
+        MESM_CHECK(ffn_block(L, Rv, xf ? t.Y1 : nullptr, t.X1, t.H, out, ldo, omap, s, xf ? Planes() : pio->y1, outp));
         return cudaSuccess;
     }
     MESM_CHECK(Lin(Rv, L.out, t.AO, D, t.Y1, D).res(vid, D).pre_ln(t.X1).ln(L.n1).run(s));
@@ -282,10 +294,17 @@ cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, cons
     if (pl) {
         // LN1's result is both the FFN's operand (planes) and its residual (fp32)
         const bool xf = ffn_x_f32();
+        if (ffn_outp_off()) pio->wrote_out = false;
+        const Planes outp = pio->wrote_out ? pio->out : Planes();
+        if (xf && ffn_ln1_fused()) {
+            // pre-LN rows + statistics only; the FFN normalises them for its X operand AND for its residual (LN1's result is both)
+            MESM_CHECK(Lin(R, L.out, nullptr, D, nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(src, D).pre_ln(t.Y1).ln_stats(t.H).run(s));
+            MESM_CHECK(ffn_block(L, R, t.Y1, t.Y1, nullptr, out, D, identity_map(), s, Planes(), outp, t.H, true));
+            return cudaSuccess;
+        }
         MESM_CHECK(Lin(R, L.out, nullptr, D, t.Y1, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(src, D).ln(L.n1)
                        .oplanes(xf ? nullptr : pio->y1.hi, xf ? nullptr : pio->y1.lo, D).run(s));
-        if (ffn_outp_off()) pio->wrote_out = false;
-        MESM_CHECK(ffn_block(L, R, xf ? t.Y1 : nullptr, t.Y1, t.H, out, D, identity_map(), s, xf ? Planes() : pio->y1, pio->wrote_out ? pio->out : Planes()));
+        MESM_CHECK(ffn_block(L, R, xf ? t.Y1 : nullptr, t.Y1, t.H, out, D, identity_map(), s, xf ? Planes() : pio->y1, outp));
         return cudaSuccess;
     }
     MESM_CHECK(Lin(R, L.out, t.AO, D, t.Y1, D).res(src, D).ln(L.n1).run(s));
@@ -441,7 +460,7 @@ cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) {
     if (op.a_hi) {                                     // A as pre-split planes: the TMA-fed kernel is the only consumer
         if (!linear_tma_eligible(op)) return cudaErrorInvalidValue;
         const double fl = 2.0 * op.M * (double)op.N * (double)op.K;
-        ProfScope ps(op.a_lo ? (op.ln_g ? "linear_tma +LN" : "linear_tma") : "input_proj linear_tma fp16 features", s, fl, op.M);
+        ProfScope ps(op.a_lo ? (op.ln_g ? "linear_tma +LN" : (op.ln_stats ? "linear_tma +LN stats" : "linear_tma")) : "input_proj linear_tma fp16 features", s, fl, op.M);
         return launch_linear_tma(op, s);
     }
     const bool tc = !force_simt() && linear_tc_eligible(op);

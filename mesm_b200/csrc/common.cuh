@@ -66,6 +66,8 @@ struct LinearOp {
     float* out; int ldo; RowMap omap;
     float* out2; int ldo2; RowMap o2map;          // optional duplicate store of the final value
     float* pre_ln;                                // optional store of the value before LayerNorm ([M,N], ld = N)
+    float* ln_stats;                              // linear_tma only: store (mean, rstd) of the pre-LayerNorm row ([M,2]) INSTEAD of normalising -
+                                                  // the consumer (fused FFN) applies LayerNorm itself, so the normalised copy never touches HBM
     int nbatch;                                   // >1: blockIdx.z batches (per-head GEMMs); element strides below
     long long bsA, bsW, bsBias, bsOut;
     // Pre-split 16-bit planes: an activation x is stored as hi = bf16(x) and lo = bf16(x - hi), two row-major
@@ -82,7 +84,7 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
     op.Wt = Wt; op.ldw = ldw; op.Wp = nullptr; op.Wp2 = nullptr; op.K2 = 0; op.A2 = nullptr; op.lda2 = 0; op.a2map = identity_map(); op.Wt2 = nullptr;
     op.bias = bias; op.rowstat = nullptr; op.fuse_rowstat = 0; op.colsum = nullptr; op.out_scale = 1.f; op.act = ACT_NONE; op.prelu = nullptr;
     op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
-    op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr;
+    op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr; op.ln_stats = nullptr;
     op.nbatch = 1; op.bsA = op.bsW = op.bsBias = op.bsOut = 0;
     op.a_hi = op.a_lo = nullptr; op.lda_p = 0; op.out_hi = op.out_lo = nullptr; op.ldp = 0; op.Wtm = nullptr;
     return op;

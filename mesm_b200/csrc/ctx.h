@@ -143,6 +143,7 @@ struct Lin {    // thin builder around LinearOp
     Lin& res(const float* r, int ldr, RowMap m = identity_map()) { op.residual = r; op.ldr = ldr; op.rmap = m; return *this; }
     Lin& ln(const Norm& n) { op.ln_g = n.g; op.ln_b = n.b; return *this; }
     Lin& pre_ln(float* p) { op.pre_ln = p; return *this; }
+    Lin& ln_stats(float* p) { op.ln_stats = p; return *this; }
     Lin& batch(int n, long long sA, long long sW, long long sBias, long long sOut) {
         op.nbatch = n; op.bsA = sA; op.bsW = sW; op.bsBias = sBias; op.bsOut = sOut; return *this;
     }

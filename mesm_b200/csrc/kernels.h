@@ -131,6 +131,10 @@ struct FfnArgs {
     // result also as planes with the row mapping of `out` (needs ldo == 256; `out` may be null)
     const uint16_t* x_hi = nullptr; const uint16_t* x_lo = nullptr;
     uint16_t* out_hi = nullptr; uint16_t* out_lo = nullptr;
+    // LayerNorm-1 fused into the prologue (optional): X holds the PRE-LayerNorm rows, ln1_stats their (mean, rstd) [M,2] as written by the
+    // output projection (LinearOp::ln_stats); the kernel normalises while it converts X, so LN1's output never exists in HBM.
+    // res_ln1 = 1 (encoder layers): the residual is LN1(R) as well (R = the same pre-LN rows), recomputed in the epilogue.
+    const float* ln1_g = nullptr; const float* ln1_b = nullptr; const float* ln1_stats = nullptr; int res_ln1 = 0;
 };
 size_t ffn_packed_bytes();
 cudaError_t launch_pack_ffn(const float* W1, const float* W2, void* W1f, void* W2f, cudaStream_t s);

@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
         const int half = (warp - 2) >> 2;                  // column half handled by this warp
         const int row = q * 32 + lane;
         const float slope_eff = op.act == ACT_PRELU ? __ldg(op.prelu) : (op.act == ACT_RELU ? 0.f : 1.f);
-        const bool do_ln = op.ln_g != nullptr;
+        const bool do_ln = op.ln_g != nullptr || op.ln_stats != nullptr;
+        const bool stats_only = op.ln_stats != nullptr;      // (mean, rstd) of the pre-LN row for the consumer; nothing normalised here
         float* T = reinterpret_cast<float*>(smem + OFF_T) + (warp - 2) * (32 * 36);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         const int trow0 = q * 32;
@@ -298,12 +299,21 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
                 for (int c = 0; c < 4; ++c) {
                     float v[32];
                     tmem_ld32(taddr0 + c * 32, v);
+                    if (stats_only && c == 3) {                // last TMEM read of this accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; sq = fmaf(d, d, sq); }
                 }
                 ln_x[half * 128 + row] = sq;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const float rs = rsqrtf((ln_x[row] + ln_x[128 + row]) * (1.f / 256.f) + 1e-5f);
+                if (stats_only) {
+                    if (half == 0 && mok) { op.ln_stats[2 * (long long)m] = mu; op.ln_stats[2 * (long long)m + 1] = rs; }
+                    continue;                                  // next tile (the top-of-loop barrier protects ln_x)
+                }
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n = n0 + half * 128 + c * 32;
@@ -452,13 +462,14 @@ bool linear_tma_eligible(const LinearOp& op) {
     if (w->K != op.K || w->N != op.N || (op.N % tma::BN) != 0) return false;
     if (w->fp16 != (op.a_lo == nullptr)) return false;                 // single fp16 plane <-> fp16 weight planes
     if (op.M < 1 || op.amap.group != 0 || op.amap.table != nullptr) return false;
-    if (op.ln_g && op.N != 256) return false;
+    if ((op.ln_g || op.ln_stats) && op.N != 256) return false;
+    if (op.ln_stats && (op.ln_g || !op.pre_ln)) return false;          // stats-only: the pre-LN rows are the only output
     if (op.act == ACT_SIGMOID) return false;
     if ((op.lda_p & 7) || (reinterpret_cast<uintptr_t>(op.a_hi) & 15) || (op.a_lo && (reinterpret_cast<uintptr_t>(op.a_lo) & 15))) return false;
     auto al16 = [](const void* p, long long ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); };
     if (!al16(op.out, op.ldo) || !al16(op.out2, op.ldo2) || !al16(op.residual, op.ldr) || !al16(op.pre_ln, op.N)) return false;
     if (op.out_hi && ((op.ldp & 3) || (reinterpret_cast<uintptr_t>(op.out_hi) & 7) || (reinterpret_cast<uintptr_t>(op.out_lo) & 7))) return false;
-    if (!op.out && !op.out_hi) return false;
+    if (!op.out && !op.out_hi && !op.ln_stats) return false;
     return true;
 }
 
