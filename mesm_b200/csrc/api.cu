@@ -221,7 +221,8 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
                       int Rv_packed, int q_pad_ld, const float* posW, const int* t_pos, PlaneIO* pio) {
     const int Rt = Bc * Lk, Rv = cu ? Rv_packed : Bc * Lq;
     const bool pl = planes_ok(L, Rv, pio) && ldo == D;
-    if (pio) pio->wrote_out = pl && pio->out;
+    if (pio) { pio->wrote_out = pl && pio->out; pio->wrote_fp32 = true; }
+    if (!vid && !(pl && pio->in && posW && ffn_x_f32() && ffn_ln1_fused())) return cudaErrorInvalidValue;     // planes-only input needs the full plane path
     if (pos_txt) {
         PL kw = L.kv; kw.N = D; kw.Wtm = nullptr;
         MESM_CHECK(Lin(Rt, kw, txt, D, t.KV, 2 * D).amap(tmap).apos(pos_txt).run(s));
@@ -251,8 +252,13 @@ cudaError_t t2v_layer(const AttnFfn& L, const float* txt, RowMap tmap, const flo
         if (xf && ffn_ln1_fused()) {
             // out-proj (+ residual) stores src2 = vid + attn (pre-LN) and its row statistics; LN1 happens inside the FFN's converter:
             // LN1's output never exists in HBM (1 KB/row written + read back per layer in round 1)
-            MESM_CHECK(Lin(Rv, L.out, nullptr, D, nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(vid, D).pre_ln(t.X1).ln_stats(t.H).run(s));
-            MESM_CHECK(ffn_block(L, Rv, t.X1, t.X1, nullptr, out, ldo, omap, s, Planes(), outp, t.H, false));
+            Lin op_(Rv, L.out, nullptr, D, nullptr, D);
+            op_.aplanes(pio->ao.hi, pio->ao.lo, D).pre_ln(t.X1).ln_stats(t.H);
+            if (vid) op_.res(vid, D); else op_.res_planes(pio->in.hi, pio->in.lo);
+            MESM_CHECK(op_.run(s));
+            const bool po = pio->planes_only && outp;                       // intermediate layer: the next consumer reads planes only
+            pio->wrote_fp32 = !po;
+            MESM_CHECK(ffn_block(L, Rv, t.X1, t.X1, nullptr, po ? nullptr : out, ldo, omap, s, Planes(), outp, t.H, false));
             return cudaSuccess;
         }
         MESM_CHECK(Lin(Rv, L.out, nullptr, D, xf ? t.Y1 : nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(vid, D).pre_ln(t.X1).ln(L.n1)
@@ -271,7 +277,8 @@ cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, cons
                       const int* t_pos, PlaneIO* pio) {
     const int R = cu ? R_packed : Bc * L1;
     const bool pl = planes_ok(L, R, pio) && pio->in && posW;
-    if (pio) pio->wrote_out = pl && pio->out;
+    if (pio) { pio->wrote_out = pl && pio->out; pio->wrote_fp32 = true; }
+    if (!src && !(pl && ffn_x_f32() && ffn_ln1_fused())) return cudaErrorInvalidValue;
     {
         Lin qk(R, L.qk, src, D, t.QKV, 3 * D);
         if (posW) qk.res(posW, 2 * D, table_map(t_pos)); else qk.apos(pos);
@@ -298,8 +305,13 @@ cudaError_t enc_layer(const AttnFfn& L, const float* src, const float* pos, cons
         const Planes outp = pio->wrote_out ? pio->out : Planes();
         if (xf && ffn_ln1_fused()) {
             // pre-LN rows + statistics only; the FFN normalises them for its X operand AND for its residual (LN1's result is both)
-            MESM_CHECK(Lin(R, L.out, nullptr, D, nullptr, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(src, D).pre_ln(t.Y1).ln_stats(t.H).run(s));
-            MESM_CHECK(ffn_block(L, R, t.Y1, t.Y1, nullptr, out, D, identity_map(), s, Planes(), outp, t.H, true));
+            Lin op_(R, L.out, nullptr, D, nullptr, D);
+            op_.aplanes(pio->ao.hi, pio->ao.lo, D).pre_ln(t.Y1).ln_stats(t.H);
+            if (src) op_.res(src, D); else op_.res_planes(pio->in.hi, pio->in.lo);
+            MESM_CHECK(op_.run(s));
+            const bool po = pio->planes_only && outp;
+            pio->wrote_fp32 = !po;
+            MESM_CHECK(ffn_block(L, R, t.Y1, t.Y1, nullptr, po ? nullptr : out, D, identity_map(), s, Planes(), outp, t.H, true));
             return cudaSuccess;
         }
         MESM_CHECK(Lin(R, L.out, nullptr, D, t.Y1, D).aplanes(pio->ao.hi, pio->ao.lo, D).res(src, D).ln(L.n1)
@@ -1021,16 +1033,20 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         float* enh_out = (!neg && out->enhanced_video_feat) ? out->enhanced_video_feat + (size_t)b0 * Lv * D : nullptr;
         float* enh = (enh_out && !packed) ? enh_out : p.enh;
         Planes xP;                                      // planes of `x` (empty: the producer of x wrote fp32 only)
+        static int po_on = -1;
+        if (po_on < 0) { const char* e = getenv("MESM_PLANES_ONLY"); po_on = (e && e[0] == '0') ? 0 : 1; }
+        const bool planes_only_ok = po_on && ptab;       // intermediate layer outputs as planes only (next layer: TMA operand + planes residual)
         for (size_t l = 0; l < ctx->enh.size(); ++l) {
             const bool lastl = (l + 1 == ctx->enh.size());
             float* dst = lastl ? enh : (l % 2 == 0 ? p.xa : p.xb);
             PlaneIO pio;
             pio.in = xP; pio.out = lastl ? p.enhP : (l % 2 == 0 ? p.xaP : p.xbP); pio.ao = p.aoP; pio.y1 = p.y1P;
+            pio.planes_only = planes_only_ok && !lastl;            // the last layer's fp32 rows are an output (enhanced_video_feat)
             T2VBuffers tb = p.t2v;
             if (l == 0) tb.Q = p.Qenh0;                 // layer 0's Q = (projV + pos) Wq is identical in the negative pass
             CK(t2v_layer(ctx->enh[l], words_c, wordsMap, nullptr, Lt, x, p.posV, Lv, Bc, b0, B, p.padV_all, wpad_all, tb,
                          dst, D, identity_map(), s, l == 0 && neg, cu, Rv, Lv, PWq_enh[l], p.t_posV, &pio));
-            x = dst;
+            x = pio.wrote_fp32 ? dst : nullptr;         // nullptr: this activation only exists as planes
             xP = pio.wrote_out ? pio.out : Planes();
         }
         if (ctx->enh.empty() && enh_out && !packed)
@@ -1043,14 +1059,17 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         // ---- aligner (model/model.py:230-234; neg: 290-294): keys = recon token + words; last layer writes the
         //      encoder buffer [Bc, Lv+1, 256] behind the global token ----
         Planes xinP = ctx->enh.empty() ? Planes() : xP;
+        bool E_fp32 = true;                              // the fp32 encoder buffer holds the aligner's result
         for (size_t l = 0; l < ctx->aln.size(); ++l) {
             const bool last = (l + 1 == ctx->aln.size());
             float* dst = last ? p.E : (l % 2 == 0 ? p.xa : p.xb);
             PlaneIO pio;
             pio.in = xinP; pio.out = last ? p.EP : (l % 2 == 0 ? p.xaP : p.xbP); pio.ao = p.aoP; pio.y1 = p.y1P;
+            pio.planes_only = planes_only_ok && (!last || !ctx->enc.empty());      // the encoder reads E as planes (operand + residual)
             CK(t2v_layer(ctx->aln[l], words_c, identity_map(), nullptr, Lk, xin, p.posV, Lv, Bc, b0, B, p.padV_all, epad_all,
                          p.t2v, dst, D, last ? c2e : identity_map(), s, false, cu, Rv, Lv, PWq_aln[l], p.t_posV, &pio));
-            xin = dst;
+            xin = pio.wrote_fp32 ? dst : nullptr;
+            E_fp32 = pio.wrote_fp32;
             xinP = pio.wrote_out ? pio.out : Planes();
         }
         Planes EcurP = ctx->aln.empty() ? Planes() : xinP, EnextP = p.E2P;      // planes of the encoder buffer (empty: fp32 only)
@@ -1061,7 +1080,9 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         for (size_t l = 0; l < ctx->enc.size(); ++l) {
             PlaneIO pio;
             pio.in = EcurP; pio.out = EnextP; pio.ao = p.aoP; pio.y1 = p.y1P;
-            CK(enc_layer(ctx->enc[l], Ecur, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re, PWqk[l], p.t_posE, &pio));
+            pio.planes_only = planes_only_ok && (l + 1 < ctx->enc.size());        // the last layer's fp32 rows feed the heads / outputs
+            CK(enc_layer(ctx->enc[l], E_fp32 ? Ecur : nullptr, p.posE, p.padE, L1, Bc, p.encb, Enext, s, cu, Re, PWqk[l], p.t_posE, &pio));
+            E_fp32 = pio.wrote_fp32;
             std::swap(Ecur, Enext);
             const Planes done = pio.wrote_out ? pio.out : Planes();
             EnextP = (pio.out.hi == p.E2P.hi) ? p.EP : p.E2P;

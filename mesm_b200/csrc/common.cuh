@@ -74,6 +74,7 @@ struct LinearOp {
     // [M, ld] planes - the form the tensor pipe consumes, so the TMA-fed GEMM (linear_tma.cu) needs no converter warps.
     const uint16_t* a_hi; const uint16_t* a_lo; int lda_p;    // A given as planes (A is then ignored); a_lo == nullptr: ONE fp16 plane (exact)
     uint16_t* out_hi; uint16_t* out_lo; int ldp;              // optional store of the final value as planes (row m -> row m)
+    const uint16_t* res_hi; const uint16_t* res_lo;           // linear_tma only: the residual given as planes [M, N] (row m, pitch N) instead of fp32
     const void* Wtm;                                          // host object: the weights as TMA-addressable planes (TmaWeights, linear_tma.cu)
 };
 
@@ -86,7 +87,7 @@ static inline LinearOp make_linear(int M, int N, int K, const float* A, int lda,
     op.residual = nullptr; op.ldr = 0; op.rmap = identity_map(); op.ln_g = nullptr; op.ln_b = nullptr;
     op.out = out; op.ldo = ldo; op.omap = identity_map(); op.out2 = nullptr; op.ldo2 = 0; op.o2map = identity_map(); op.pre_ln = nullptr; op.ln_stats = nullptr;
     op.nbatch = 1; op.bsA = op.bsW = op.bsBias = op.bsOut = 0;
-    op.a_hi = op.a_lo = nullptr; op.lda_p = 0; op.out_hi = op.out_lo = nullptr; op.ldp = 0; op.Wtm = nullptr;
+    op.a_hi = op.a_lo = nullptr; op.lda_p = 0; op.out_hi = op.out_lo = nullptr; op.ldp = 0; op.Wtm = nullptr; op.res_hi = op.res_lo = nullptr;
     return op;
 }
 

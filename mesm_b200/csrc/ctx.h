@@ -129,6 +129,7 @@ struct Lin {    // thin builder around LinearOp
     Lin& aplanes(const uint16_t* hi, const uint16_t* lo, int ld) { op.a_hi = hi; op.a_lo = lo; op.lda_p = ld; return *this; }
     Lin& oplanes(uint16_t* hi, uint16_t* lo, int ld) { op.out_hi = hi; op.out_lo = lo; op.ldp = ld; return *this; }
     Lin& wtm(const void* w) { op.Wtm = w; return *this; }
+    Lin& res_planes(const uint16_t* hi, const uint16_t* lo) { op.res_hi = hi; op.res_lo = lo; return *this; }
     Lin& bias(const float* b) { op.bias = b; return *this; }
     Lin& amap(RowMap m) { op.amap = m; return *this; }
     Lin& omap(RowMap m) { op.omap = m; return *this; }
@@ -158,7 +159,12 @@ constexpr float kScale64 = 0.125f;                 // 64^-0.5
 // its Q / QK / V projections on linear_tma.cu), where to store its output as planes (same row mapping as the fp32 output), and the two
 // plane scratch buffers every layer needs (attention output, LayerNorm-1 output).  Empty members fall back to the fp32 operands.
 struct Planes { uint16_t* hi = nullptr; uint16_t* lo = nullptr; explicit operator bool() const { return hi != nullptr; } };
-struct PlaneIO { Planes in, out, ao, y1; bool wrote_out = false; /* set by the layer: `out` now holds its result */ };
+struct PlaneIO {
+    Planes in, out, ao, y1;
+    bool planes_only = false;   // request: store the layer's result as planes only (no fp32 copy) - honoured on the plane path
+    bool wrote_out = false;     // set by the layer: `out` now holds its result
+    bool wrote_fp32 = true;     // set by the layer: the fp32 output buffer holds its result
+};
 
 struct T2VBuffers { float *KV, *Q, *AO, *X1, *Y1, *H; };
 struct EncBuffers { float *QKV, *AO, *Y1, *H; float* split = nullptr; /* key-split attention scratch (attn_split_floats), Lv + 1 > 224 only */ };

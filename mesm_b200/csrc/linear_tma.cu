@@ -187,11 +187,16 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int m = m0 + row;
             const bool mok = m < op.M;
-            if (op.residual) {
+            if (op.residual || op.res_hi) {
                 // this thread's residual row segment (its TMEM lane x this warp's column half) into L2 now: the loads of
                 // rows_pass follow within a few thousand cycles.  (Prefetching from the producer warp, two tiles ahead as
                 // linear_tc does, was useless here: ~150 MB stream through L2 in between and the lines were fetched twice -
                 // ncu: 920 MB of DRAM reads for 614 MB of operands.)
+                if (op.res_hi && mok) {
+                    const uint16_t* rh = op.res_hi + (long long)m * op.N + n0 + half * 128;
+                    const uint16_t* rl = op.res_lo + (long long)m * op.N + n0 + half * 128;
+                    prefetch_l2(rh); prefetch_l2(rh + 64); prefetch_l2(rl); prefetch_l2(rl + 64);
+                }
                 const long long ro = rowoff[256 + row];
                 if (ro >= 0) {
                     const float* r = op.residual + ro + n0 + half * 128;
@@ -215,10 +220,26 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
                 for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(&T[(4 * i + rsub) * 36 + c4]);
                 if (add_res) {
                     float4 r[8];
+                    if (op.res_hi) {                        // residual stored pre-split: r = hi + lo (16 mantissa bits, the precision it is consumed at anyway)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int mm = m0 + trow0 + 4 * i + rsub;
+                            uint2 h = make_uint2(0u, 0u), l = make_uint2(0u, 0u);
+                            if (mm < op.M && nok) {
+                                h = __ldg(reinterpret_cast<const uint2*>(op.res_hi + (long long)mm * op.N + nn));
+                                l = __ldg(reinterpret_cast<const uint2*>(op.res_lo + (long long)mm * op.N + nn));
+                            }
+                            r[i].x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+                            r[i].y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+                            r[i].z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+                            r[i].w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+                        }
+                    } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const long long o = rowoff[2 * 128 + trow0 + 4 * i + rsub];
                         r[i] = (o >= 0 && nok) ? __ldg(reinterpret_cast<const float4*>(op.residual + o + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { x[i].x += r[i].x; x[i].y += r[i].y; x[i].z += r[i].z; x[i].w += r[i].w; }
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
                 __syncwarp();
                 if (do_ln) {
                     // residual added and pre-LN value stored in the transposed (coalesced) domain; result kept for the stats
-                    rows_pass(n, op.residual != nullptr, true, false, op.pre_ln);
+                    rows_pass(n, op.residual != nullptr || op.res_hi != nullptr, true, false, op.pre_ln);
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -285,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tma_kernel(const __grid_con
                     }
                     tmem_st32(taddr0 + c * 32, v);
                 } else {
-                    rows_pass(n, op.residual != nullptr, false, true, nullptr);
+                    rows_pass(n, op.residual != nullptr || op.res_hi != nullptr, false, true, nullptr);
                 }
                 __syncwarp();
             }
@@ -468,6 +489,7 @@ bool linear_tma_eligible(const LinearOp& op) {
     if ((op.lda_p & 7) || (reinterpret_cast<uintptr_t>(op.a_hi) & 15) || (op.a_lo && (reinterpret_cast<uintptr_t>(op.a_lo) & 15))) return false;
     auto al16 = [](const void* p, long long ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); };
     if (!al16(op.out, op.ldo) || !al16(op.out2, op.ldo2) || !al16(op.residual, op.ldr) || !al16(op.pre_ln, op.N)) return false;
+    if (op.res_hi && (op.residual || !op.res_lo || (op.N & 3) || (reinterpret_cast<uintptr_t>(op.res_hi) & 7) || (reinterpret_cast<uintptr_t>(op.res_lo) & 7))) return false;
     if (op.out_hi && ((op.ldp & 3) || (reinterpret_cast<uintptr_t>(op.out_hi) & 7) || (reinterpret_cast<uintptr_t>(op.out_lo) & 7))) return false;
     if (!op.out && !op.out_hi && !op.ln_stats) return false;
     return true;
