@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_load_slot(uint32_t dst, const CUtensorMap* t
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(bar) : "memory");
 }
+// Remote arrive with the default (CTA-scope) release, as CUTLASS's ClusterBarrier::arrive(cta_id) does.  What the signal orders is data the
+// arriving CTA wrote into ITS OWN shared / tensor memory for ITS OWN tensor core (fence.proxy.async / tcgen05.fence before it): nothing
+// needs cluster-wide visibility.  The .release.cluster form used in round 1 costs the issuing thread ~1 k cycles per arrive, and the kernel
+// does one per K block of X, two per hidden chunk and (before) one per weight slot in every warp (tools/tma_probe.cu).
+__device__ __forceinline__ void arrive_remote_light(uint32_t cluster_saddr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
+}
 __device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(bar) : "memory");
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
     const int m0 = blockIdx.x * BM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_peer + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }   // full: one arrival per CTA, both in the leader
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_peer + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }   // full (leader): ONE local arrival + the bytes of both CTAs' loads
         for (int k = 0; k < 8; ++k) mbar_init(bar_xfull + 8 * k, op.x_planes ? 2 : 16);   // the TMA producer / the 8 converter warps of each CTA (used in the leader)
         mbar_init(bar_hacc_full, 1); mbar_init(bar_hbf_free, 1); mbar_init(bar_yfull, 1);
         mbar_init(bar_hacc_free, 16); mbar_init(bar_hbf_full, 16);             // the E1 warps of both CTAs (used in the leader)
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
                     mbar_wait_spin(bar_empty + 8 * s, ph ^ 1, 1000 + g);
                     if (t == 0) FSTAMP(40 + e);
                     if (g >= 20 && g < 36) FSTAMP(64 + g - 20);
-                    mbar_arrive_expect_tx_remote(full_leader + 8 * s, SLOT);
+                    if (cta_rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * SLOT);      // the leader expects both halves; the peer only loads
                     tma_load_slot(sbase + OFF_RING + s * SLOT, g2 ? &op.tm2 : &op.tm1, ((jc * 2 + (int)cta_rank) * 4 + t) * 128, full_leader + 8 * s);
                 }
             }
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
             auto wait_slot = [&](int& s) {
                 s = g % NSLOT;
                 const uint32_t ph = (g / NSLOT) & 1;
-                WT(w_full, mbar_wait_spin(bar_full + 8 * s, ph, 2000 + g, true));      // both CTAs' halves of the slot have landed
+                WT(w_full, mbar_wait_spin(bar_full + 8 * s, ph, 2000 + g, false));      // both CTAs' halves of the slot have landed
                 if (g >= 20 && g < 36) FSTAMP(80 + g - 20);
                 tc_fence_after();
             };
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
 #pragma unroll
                     for (int kbi = 0; kbi < 2; ++kbi) {
                         const int kb = t * 2 + kbi;
-                        if (j == 0) { mbar_wait_cluster(bar_xfull + 8 * kb, 0, 3000 + kb); tc_fence_after(); if (kb == 0) FSTAMP(2); }
+                        if (j == 0) { mbar_wait_spin(bar_xfull + 8 * kb, 0, 3000 + kb); tc_fence_after(); if (kb == 0) FSTAMP(2); }
                         const uint32_t xa = sbase + kb * XBLK, wb = slot + kbi * 8192;
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
@@ -237,11 +244,11 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
             g1(0);
             for (int j = 0; j < NCH; ++j) {
                 if (j + 1 < NCH) {
-                    WT(w_hacc, mbar_wait_spin(bar_hacc_free, j & 1, 4000 + j, true));       // E1(j) of both CTAs holds Hacc(j) in registers
+                    WT(w_hacc, mbar_wait_spin(bar_hacc_free, j & 1, 4000 + j));       // E1(j) of both CTAs holds Hacc(j) in registers
                     tc_fence_after();
                     g1(j + 1);
                 }
-                WT(w_hbf, mbar_wait_spin(bar_hbf_full, j & 1, 4500 + j, true));            // Hbf(j) written in both CTAs
+                WT(w_hbf, mbar_wait_spin(bar_hbf_full, j & 1, 4500 + j));            // Hbf(j) written in both CTAs
                 tc_fence_after();
                 g2f(j);
             }
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(xfull_leader + 8 * (kb0 + kk));
+                    if (lane == 0) arrive_remote_light(xfull_leader + 8 * (kb0 + kk));
                 }
             }
         }
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
             tmem_ld32(lane_base + TM_HACC + half * 64 + 32, v1);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(hacc_free_leader);        // Hacc may be overwritten by G1(j+1)
+            if (lane == 0) arrive_remote_light(hacc_free_leader);       // Hacc may be overwritten by G1(j+1)
             const float* bb = b1_s + ((j + jrot) % NCH) * HC + half * 64;
             float hi[32], lo[32];                                       // packed bf16x2 (bit patterns)
 #pragma unroll
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
             tmem_st32(lane_base + TM_HLO + half * 32, lo);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(hbf_full_leader);
+            if (lane == 0) arrive_remote_light(hbf_full_leader);
         }
 
         // ---- final epilogue: Y + b2 + R -> LayerNorm -> out (transposed through shared memory, coalesced) ----
