@@ -62,6 +62,7 @@ struct FfnOp {
     uint16_t* out_hi; uint16_t* out_lo;      // optional: the result also as planes, same row mapping and pitch as `out` (ldo == 256)
     const float* ln1_g; const float* ln1_b; const float* ln1_stats; int res_ln1;      // LayerNorm-1 applied in the prologue (kernels.h: FfnArgs)
     const float* b1; const float* b2; const float* ln_g; const float* ln_b; const float* prelu;
+    int wave_ctas;                           // CTAs resident at once (one per SM): the tile blockIdx.x + wave_ctas starts one tile-time from now
     int dbg;                                 // probe only: bit 0 skips the G1 MMAs, bit 1 the G2 MMAs (timing experiments)
 };
 
@@ -335,6 +336,17 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_pair_kernel(const __grid_const
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");       // tables / vectors visible to all workers
         if (tcid == 0) FSTAMP(20);
+        if (!op.x_planes && op.wave_ctas > 0) {
+            // L2 prefetch of the X rows of the tile that starts on this SM's successor one wave from now (CTAs are dispatched in index
+            // order, one per SM): a wave of tiles starting together asks HBM for 19 MB at once and the first K block reached the MMA
+            // thread after ~14 k cycles; prefetched a tile-time ahead, those loads hit L2.  Two threads per row, four 128-byte lines each.
+            const long long mn = (long long)(blockIdx.x + op.wave_ctas) * BM + (tcid >> 1);
+            if (mn < op.M) {
+                const float* xr = op.X + mn * op.ldx + (tcid & 1) * 128;
+#pragma unroll
+                for (int c = 0; c < 128; c += 32) prefetch_l2(xr + c);
+            }
+        }
 
         // ---- E1 per hidden chunk: Hacc -> registers -> +b1, PReLU -> packed bf16 hi / lo -> Hbf (TMEM) ----
         const float slope = __ldg(op.prelu);
@@ -604,6 +616,7 @@ cudaError_t launch_ffn_fused(const FfnArgs& a, cudaStream_t s) {
     } else {
         op.tmXh = op.tm1; op.tmXl = op.tm1;
     }
+    { static int wave = -1; if (wave < 0) { const char* e = getenv("MESM_FFN_PREFETCH"); int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0); wave = (e && e[0] == '0') ? 0 : (nsm & ~1); } op.wave_ctas = wave; }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MESM_FFN_DBG"); dbg = e ? atoi(e) : 0; } op.dbg = dbg; }
     const unsigned mt = (unsigned)((a.M + ffn::BM - 1) / ffn::BM);
     cudaLaunchConfig_t cfg = {};
