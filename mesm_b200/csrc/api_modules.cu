@@ -319,7 +319,8 @@ int mesm_debug_attention(const float* qkv, const uint8_t* k_pad, int32_t B, int3
         a.split_ws = split; a.split_rows = (long long)B * L;
     }
     for (int i = 0; i < iters; ++i) {
-        if (use_tc == 2) { if (!attn_tc_split_eligible(a)) { cudaFree(split); return fail(ctx, 3, "not eligible"); } CK(launch_attn_tc_split(a, a.split_rows, s)); }
+        if (use_tc == 3) { if (!attn_mma_eligible(a)) return fail(ctx, 3, "not eligible"); CK(launch_attn_mma(a, s)); }
+        else if (use_tc == 2) { if (!attn_tc_split_eligible(a)) { cudaFree(split); return fail(ctx, 3, "not eligible"); } CK(launch_attn_tc_split(a, a.split_rows, s)); }
         else if (use_tc) { if (!attn_tc_eligible(a)) return fail(ctx, 3, "not eligible"); CK(launch_attn_tc(a, s)); }
         else { CK(launch_mha_rows(a, s, true)); }
     }

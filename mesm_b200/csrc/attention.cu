@@ -138,6 +138,9 @@ cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_sim
     {
         static int force = -1;
         if (force < 0) { const char* e = getenv("MESM_FORCE_SIMT"); const char* e2 = getenv("MESM_FORCE_SIMT_ATTN"); force = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
+        static int mma = -1;
+        if (mma < 0) { const char* e = getenv("MESM_ATTN_MMA"); mma = (e && e[0] == '0') ? 0 : 1; }
+        if (!force && !force_simt && mma && attn_mma_eligible(a)) return launch_attn_mma(a, s);
         if (!force && !force_simt && attn_tc_eligible(a)) return launch_attn_tc(a, s);
         if (!force && !force_simt && attn_tc_split_eligible(a)) {
             // rows of the query side = rows of the output: uniform B * Lq, packed: the caller passes it through split_rows

@@ -35,6 +35,8 @@ cudaError_t launch_attn_tc_split(const MhaRowsArgs& a, long long rows, cudaStrea
 size_t attn_split_floats(long long rows, int Lk);         // 0 when one key tile suffices
 cudaError_t launch_mha_rows(const MhaRowsArgs& a, cudaStream_t s, bool force_simt = false);      // dispatcher: tcgen05 kernel when eligible
 bool attn_tc_eligible(const MhaRowsArgs& a);
+bool attn_mma_eligible(const MhaRowsArgs& a);                       // attn_mma.cu: warp-level mma.sync kernel, any Lk whose operands fit shared memory
+cudaError_t launch_attn_mma(const MhaRowsArgs& a, cudaStream_t s);
 cudaError_t launch_attn_tc(const MhaRowsArgs& a, cudaStream_t s);
 
 struct MhaSmallArgs {

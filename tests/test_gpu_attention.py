@@ -48,6 +48,18 @@ def test_attention_kernels_match_reference(B, L):
         assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
 
 
+@pytest.mark.parametrize("B,L", [(3, 25), (5, 76), (4, 195), (2, 224), (7, 129), (3, 33), (6, 17), (2, 16), (3, 601), (5, 225), (4, 300), (40, 201), (700, 150), (2, 430)])
+def test_attention_mma_kernel_matches_reference(B, L):
+    """Warp-level mma.sync kernel (attn_mma.cu): every key count the operands fit shared memory for, ragged key masks, planes checked
+    through the forward tests."""
+    qkv, pad = _inputs(B, L, seed=L)
+    ref = _reference(qkv, pad, B, L)
+    out, _ = _run(qkv, pad, B, L, 3)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 3e-5
+    again, _ = _run(qkv, pad, B, L, 3, iters=3)
+    assert torch.equal(out, again)
+
+
 @pytest.mark.parametrize("B,L", [(3, 601), (2, 449), (5, 225), (4, 300)])
 def test_attention_key_split_matches_reference(B, L):
     """More keys than one 224-key tile (the shipped max_video_l = 600 -> 601 encoder keys): one tcgen05 pass per key chunk + exact
