@@ -479,6 +479,14 @@ cudaError_t launch_linear(const LinearOp& op, cudaStream_t s) {
     const double flops = 2.0 * op.M * (double)op.N * ((double)op.K + op.K2) * (op.nbatch > 1 ? op.nbatch : 1);
     const char* name = "linear_simt";
     if (tc) name = op.K > 1024 ? "input_proj linear_tc fp32 features" : (op.K == 1024 ? "linear_tc K=1024" : (op.N > 256 ? "linear_tc K<=512 N>256" : (op.ln_g ? "linear_tc K<=512 N=256 +LN" : "linear_tc K<=512 N=256")));
+    static int shapes = -1;            // MESM_PROFILE_SHAPES=1: one profile row per (kernel, M, N, K) instead of per kernel class
+    if (shapes < 0) { const char* e = getenv("MESM_PROFILE_SHAPES"); shapes = (e && e[0] == '1') ? 1 : 0; }
+    if (shapes && g_stats.profile) {
+        static thread_local std::unordered_map<std::string, std::string> names;      // ProfScope keeps the pointer: the strings must outlive it
+        const std::string key = std::string(tc ? "linear_tc " : "linear_simt ") + std::to_string(op.M) + "x" + std::to_string(op.N) + "x" + std::to_string(op.K + op.K2) +
+                                (op.nbatch > 1 ? " nb" + std::to_string(op.nbatch) : "") + (op.act ? " act" + std::to_string(op.act) : "") + (op.ln_g ? " ln" : "");
+        name = names.emplace(key, key).first->second.c_str();
+    }
     ProfScope ps(name, s, flops, op.M);
     return tc ? launch_linear_tc(op, s) : launch_linear_simt(op, s);
 }

@@ -409,6 +409,150 @@ __global__ void __launch_bounds__(AH_THREADS, 2) attn_mma_heads_kernel(const Mha
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoder cross-attention (model/transformer.py:367-381 through model/attention.py): <= 16 queries per pair (10 in every shipped
+// configuration) against the pair's Lv clips, per-head operands [content ; sine] (head_dim 64) for the scores and 32 value dims.
+// One CTA per pair, warp w = head w.  There is a single query tile, so every key / value element is used exactly once per
+// (pair, head): the B fragments are loaded from global memory straight into registers (fp32 -> bf16 hi / lo there) - no shared
+// memory, no barrier, every load of a 32-key block independent of the others.  The thread-per-key fp32 kernel it replaces
+// (dec_cross_kernel, attention.cu) issued ~1700 instructions per 32 keys and head, this one ~600.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NH * 32, 2) dec_cross_mma_kernel(const MhaSmallArgs a) {
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    int S = a.S;
+    long long kfirst = (long long)b * a.k_bs + a.k_off, kpad0 = (long long)b * a.S;
+    if (a.k_cu) {
+        const int c0 = a.k_cu[b] - a.k_cu[0];
+        S = a.k_cu[b + 1] - a.k_cu[b];
+        kfirst = (long long)c0 + (a.k_enc ? b : 0) + a.k_off;
+        kpad0 = c0;
+    }
+    const float qs = a.scale * kLog2e;
+    const int r0 = g, r1 = g + 8;
+    // A fragments of the four 16-dim steps: steps 0, 1 = content query, steps 2, 3 = sine query
+    uint32_t qh[4][4], ql[4][4];
+    {
+        const long long row0 = (long long)b * a.q_bs + (long long)(r0 < a.L ? r0 : 0) * a.q_is, row1 = (long long)b * a.q_bs + (long long)(r1 < a.L ? r1 : 0) * a.q_is;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const float* p0 = (ks < 2 ? a.q + row0 * a.ldq : a.q2 + row0 * a.ldq2) + h * 32 + 16 * (ks & 1) + 2 * t;
+            const float* p1 = (ks < 2 ? a.q + row1 * a.ldq : a.q2 + row1 * a.ldq2) + h * 32 + 16 * (ks & 1) + 2 * t;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float2 x0 = r0 < a.L ? __ldg(reinterpret_cast<const float2*>(p0 + 8 * half)) : make_float2(0.f, 0.f);
+                const float2 x1 = r1 < a.L ? __ldg(reinterpret_cast<const float2*>(p1 + 8 * half)) : make_float2(0.f, 0.f);
+                tc::split_bf16x2(x0.x * qs, x0.y * qs, qh[ks][2 * half], ql[ks][2 * half]);
+                tc::split_bf16x2(x1.x * qs, x1.y * qs, qh[ks][2 * half + 1], ql[ks][2 * half + 1]);
+            }
+        }
+    }
+    float o[4][4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+
+    for (int k0 = 0; k0 < S; k0 += 32) {
+        // validity of key k0 + lane -> one bit per key of the block
+        const int mykey = k0 + lane;
+        const bool myvalid = mykey < S && !(a.k_pad && a.k_pad[kpad0 + mykey]);
+        const unsigned vmask = __ballot_sync(0xffffffffu, myvalid);
+        float s[4][4];
+#pragma unroll
+        for (int jp = 0; jp < 4; jp += 2) {                     // two n-tiles (8 keys each) at a time: 16 independent 8-byte loads
+            float2 raw[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int key = min(k0 + 8 * (jp + u) + g, S - 1);      // keys beyond S: any valid row, their scores are masked below
+                const long long krow = kfirst + (long long)key * a.k_is;
+                const float* kc = a.k + krow * a.ldk + h * 32 + 2 * t;
+                const float* kp = a.k2 + (a.k2_table ? (long long)__ldg(a.k2_table + krow) : krow) * a.ldk2 + h * 32 + 2 * t;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    raw[u][c] = __ldg(reinterpret_cast<const float2*>(kc + 8 * c));
+                    raw[u][4 + c] = __ldg(reinterpret_cast<const float2*>(kp + 8 * c));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                uint32_t kh[8], kl[8];                          // [2 ks + half]: b0 / b1 of the four 16-dim steps
+#pragma unroll
+                for (int c = 0; c < 8; ++c) tc::split_bf16x2(raw[u][c].x, raw[u][c].y, kh[c], kl[c]);
+                mma16816z(s[jp + u], qh[0], kh[0], kh[1]);
+#pragma unroll
+                for (int ks = 1; ks < 4; ++ks) mma16816(s[jp + u], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma16816(s[jp + u], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma16816(s[jp + u], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
+            }
+        }
+        if (vmask != 0xffffffffu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned bits = vmask >> (8 * j + 2 * t);
+                if (!(bits & 1u)) { s[j][0] = -CUDART_INF_F; s[j][2] = -CUDART_INF_F; }
+                if (!(bits & 2u)) { s[j][1] = -CUDART_INF_F; s[j][3] = -CUDART_INF_F; }
+            }
+        }
+        float cm0 = fmaxf(s[0][0], s[0][1]), cm1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) { cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1])); cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3])); }
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+        const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+        const float mu0 = mn0 == -CUDART_INF_F ? 0.f : mn0, mu1 = mn1 == -CUDART_INF_F ? 0.f : mn1;
+        const float sc0 = tc::ex2_approx(m0 - mu0), sc1 = tc::ex2_approx(m1 - mu1);
+        m0 = mn0; m1 = mn1;
+        l0 *= sc0; l1 *= sc1;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { o[d][0] *= sc0; o[d][1] *= sc0; o[d][2] *= sc1; o[d][3] *= sc1; }
+#pragma unroll
+        for (int k16 = 0; k16 < 2; ++k16) {
+            if (k0 + 16 * k16 >= S) break;                      // warp-uniform
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float p0 = tc::ex2_approx(s[2 * k16 + u][0] - mu0), p1 = tc::ex2_approx(s[2 * k16 + u][1] - mu0);
+                const float p2 = tc::ex2_approx(s[2 * k16 + u][2] - mu1), p3 = tc::ex2_approx(s[2 * k16 + u][3] - mu1);
+                l0 += p0 + p1; l1 += p2 + p3;
+                tc::split_bf16x2(p0, p1, ph[2 * u], pl[2 * u]);
+                tc::split_bf16x2(p2, p3, ph[2 * u + 1], pl[2 * u + 1]);
+            }
+            // B fragments of V: {key 2t, key 2t + 1} x dim g (b0) and keys + 8 (b1) per 8-dim n-tile; masked / out-of-range keys have p = 0
+            float vr[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int key = min(k0 + 16 * k16 + 2 * t + (kk & 1) + 8 * (kk >> 1), S - 1);
+                const float* vp = a.v + (kfirst + (long long)key * a.k_is) * a.ldv + h * 32 + g;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) vr[kk][d] = __ldg(vp + 8 * d);
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                uint32_t vh0, vl0, vh1, vl1;
+                tc::split_bf16x2(vr[0][d], vr[1][d], vh0, vl0);
+                tc::split_bf16x2(vr[2][d], vr[3][d], vh1, vl1);
+                mma16816(o[d], ph, vh0, vh1);
+                mma16816(o[d], pl, vh0, vh1);
+                mma16816(o[d], ph, vl0, vl1);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;          // l == 0 -> NaN like the reference
+    if (r0 < a.L) {
+        float* p = a.out + ((long long)b * a.q_bs + (long long)r0 * a.q_is) * a.ldo + h * 32 + 2 * t;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) *reinterpret_cast<float2*>(p + 8 * d) = make_float2(o[d][0] * i0, o[d][1] * i0);
+    }
+    if (r1 < a.L) {
+        float* p = a.out + ((long long)b * a.q_bs + (long long)r1 * a.q_is) * a.ldo + h * 32 + 2 * t;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) *reinterpret_cast<float2*>(p + 8 * d) = make_float2(o[d][2] * i1, o[d][3] * i1);
+    }
+}
+
 }  // namespace am
 
 static size_t attn_mma_smem(int Lk) {
@@ -459,6 +603,19 @@ cudaError_t launch_attn_mma(const MhaRowsArgs& a, cudaStream_t s) {
     if (v == 1) return launch_variant<8, 3, 4>(a, smem, s);
     if (v == 2) return launch_variant<12, 2, 4>(a, smem, s);
     return launch_variant<8, 2, 8>(a, smem, s);
+}
+
+bool dec_cross_mma_eligible(const MhaSmallArgs& a) {
+    auto al8 = [](const float* p, int ld) { return p && ((reinterpret_cast<uintptr_t>(p) & 7) == 0) && (ld % 2 == 0); };
+    return a.L >= 1 && a.L <= 16 && a.nheads == NH && a.hq == HD && a.hv == HD && a.q2 && a.k2 && !a.attn_w && !a.causal && a.S >= 1 &&
+           al8(a.q, a.ldq) && al8(a.q2, a.ldq2) && al8(a.k, a.ldk) && al8(a.k2, a.ldk2) && al8(a.out, a.ldo) && a.v;
+}
+
+cudaError_t launch_dec_cross_mma(const MhaSmallArgs& a, cudaStream_t s) {
+    ProfScope _ps("dec_cross_mma", s);
+    am::dec_cross_mma_kernel<<<a.B, NH * 32, 0, s>>>(a);
+    g_stats.launches++;
+    return cudaGetLastError();
 }
 
 }  // namespace mesm

@@ -57,6 +57,8 @@ struct MhaSmallArgs {
     int causal = 0;                  // 1: key j is masked for query i when j > i (CLIP text tower, model/text_encoder.py:321-327)
 };
 cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s);
+bool dec_cross_mma_eligible(const MhaSmallArgs& a);                    // attn_mma.cu: decoder cross-attention on mma.sync
+cudaError_t launch_dec_cross_mma(const MhaSmallArgs& a, cudaStream_t s);
 
 struct ReconPoolArgs {
     const float* x; int ldx;
