@@ -270,7 +270,7 @@ template <int NW, int MINB, int NTM>
 __global__ void __launch_bounds__(NW * 32, MINB) attn_mma_kernel(const MhaRowsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NT = NW * 32;
-    const int h = blockIdx.x, b = blockIdx.y;
+    const int h = blockIdx.x & (NH - 1), b = blockIdx.x / NH;      // the heads of a pair are neighbours: they read the same rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int bg = a.b0 + b;
     const bool quirk = a.q_pad != nullptr;
@@ -576,8 +576,7 @@ static cudaError_t launch_variant(const MhaRowsArgs& a, size_t smem, cudaStream_
         MESM_CHECK(cudaFuncSetAttribute(am::attn_mma_kernel<NW, MINB, NTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    dim3 grid(NH, a.B);
-    am::attn_mma_kernel<NW, MINB, NTM><<<grid, NW * 32, smem, s>>>(a);
+    am::attn_mma_kernel<NW, MINB, NTM><<<(unsigned)a.B * NH, NW * 32, smem, s>>>(a);
     g_stats.launches++;
     return cudaGetLastError();
 }
