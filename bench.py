@@ -366,8 +366,9 @@ def latency_b32(dev, feature_f16):
 
 def _f32_features(b):
     """The reference legs take fp32 tensors: the stored fp16 values upcast (exactly the values our arm computes on)."""
-    if b["video_feat"].dtype == torch.float16:
-        b = dict(b, video_feat=b["video_feat"].float())
+    for k in ("video_feat", "words_feat"):
+        if b[k].dtype == torch.float16:
+            b = dict(b, **{k: b[k].float()})
     return b
 
 
@@ -420,7 +421,7 @@ def main():
               "Lv": cfg["max_video_l"], "Lt": cfg["max_words_l"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
               "ragged_video": f"U{{{cfg['max_video_l'] // 2}..{cfg['max_video_l']}}}" if wlc["ragged"] else "uniform",
               "negative_branch": True, "align_scores": True, "nms_thd": NMS_THD, "parallelism": f"dp{world}",
-              "feature_storage": "fp16 (fp16-representable clip features, used exactly; computed in fp32 accumulate)" if args.feature_dtype == "f16" else "fp32",
+              "feature_storage": "fp16 (fp16-representable clip and word features, used exactly; computed in fp32 accumulate)" if args.feature_dtype == "f16" else "fp32",
               "l2": "inputs (GBs per GPU) larger than L2; no flush needed"}
     if wlc["dense_nms"]:
         config["dense_nms_candidates"] = wlc["dense_nms"]
@@ -441,6 +442,7 @@ def main():
         wl = make_workload(cfg, 64, 1234, "cpu", wlc)
         if args.feature_dtype == "f16":
             wl["video_feat"] = wl["video_feat"].half().float()       # the same fp16-representable values our arm stores in 16 bits
+            wl["words_feat"] = wl["words_feat"].half().float()
         sub = take_groups(wl, args.cpu_sample_pairs)
         pps, sec, ref = cpu_reference_pairs_per_s(args.config, cfg, model.state_dict(), sub, max(args.steps, 1), max(args.warmup, 0), threads)
         line = {"impl": "reference", "metric": "video-query pairs/sec", "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
@@ -469,6 +471,7 @@ def main():
     f16 = args.feature_dtype == "f16"
     if f16:
         wl["video_feat"] = wl["video_feat"].half()                   # resident in HBM in the storage format
+        wl["words_feat"] = wl["words_feat"].half()                   # (the engine widens the 16-bit word features on the device)
     B, Lv = args.pairs, cfg["max_video_l"]
     lib = _lib.lib()
     from mesm_b200.sharding import gather_topk

@@ -169,3 +169,18 @@ def test_benchmark_shapes_properties(cfg_name, lv, groups):
         n0 = sum(nc[:groups // 2])
         sub = eng.forward(args[0][:n0], args[1][:n0], args[2][:n0], inp["num_clips"][:groups // 2], want=("core",))
         assert rel_err(sub["pred_logits"], a["pred_logits"][:n0]) < 1e-4 and rel_err(sub["pred_spans"], a["pred_spans"][:n0]) < 1e-4
+
+
+def test_forward_accepts_16bit_word_features():
+    """Word features stored in 16 bits (bench.py --feature-dtype f16) are widened on the device: same bits as their fp32 upcast."""
+    import mesm_b200
+    cfg, sd, inp, neg, gold, meta = load_case(sorted(golden_cases())[0])
+    eng = mesm_b200.Engine(engine_cfg(cfg), chunk_pairs=256)
+    eng.load_state_dict(sd)
+    dev = eng.device
+    w16 = inp["words_feat"].half().to(dev)
+    args = (inp["video_feat"].to(dev), inp["video_mask"].to(dev))
+    a = eng.forward(*args, w16, inp["num_clips"], neg_index=neg.to(dev), want=("core",))
+    b = eng.forward(*args, w16.float(), inp["num_clips"], neg_index=neg.to(dev), want=("core",))
+    for k in ("pred_logits", "pred_spans", "saliency_scores"):
+        assert torch.equal(a[k], b[k]), k
