@@ -30,6 +30,7 @@ int main(int argc, char** argv) {
 #ifdef MESM_TC_TIMING
     long long t[160]; ffn_read_times(t);
     printf("setup %lld | first X block at MMA %lld | X converted %lld | yfull committed %lld | yfull seen %lld | done %lld\n", t[1] - t[0], t[2] - t[0], t[20] - t[0], t[19] - t[0], t[37] - t[0], t[38] - t[0]);
+    printf("epilogue: yfull seen %lld | pass 1 (+b2 +R, sums) done %lld | pass 2 (variance) done %lld | pass 3 (normalise, store) done %lld\n", t[37] - t[0], t[150] - t[0], t[151] - t[0], t[38] - t[0]);
     printf("MMA thread waits (cycles): local slot full %lld | peer slot %lld | hacc_free %lld | hbf_full %lld\n", t[60], t[61], t[62], t[63]);
     for (int g = 0; g < 16; ++g)
         printf("  slot g=%d: producer issued %7lld | leader local full %7lld | peer relayed %7lld | commit issued %7lld\n", g + 20, t[64 + g] - t[0], t[80 + g] - t[0], t[96 + g] - t[0], t[112 + g] - t[0]);
