@@ -362,7 +362,7 @@ cudaError_t launch_mha_small(const MhaSmallArgs& a, cudaStream_t s) {
     if (cross_on < 0) { const char* e = getenv("MESM_DEC_CROSS"); cross_on = (e && e[0] == '0') ? 0 : 1; }
     static int cross_mma = -1;
     if (cross_mma < 0) { const char* e = getenv("MESM_DEC_CROSS_MMA"); cross_mma = (e && e[0] == '0') ? 0 : 1; }
-    if (cross_on && cross_mma && dec_cross_mma_eligible(a)) return launch_dec_cross_mma(a, s);
+    if (cross_on && cross_mma && dec_cross_mma_eligible(a)) return launch_dec_cross_mma(a, s);      // decoder cross- and self-attention (<= 16 queries)
     if (cross_on && !a.causal && dec_cross_eligible(a)) {
         ProfScope _ps("dec_cross", s);
         const size_t smem = (size_t)(10 * 512 + 8 * 10 * 32) * sizeof(float);

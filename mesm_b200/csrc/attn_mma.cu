@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(AH_THREADS, 2) attn_mma_heads_kernel(const Mha
 // memory, no barrier, every load of a 32-key block independent of the others.  The thread-per-key fp32 kernel it replaces
 // (dec_cross_kernel, attention.cu) issued ~1700 instructions per 32 keys and head, this one ~600.
 // ---------------------------------------------------------------------------------------------------------------------
+// NKS = 16-dim steps of the score product: 4 = [content ; sine] operands (cross-attention), 2 = one 32-dim operand (decoder self-attention)
+template <int NKS>
 __global__ void __launch_bounds__(NH * 32, 2) dec_cross_mma_kernel(const MhaSmallArgs a) {
     const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     int S = a.S;
@@ -430,11 +432,11 @@ __global__ void __launch_bounds__(NH * 32, 2) dec_cross_mma_kernel(const MhaSmal
     const float qs = a.scale * kLog2e;
     const int r0 = g, r1 = g + 8;
     // A fragments of the four 16-dim steps: steps 0, 1 = content query, steps 2, 3 = sine query
-    uint32_t qh[4][4], ql[4][4];
+    uint32_t qh[NKS][4], ql[NKS][4];
     {
         const long long row0 = (long long)b * a.q_bs + (long long)(r0 < a.L ? r0 : 0) * a.q_is, row1 = (long long)b * a.q_bs + (long long)(r1 < a.L ? r1 : 0) * a.q_is;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        for (int ks = 0; ks < NKS; ++ks) {
             const float* p0 = (ks < 2 ? a.q + row0 * a.ldq : a.q2 + row0 * a.ldq2) + h * 32 + 16 * (ks & 1) + 2 * t;
             const float* p1 = (ks < 2 ? a.q + row1 * a.ldq : a.q2 + row1 * a.ldq2) + h * 32 + 16 * (ks & 1) + 2 * t;
 #pragma unroll
@@ -459,31 +461,32 @@ __global__ void __launch_bounds__(NH * 32, 2) dec_cross_mma_kernel(const MhaSmal
         float s[4][4];
 #pragma unroll
         for (int jp = 0; jp < 4; jp += 2) {                     // two n-tiles (8 keys each) at a time: 16 independent 8-byte loads
-            float2 raw[2][8];
+            float2 raw[2][2 * NKS];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int key = min(k0 + 8 * (jp + u) + g, S - 1);      // keys beyond S: any valid row, their scores are masked below
                 const long long krow = kfirst + (long long)key * a.k_is;
                 const float* kc = a.k + krow * a.ldk + h * 32 + 2 * t;
-                const float* kp = a.k2 + (a.k2_table ? (long long)__ldg(a.k2_table + krow) : krow) * a.ldk2 + h * 32 + 2 * t;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    raw[u][c] = __ldg(reinterpret_cast<const float2*>(kc + 8 * c));
-                    raw[u][4 + c] = __ldg(reinterpret_cast<const float2*>(kp + 8 * c));
+                for (int c = 0; c < 4; ++c) raw[u][c] = __ldg(reinterpret_cast<const float2*>(kc + 8 * c));
+                if (NKS == 4) {
+                    const float* kp = a.k2 + (a.k2_table ? (long long)__ldg(a.k2_table + krow) : krow) * a.ldk2 + h * 32 + 2 * t;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) raw[u][(NKS == 4 ? 4 : 0) + c] = __ldg(reinterpret_cast<const float2*>(kp + 8 * c));
                 }
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                uint32_t kh[8], kl[8];                          // [2 ks + half]: b0 / b1 of the four 16-dim steps
+                uint32_t kh[2 * NKS], kl[2 * NKS];              // [2 ks + half]: b0 / b1 of the 16-dim steps
 #pragma unroll
-                for (int c = 0; c < 8; ++c) tc::split_bf16x2(raw[u][c].x, raw[u][c].y, kh[c], kl[c]);
+                for (int c = 0; c < 2 * NKS; ++c) tc::split_bf16x2(raw[u][c].x, raw[u][c].y, kh[c], kl[c]);
                 mma16816z(s[jp + u], qh[0], kh[0], kh[1]);
 #pragma unroll
-                for (int ks = 1; ks < 4; ++ks) mma16816(s[jp + u], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
+                for (int ks = 1; ks < NKS; ++ks) mma16816(s[jp + u], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) mma16816(s[jp + u], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
+                for (int ks = 0; ks < NKS; ++ks) mma16816(s[jp + u], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) mma16816(s[jp + u], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
+                for (int ks = 0; ks < NKS; ++ks) mma16816(s[jp + u], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
             }
         }
         if (vmask != 0xffffffffu) {
@@ -606,13 +609,16 @@ cudaError_t launch_attn_mma(const MhaRowsArgs& a, cudaStream_t s) {
 
 bool dec_cross_mma_eligible(const MhaSmallArgs& a) {
     auto al8 = [](const float* p, int ld) { return p && ((reinterpret_cast<uintptr_t>(p) & 7) == 0) && (ld % 2 == 0); };
-    return a.L >= 1 && a.L <= 16 && a.nheads == NH && a.hq == HD && a.hv == HD && a.q2 && a.k2 && !a.attn_w && !a.causal && a.S >= 1 &&
-           al8(a.q, a.ldq) && al8(a.q2, a.ldq2) && al8(a.k, a.ldk) && al8(a.k2, a.ldk2) && al8(a.out, a.ldo) && a.v;
+    if ((a.q2 != nullptr) != (a.k2 != nullptr)) return false;
+    if (a.q2 && !(al8(a.q2, a.ldq2) && al8(a.k2, a.ldk2))) return false;
+    return a.L >= 1 && a.L <= 16 && a.nheads == NH && a.hq == HD && a.hv == HD && !a.attn_w && !a.causal && a.S >= 1 &&
+           al8(a.q, a.ldq) && al8(a.k, a.ldk) && al8(a.out, a.ldo) && a.v;
 }
 
 cudaError_t launch_dec_cross_mma(const MhaSmallArgs& a, cudaStream_t s) {
-    ProfScope _ps("dec_cross_mma", s);
-    am::dec_cross_mma_kernel<<<a.B, NH * 32, 0, s>>>(a);
+    ProfScope _ps(a.q2 ? "dec_cross_mma" : "dec_self_mma", s);
+    if (a.q2) am::dec_cross_mma_kernel<4><<<a.B, NH * 32, 0, s>>>(a);
+    else am::dec_cross_mma_kernel<2><<<a.B, NH * 32, 0, s>>>(a);
     g_stats.launches++;
     return cudaGetLastError();
 }
