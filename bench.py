@@ -629,6 +629,17 @@ def main():
     h2d_box = [0]
     vl_box = [None if vlen_host is None else sb["video_len"]] * NB
 
+    # ---- NVLink-assisted ingest (mesm_b200/relay.py): ranks on a slow host link route part of their videos through a fast peer ----
+    relay, relay_info = None, None
+    if dist and shared and not padded and not os.environ.get("MESM_NO_RELAY"):
+        try:
+            ff = os.environ.get("MESM_RELAY_FORCE")
+            relay, relay_info = mesm_b200.plan_ingest_relay(local, dist, int(0.12 * host["video_feat"].numel() * host["video_feat"].element_size()),
+                                                            nbuf=NB, force_fraction=float(ff) if ff else None)
+        except Exception as e:                                   # noqa: BLE001 - the direct path always works
+            relay, relay_info = None, {"error": f"{type(e).__name__}: {e}"}
+    use_relay = [relay is not None]
+
     def e2e_stream(total):
         # Host order: scoring of sub-batch i is enqueued first, then the ingest of sub-batch i+2 into the buffer it frees.
         for e in freed:
@@ -643,7 +654,7 @@ def main():
                     h2d_box[0] = sum(v.numel() * v.element_size() for v in host.values())
                 else:
                     staged = mesm_b200.prepare_batch_input(dict(host, num_clips=sb["num_clips"]), dev, non_blocking=True, out=dbuf[i % NB],
-                                                           shared_group_video=shared)
+                                                           shared_group_video=shared, relay=relay if use_relay[0] else None)
                     h2d_box[0] = mesm_b200.prepare_batch_input.last_h2d_bytes
                     vl_box[i % NB] = None if vlen_host is None else staged["video_len"]
                 ready[i % NB].record(copy)
@@ -687,6 +698,25 @@ def main():
     d2h = hres[0].numel() * 8 + hkeep[0].numel() * 4
     e2e_stream(max(2 * nsub, NB))    # warm-up: every buffer, the allocator's steady state and the copy path
     torch.cuda.synchronize()
+    if relay_info is not None and relay_info.get("pairs"):
+        # keep the relay only if it is faster for the NODE (max over ranks), measured on a few streamed steps each way
+        def timed(on):
+            use_relay[0] = on and relay is not None
+            e2e_stream(NB)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t_ = time.perf_counter()
+            e2e_stream(3 * nsub)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t_], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt)
+        t_off, t_on = timed(False), timed(True)
+        relay_info["trial_s"] = {"direct": round(t_off, 4), "relayed": round(t_on, 4)}
+        relay_info["used"] = bool(t_on < 0.98 * t_off)
+        use_relay[0] = relay_info["used"] and relay is not None
+    elif relay_info is not None:
+        relay_info["used"] = False
     gc.collect()
     if dist:
         dist.barrier()
@@ -707,6 +737,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_box[0] * nsub, "d2h_bytes_per_step": d2h * nsub,
                     "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest up to {NB} sub-batches ahead ({NB} device buffers) on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
+    if relay_info is not None:
+        line["e2e"]["ingest_relay"] = relay_info
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}

@@ -6,6 +6,7 @@ Layout: ``csrc/`` CUDA kernels + C ABI (include/mesm_b200.h) -> ``libmesm_b200.s
 from .engine import Engine, decode_nms, temporal_nms_lists, align_scores, loss_saliency  # noqa: F401
 from .ingest import prepare_batch_input, upload_clips, build_video_feat  # noqa: F401
 from .numa import bind_to_gpu_node  # noqa: F401
+from .relay import IngestRelay, plan_ingest_relay  # noqa: F401
 
 __all__ = ["Engine", "decode_nms", "temporal_nms_lists", "align_scores", "loss_saliency", "prepare_batch_input", "upload_clips",
-           "build_video_feat", "bind_to_gpu_node"]
+           "build_video_feat", "bind_to_gpu_node", "IngestRelay", "plan_ingest_relay"]

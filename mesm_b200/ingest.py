@@ -111,11 +111,13 @@ def clip_counts(video_mask):
     return last.to(torch.int32)
 
 
-def prepare_batch_input(batched_data, device, non_blocking=False, out=None, shared_group_video=False):
+def prepare_batch_input(batched_data, device, non_blocking=False, out=None, shared_group_video=False, relay=None):
     """dataset/base.py:358-383.  ``out`` (optional): dict of preallocated device tensors to copy into (double buffering);
     keys missing from it are allocated.  ``shared_group_video=True`` (charades / tacos batches, whose collate replicates
     the video of a group for each of its queries): every video crosses PCIe once; the batch gets
-    ``shared_group_video=True`` so that ``MESM.forward`` reads the clips of a pair from its group's first pair.  ``prepare_batch_input.last_h2d_bytes`` = host->device bytes this call enqueued."""
+    ``shared_group_video=True`` so that ``MESM.forward`` reads the clips of a pair from its group's first pair.  ``relay``
+    (optional, ``mesm_b200.relay.IngestRelay``; needs ``out`` and ``shared_group_video``): part of the videos reaches this GPU
+    through a peer GPU's host link and NVLink.  ``prepare_batch_input.last_h2d_bytes`` = host->device bytes this call enqueued."""
     from .utils import span_xx_to_cxw
     device = torch.device(device)
     out = out or {}
@@ -126,8 +128,12 @@ def prepare_batch_input(batched_data, device, non_blocking=False, out=None, shar
     if ragged:
         host_mask = batched_data["video_mask"]
         shared = bool(shared_group_video) and "num_clips" in batched_data
-        f, m, n = upload_clips(batched_data["video_feat"], batched_data["video_mask"], device, out.get("video_feat"),
-                               out.get("video_mask"), batched_data["num_clips"] if shared else None, non_blocking=non_blocking)
+        if relay is not None and shared and out.get("video_feat") is not None and out.get("video_mask") is not None:
+            f, m, n = relay.upload(batched_data["video_feat"].contiguous(), batched_data["video_mask"].contiguous(), out["video_feat"],
+                                   out["video_mask"], batched_data["num_clips"], non_blocking=non_blocking)
+        else:
+            f, m, n = upload_clips(batched_data["video_feat"], batched_data["video_mask"], device, out.get("video_feat"),
+                                   out.get("video_mask"), batched_data["num_clips"] if shared else None, non_blocking=non_blocking)
         if shared:
             batched_data["shared_group_video"] = True
         batched_data["video_feat"], batched_data["video_mask"] = f, m

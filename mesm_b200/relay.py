@@ -1,0 +1,150 @@
+"""NVLink-assisted host -> device ingest for multi-GPU nodes whose GPUs do not get equal host bandwidth.
+
+On the 8 x B200 boxes this was measured on (profiles/r2_h2d_probe_n8.md) four GPUs receive 22.7 GB/s from the host and the
+other four 35.5 GB/s when all eight ranks upload at once; one step of the benchmark moves 1.4 GB per GPU, so the slow ranks
+are copy-bound (65 ms against 55 ms of kernels) and, under max-over-ranks timing, so is the node.  A rank on a slow link can
+send part of its rows over a FAST peer's link instead: pinned host -> staging buffer on the peer GPU (that GPU's PCIe link),
+then peer GPU -> own GPU over NVLink.  Every byte still crosses PCIe exactly once.  Both hops are plain copies issued by
+THIS process on streams of the peer device (no kernel is launched there, so the peer rank's compute is not time-sliced), no
+inter-process communication is involved, and the result in the destination tensor is bit-identical to a direct upload.
+
+``plan_ingest_relay`` probes the links (all ranks at once), pairs the slowest ranks with the fastest and returns an
+``IngestRelay`` for the ranks that should offload (None elsewhere, and everywhere when the links are symmetric).
+``prepare_batch_input(..., relay=...)`` / ``IngestRelay.upload`` are drop-ins for the direct ragged upload.
+"""
+import torch
+
+from . import ingest
+
+
+class IngestRelay:
+    def __init__(self, device, relay_device, fraction, staging_bytes, nbuf=3):
+        self.device, self.relay_device = torch.device(device), torch.device(relay_device)
+        if self.device == self.relay_device:
+            raise ValueError("the relay device must be another GPU")
+        self.fraction = float(fraction)
+        self.h2d_stream = torch.cuda.Stream(device=self.relay_device)            # host -> peer GPU, then peer GPU -> own GPU
+        self.dst_stream = torch.cuda.Stream(device=self.device, priority=-1)     # own-GPU side of the peer copies
+        self.staging = [torch.empty(int(staging_bytes), dtype=torch.uint8, device=self.relay_device) for _ in range(nbuf)]
+        self.free = [torch.cuda.Event() for _ in range(nbuf)]
+        for e in self.free:
+            e.record(self.h2d_stream)
+        self.k = 0
+        self.last_relayed_bytes = 0
+
+    def describe(self):
+        return {"relay_device": str(self.relay_device), "fraction": round(self.fraction, 3)}
+
+    def upload(self, video_feat, video_mask, out_feat, out_mask, num_clips, non_blocking=True):
+        """``ingest.upload_clips(video_feat, video_mask, out_feat=..., out_mask=..., num_clips=...)`` on the current stream of
+        ``out_feat``'s device, with the videos of the LAST groups of the batch (about ``fraction`` of the valid clip rows)
+        routed through the relay GPU.  Returns (out_feat, out_mask, bytes crossing PCIe)."""
+        nc = [int(x) for x in (num_clips.tolist() if torch.is_tensor(num_clips) else num_clips)]
+        B, L, Dv = video_feat.shape
+        n_valid = ingest.clip_counts(video_mask).tolist()
+        first, b = [], 0
+        for c in nc:
+            first.append(b)
+            b += c
+        if b != B:
+            raise ValueError("IngestRelay.upload: num_clips does not cover the batch")
+        rows = [n_valid[f] for f in first]
+        total = sum(rows)
+        esz = video_feat.element_size()
+        stg = self.staging[self.k % len(self.staging)]
+        # relayed groups: from the end of the batch, up to `fraction` of the rows and the staging capacity
+        budget_rows = min(int(total * self.fraction), stg.numel() // (Dv * esz))
+        Gd, acc = len(nc), 0
+        while Gd > 1 and acc + rows[Gd - 1] <= budget_rows:
+            Gd -= 1
+            acc += rows[Gd]
+        if Gd == len(nc):                                   # nothing fits: plain direct upload
+            self.last_relayed_bytes = 0
+            return ingest.upload_clips(video_feat, video_mask, out_feat=out_feat, out_mask=out_mask, num_clips=nc, non_blocking=non_blocking)
+        Bd = first[Gd]
+        cur = torch.cuda.current_stream(self.device)
+        # direct part on the caller's stream (uploads, zero fill, mask, the shared-video guard) ...
+        _, _, n_direct = ingest.upload_clips(video_feat[:Bd], video_mask[:Bd], out_feat=out_feat[:Bd], out_mask=out_mask[:Bd],
+                                             num_clips=nc[:Gd], non_blocking=non_blocking)
+        # ... mask and zero fill of the relayed pairs (their pad rows must be zero; the peer copies below overwrite the valid rows)
+        with torch.cuda.stream(cur):
+            vm = video_mask[Bd:]
+            out_mask[Bd:].copy_(vm if vm.dtype == torch.bool else vm != 0, non_blocking=non_blocking)
+            out_feat[Bd:].zero_()
+            zeroed = torch.cuda.Event()
+            zeroed.record(cur)
+        self.dst_stream.wait_event(zeroed)
+        self.h2d_stream.wait_event(self.free[self.k % len(self.free)])       # the staging buffer's previous contents have been forwarded
+        segs, off = [], 0
+        with torch.cuda.stream(self.h2d_stream):                              # (makes the relay device current for these copies)
+            for g in range(Gd, len(nc)):
+                n = rows[g]
+                if n == 0:
+                    continue
+                nbytes = n * Dv * esz
+                seg = stg[off:off + nbytes].view(video_feat.dtype).view(n, Dv)
+                seg.copy_(video_feat[first[g], :n], non_blocking=True)        # host -> peer GPU over the peer's PCIe link
+                segs.append((first[g], n, seg))
+                off += (nbytes + 255) & ~255
+            # peer GPU -> own GPU over NVLink: torch runs a cross-device copy on the SOURCE device's current stream (h2d_stream, so
+            # behind the uploads above) and makes the destination device's current stream wait for it
+            with torch.cuda.stream(self.dst_stream):
+                for b0, n, seg in segs:
+                    out_feat[b0, :n].copy_(seg, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self.dst_stream)
+            self.free[self.k % len(self.free)].record(self.h2d_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.h2d_stream)
+            ingest._inflight.append((ev, (video_feat, video_mask)))          # the pinned sources stay alive until the DMA has read them
+        cur.wait_event(done)
+        if not non_blocking:
+            cur.synchronize()
+        self.k += 1
+        relayed = sum(n for _, n, _ in segs) * Dv * esz
+        self.last_relayed_bytes = relayed
+        return out_feat, out_mask, n_direct + relayed + (B - Bd) * L
+
+
+def probe_h2d_gbs(device, nbytes=256 << 20, reps=4):
+    """Host -> device bandwidth of this rank's link right now (call it on every rank at the same time)."""
+    dev = torch.device(device)
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        d.copy_(h, non_blocking=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        e1.record(s)
+    e1.synchronize()
+    return reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+def plan_ingest_relay(local_rank, dist, staging_bytes, nbuf=3, min_ratio=1.15, max_fraction=0.3, force_fraction=None):
+    """Single node, one rank per GPU.  Returns (IngestRelay or None, info dict).  The slowest rank is paired with the fastest, the
+    second slowest with the second fastest, ...; a pair is used when the fast link has at least ``min_ratio`` times the
+    bandwidth of the slow one, and the slow rank then offloads the share of its rows that equalises the two links' load."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", local_rank)
+    dist.barrier()
+    bw = probe_h2d_gbs(dev)
+    t = torch.zeros(world, 2, device=dev)
+    t[rank, 0], t[rank, 1] = bw, float(local_rank)
+    dist.all_reduce(t)
+    bws, locs = t[:, 0].tolist(), [int(x) for x in t[:, 1].tolist()]
+    order = sorted(range(world), key=lambda r: bws[r])
+    info = {"h2d_gbs": [round(x, 1) for x in bws], "pairs": []}
+    relay = None
+    for i in range(world // 2):
+        slow, fast = order[i], order[world - 1 - i]
+        ratio = bws[fast] / max(bws[slow], 1e-9)
+        if force_fraction is None and ratio < min_ratio:
+            continue
+        f = force_fraction if force_fraction is not None else min(max_fraction, (bws[fast] - bws[slow]) / (bws[fast] + bws[slow]))
+        info["pairs"].append({"rank": slow, "via_rank": fast, "fraction": round(f, 3)})
+        if rank == slow and f > 0:
+            relay = IngestRelay(dev, torch.device("cuda", locs[fast]), f, staging_bytes, nbuf)
+    return relay, info

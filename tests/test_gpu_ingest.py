@@ -194,3 +194,36 @@ def test_fp16_feature_storage_upload_and_forward(shared):
         assert rel_err(out[k], gold[k], vm) <= 1e-3, k
     assert rel_err(out["projed_video_feat"][:, 0], gold["projed_video_row0"]) <= 1e-3
     assert model._eng.last_feature_bytes == rows * Dv * 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs a second GPU to relay through")
+def test_relayed_upload_is_bit_identical_to_the_direct_one():
+    """mesm_b200.relay: part of the videos reaches GPU 0 through GPU 1's host link and a peer copy; same bits, pad rows zero."""
+    import mesm_b200
+    from mesm_b200.relay import IngestRelay
+    g = torch.Generator().manual_seed(11)
+    nc = [1, 3, 2, 1, 4, 2, 3]
+    B, L, Dv = sum(nc), 23, 130
+    lens_g = torch.randint(5, L + 1, (len(nc),), generator=g)
+    lens = torch.repeat_interleave(lens_g, torch.tensor(nc))
+    mask = torch.arange(L)[None] < lens[:, None]
+    vg = torch.randn(len(nc), L, Dv, generator=g).half()
+    vf = (torch.repeat_interleave(vg, torch.tensor(nc), dim=0) * mask[..., None]).contiguous().pin_memory()
+    mask = mask.pin_memory()
+    dev = torch.device("cuda", 0)
+    ref_f = torch.full((B, L, Dv), 7.0, dtype=torch.float16, device=dev)
+    ref_m = torch.zeros(B, L, dtype=torch.bool, device=dev)
+    mesm_b200.upload_clips(vf, mask, out_feat=ref_f, out_mask=ref_m, num_clips=nc)
+    relay = IngestRelay(dev, torch.device("cuda", 1), 0.5, 1 << 20, nbuf=2)
+    first = torch.cumsum(torch.tensor([0] + nc[:-1]), 0)
+    for rep in range(5):                                  # more calls than staging buffers
+        out_f = torch.full((B, L, Dv), 7.0, dtype=torch.float16, device=dev)
+        out_m = torch.zeros(B, L, dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            batch = mesm_b200.prepare_batch_input(dict(video_feat=vf, video_mask=mask, num_clips=torch.tensor(nc)), dev, non_blocking=True,
+                                                  out=dict(video_feat=out_f, video_mask=out_m), shared_group_video=True, relay=relay)
+        torch.cuda.synchronize(dev)
+        assert relay.last_relayed_bytes > 0
+        assert torch.equal(out_m, ref_m)
+        assert torch.equal(out_f[first], ref_f[first])    # the rows the forward reads (first pair of every group)
+        assert batch["video_len"].tolist() == lens.tolist()
