@@ -706,7 +706,7 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             t_ = time.perf_counter()
-            e2e_stream(3 * nsub)
+            e2e_stream(4 * nsub)
             torch.cuda.synchronize()
             tt = torch.tensor([time.perf_counter() - t_], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -26,9 +26,10 @@ class IngestRelay:
         self.h2d_stream = torch.cuda.Stream(device=self.relay_device)            # host -> peer GPU, then peer GPU -> own GPU
         self.dst_stream = torch.cuda.Stream(device=self.device, priority=-1)     # own-GPU side of the peer copies
         self.staging = [torch.empty(int(staging_bytes), dtype=torch.uint8, device=self.relay_device) for _ in range(nbuf)]
+        self.landing = [torch.empty(int(staging_bytes), dtype=torch.uint8, device=self.device) for _ in range(nbuf)]
         self.free = [torch.cuda.Event() for _ in range(nbuf)]
         for e in self.free:
-            e.record(self.h2d_stream)
+            e.record(self.dst_stream)
         self.k = 0
         self.last_relayed_bytes = 0
 
@@ -63,45 +64,52 @@ class IngestRelay:
             return ingest.upload_clips(video_feat, video_mask, out_feat=out_feat, out_mask=out_mask, num_clips=nc, non_blocking=non_blocking)
         Bd = first[Gd]
         cur = torch.cuda.current_stream(self.device)
-        # direct part on the caller's stream (uploads, zero fill, mask, the shared-video guard) ...
-        _, _, n_direct = ingest.upload_clips(video_feat[:Bd], video_mask[:Bd], out_feat=out_feat[:Bd], out_mask=out_mask[:Bd],
-                                             num_clips=nc[:Gd], non_blocking=non_blocking)
-        # ... mask and zero fill of the relayed pairs (their pad rows must be zero; the peer copies below overwrite the valid rows)
+        slot = self.k % len(self.staging)
+        # mask and zero fill of the relayed pairs first (their pad rows must be zero; the scatter below writes the valid rows) ...
         with torch.cuda.stream(cur):
             vm = video_mask[Bd:]
             out_mask[Bd:].copy_(vm if vm.dtype == torch.bool else vm != 0, non_blocking=non_blocking)
             out_feat[Bd:].zero_()
             zeroed = torch.cuda.Event()
             zeroed.record(cur)
-        self.dst_stream.wait_event(zeroed)
-        self.h2d_stream.wait_event(self.free[self.k % len(self.free)])       # the staging buffer's previous contents have been forwarded
-        segs, off = [], 0
-        with torch.cuda.stream(self.h2d_stream):                              # (makes the relay device current for these copies)
+        # ... then the direct part on the caller's stream (uploads, zero fill, mask, the shared-video guard)
+        _, _, n_direct = ingest.upload_clips(video_feat[:Bd], video_mask[:Bd], out_feat=out_feat[:Bd], out_mask=out_mask[:Bd],
+                                             num_clips=nc[:Gd], non_blocking=non_blocking)
+        # relayed part: valid rows of the groups' first pairs, compacted: host -> staging on the peer GPU (its PCIe link), ONE peer
+        # copy staging -> landing buffer on this GPU (NVLink), one scatter kernel landing -> rows of the padded tensor
+        nrows = acc
+        stg2 = stg[:nrows * Dv * esz].view(video_feat.dtype).view(nrows, Dv)
+        land2 = self.landing[slot][:nrows * Dv * esz].view(video_feat.dtype).view(nrows, Dv)
+        idx = torch.empty(nrows, dtype=torch.int64).pin_memory()
+        self.h2d_stream.wait_event(self.free[slot])                          # staging / landing of this slot have been consumed
+        with torch.cuda.stream(self.h2d_stream):                             # (makes the relay device current for these copies)
+            off = 0
             for g in range(Gd, len(nc)):
                 n = rows[g]
                 if n == 0:
                     continue
-                nbytes = n * Dv * esz
-                seg = stg[off:off + nbytes].view(video_feat.dtype).view(n, Dv)
-                seg.copy_(video_feat[first[g], :n], non_blocking=True)        # host -> peer GPU over the peer's PCIe link
-                segs.append((first[g], n, seg))
-                off += (nbytes + 255) & ~255
-            # peer GPU -> own GPU over NVLink: torch runs a cross-device copy on the SOURCE device's current stream (h2d_stream, so
-            # behind the uploads above) and makes the destination device's current stream wait for it
+                stg2[off:off + n].copy_(video_feat[first[g], :n], non_blocking=True)
+                idx[off:off + n] = torch.arange(first[g] * L, first[g] * L + n)
+                off += n
             with torch.cuda.stream(self.dst_stream):
-                for b0, n, seg in segs:
-                    out_feat[b0, :n].copy_(seg, non_blocking=True)
+                self.dst_stream.wait_event(zeroed)
+                idx_d = idx.to(self.device, non_blocking=True)
+                # torch runs a cross-device copy on the SOURCE device's current stream (h2d_stream: behind the uploads above) and makes
+                # the destination device's current stream (dst_stream) wait for it
+                land2.copy_(stg2, non_blocking=True)
+                out_feat.view(B * L, Dv).index_copy_(0, idx_d, land2)
                 done = torch.cuda.Event()
                 done.record(self.dst_stream)
-            self.free[self.k % len(self.free)].record(self.h2d_stream)
+                self.free[slot].record(self.dst_stream)
             ev = torch.cuda.Event()
             ev.record(self.h2d_stream)
             ingest._inflight.append((ev, (video_feat, video_mask)))          # the pinned sources stay alive until the DMA has read them
+        ingest._inflight.append((done, (idx, idx_d)))
         cur.wait_event(done)
         if not non_blocking:
             cur.synchronize()
         self.k += 1
-        relayed = sum(n for _, n, _ in segs) * Dv * esz
+        relayed = nrows * Dv * esz
         self.last_relayed_bytes = relayed
         return out_feat, out_mask, n_direct + relayed + (B - Bd) * L
 
