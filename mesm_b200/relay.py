@@ -143,16 +143,25 @@ def plan_ingest_relay(local_rank, dist, staging_bytes, nbuf=3, min_ratio=1.15, m
     t[rank, 0], t[rank, 1] = bw, float(local_rank)
     dist.all_reduce(t)
     bws, locs = t[:, 0].tolist(), [int(x) for x in t[:, 1].tolist()]
-    order = sorted(range(world), key=lambda r: bws[r])
-    info = {"h2d_gbs": [round(x, 1) for x in bws], "pairs": []}
+    info = {"h2d_gbs": [round(x, 1) for x in bws], "pairs": pair_links(bws, min_ratio, max_fraction, force_fraction)}
     relay = None
+    for pr in info["pairs"]:
+        if rank == pr["rank"] and pr["fraction"] > 0:
+            relay = IngestRelay(dev, torch.device("cuda", locs[pr["via_rank"]]), pr["fraction"], staging_bytes, nbuf)
+    return relay, info
+
+
+def pair_links(bws, min_ratio=1.15, max_fraction=0.3, force_fraction=None):
+    """Pairs of (slow rank, fast rank, share of the slow rank's rows to send through the fast rank's link) from the per-rank
+    host -> device bandwidths: slowest with fastest, second slowest with second fastest, ...  With loads equal before the
+    split, x = (f - s) / (f + s) makes both links finish together ((1 - x) / s = (1 + x) / f)."""
+    world = len(bws)
+    order = sorted(range(world), key=lambda r: (bws[r], r))
+    pairs = []
     for i in range(world // 2):
         slow, fast = order[i], order[world - 1 - i]
-        ratio = bws[fast] / max(bws[slow], 1e-9)
-        if force_fraction is None and ratio < min_ratio:
+        if force_fraction is None and bws[fast] < min_ratio * max(bws[slow], 1e-9):
             continue
         f = force_fraction if force_fraction is not None else min(max_fraction, (bws[fast] - bws[slow]) / (bws[fast] + bws[slow]))
-        info["pairs"].append({"rank": slow, "via_rank": fast, "fraction": round(f, 3)})
-        if rank == slow and f > 0:
-            relay = IngestRelay(dev, torch.device("cuda", locs[fast]), f, staging_bytes, nbuf)
-    return relay, info
+        pairs.append({"rank": slow, "via_rank": fast, "fraction": round(float(f), 3)})
+    return pairs

@@ -143,3 +143,17 @@ def test_header_and_binding_agree_on_struct_layouts():
     assert fields("mesm_cfg") == [f[0] for f in _lib.MesmCfg._fields_]
     assert fields("mesm_outputs") == [f[0] for f in _lib.MesmOutputs._fields_]
     assert fields("mesm_decode_params") == [f[0] for f in _lib.MesmDecodeParams._fields_]
+
+
+def test_relay_pairing_of_asymmetric_host_links():
+    """mesm_b200.relay.pair_links: slowest rank with fastest, share that equalises the two links; symmetric nodes get no relay."""
+    from mesm_b200.relay import pair_links
+    assert pair_links([55.5, 55.6]) == []
+    assert pair_links([36.0, 35.0, 36.5, 35.5]) == []
+    pairs = pair_links([23.3, 23.3, 28.8, 28.5, 36.2, 36.3, 38.6, 39.7])
+    assert [(p["rank"], p["via_rank"]) for p in pairs] == [(0, 7), (1, 6), (3, 5), (2, 4)]
+    for p, (s, f) in zip(pairs, [(23.3, 39.7), (23.3, 38.6), (28.5, 36.3), (28.8, 36.2)]):
+        x = p["fraction"]
+        assert abs((1 - x) / s - (1 + x) / f) < 2e-4          # both links finish together
+    assert all(p["fraction"] <= 0.3 for p in pair_links([10.0, 40.0]))
+    assert pair_links([50.0, 50.0], force_fraction=0.2) == [{"rank": 0, "via_rank": 1, "fraction": 0.2}]
