@@ -152,6 +152,12 @@ int mesm_upload_clips_f16(const void* host_feat, const uint8_t* host_mask, int32
                           void* dev_feat, uint8_t* dev_mask, const int64_t* num_clips, int32_t G, int64_t* bytes_copied,
                           void* stream);
 
+/* n host -> device copies in ONE submission (cudaMemcpyBatchAsync when the runtime has it, else a loop of cudaMemcpyAsync):
+ * dst[i] <- src[i], bytes[i] each; src pinned host memory, dst on the device the stream belongs to (the current device).
+ * Part of the prepare_batch_input replacement (dataset/base.py:358-363): the relayed upload of mesm_b200/relay.py stages the
+ * per-video row slabs of a batch on a peer GPU with it. */
+int mesm_memcpy_batch_h2d(const void* const* src, void* const* dst, const size_t* bytes, int64_t n, void* stream);
+
 /* ---- CLIP text tower: replaces CLIPTextEncoder.forward (model/text_encoder.py:240-354), called by MESM.CLIP_encode_text
  * (model/model.py:103-109).  State-dict keys as in the reference: token_embedding.weight [vocab,width], positional_embedding
  * [context,width], transformer.resblocks.N.{ln_1,ln_2}.{weight,bias}, .attn.in_proj_{weight [3w,w],bias}, .attn.out_proj.*,

@@ -57,6 +57,7 @@ SYMBOLS = {
                                   POINTER(c_int64), c_void_p]),
     "mesm_upload_clips_f16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64), c_int32,
                                       POINTER(c_int64), c_void_p]),
+    "mesm_memcpy_batch_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mesm_clip_create": (c_void_p, [c_int32] * 7),
     "mesm_clip_destroy": (None, [c_void_p]),
     "mesm_clip_last_error": (c_char_p, [c_void_p]),

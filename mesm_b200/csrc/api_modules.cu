@@ -170,6 +170,21 @@ int mesm_upload_clips_f16(const void* host_feat, const uint8_t* host_mask, int32
     return upload_clips_impl((const uint8_t*)host_feat, host_mask, B, L, Dv, 2, (uint8_t*)dev_feat, dev_mask, num_clips, G, bytes_copied, stream);
 }
 
+int mesm_memcpy_batch_h2d(const void* const* src, void* const* dst, const size_t* bytes, int64_t n, void* stream) {
+    mesm_ctx* ctx = nullptr;
+    if (n < 0 || (n > 0 && (!src || !dst || !bytes))) return fail(ctx, 1, "mesm_memcpy_batch_h2d: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<void*> d, h;
+    std::vector<size_t> sz;
+    for (int64_t i = 0; i < n; ++i)
+        if (bytes[i]) { d.push_back(dst[i]); h.push_back(const_cast<void*>(src[i])); sz.push_back(bytes[i]); }
+    if (d.empty()) return 0;
+    if (use_memcpy_batch() && memcpy_batch_h2d(d, h, sz, s) == cudaSuccess) return 0;
+    (void)cudaGetLastError();
+    for (size_t i = 0; i < d.size(); ++i) CK(cudaMemcpyAsync(d[i], h[i], sz[i], cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
 size_t mesm_mha_workspace_bytes(int32_t L, int32_t S, int32_t B, int32_t E, int32_t Ev) {
     (void)S; (void)E;
     const size_t Kp = ((size_t)Ev + 15) / 16 * 16, ldw = ((size_t)Ev + 3) / 4 * 4;

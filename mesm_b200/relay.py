@@ -12,9 +12,14 @@ inter-process communication is involved, and the result in the destination tenso
 ``IngestRelay`` for the ranks that should offload (None elsewhere, and everywhere when the links are symmetric).
 ``prepare_batch_input(..., relay=...)`` / ``IngestRelay.upload`` are drop-ins for the direct ragged upload.
 """
+import ctypes
+
+import numpy as np
 import torch
 
-from . import ingest
+from . import _lib, ingest
+from ._lib import check
+from .engine import _stream
 
 
 class IngestRelay:
@@ -80,17 +85,21 @@ class IngestRelay:
         nrows = acc
         stg2 = stg[:nrows * Dv * esz].view(video_feat.dtype).view(nrows, Dv)
         land2 = self.landing[slot][:nrows * Dv * esz].view(video_feat.dtype).view(nrows, Dv)
-        idx = torch.empty(nrows, dtype=torch.int64).pin_memory()
+        # one batched submission of the per-video host -> staging copies, destination rows of the scatter (both built vectorised: the
+        # thread that runs this also enqueues the forward passes)
+        gi = [g for g in range(Gd, len(nc)) if rows[g] > 0]
+        n_g = torch.tensor([rows[g] for g in gi], dtype=torch.int64)
+        f_g = torch.tensor([first[g] for g in gi], dtype=torch.int64)
+        start_g = torch.cumsum(n_g, 0) - n_g
+        rowb = Dv * esz
+        src_p = (video_feat.data_ptr() + f_g * (L * rowb)).numpy().astype(np.uint64)
+        dst_p = (stg.data_ptr() + start_g * rowb).numpy().astype(np.uint64)
+        size_p = (n_g * rowb).numpy().astype(np.uint64)
+        idx = (torch.repeat_interleave(f_g * L - start_g, n_g) + torch.arange(nrows)).pin_memory()
         self.h2d_stream.wait_event(self.free[slot])                          # staging / landing of this slot have been consumed
         with torch.cuda.stream(self.h2d_stream):                             # (makes the relay device current for these copies)
-            off = 0
-            for g in range(Gd, len(nc)):
-                n = rows[g]
-                if n == 0:
-                    continue
-                stg2[off:off + n].copy_(video_feat[first[g], :n], non_blocking=True)
-                idx[off:off + n] = torch.arange(first[g] * L, first[g] * L + n)
-                off += n
+            check(_lib.lib().mesm_memcpy_batch_h2d(src_p.ctypes.data_as(ctypes.c_void_p), dst_p.ctypes.data_as(ctypes.c_void_p),
+                                                   size_p.ctypes.data_as(ctypes.c_void_p), len(gi), _stream()))
             with torch.cuda.stream(self.dst_stream):
                 self.dst_stream.wait_event(zeroed)
                 idx_d = idx.to(self.device, non_blocking=True)
