@@ -711,9 +711,17 @@ def main():
             tt = torch.tensor([time.perf_counter() - t_], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt)
-        t_off, t_on = timed(False), timed(True)
-        relay_info["trial_s"] = {"direct": round(t_off, 4), "relayed": round(t_on, 4)}
+        def timed_mode(batched):
+            if relay is not None:
+                relay.batched = batched
+            return timed(True)
+        t_off, t_b, t_c = timed(False), timed_mode(True), timed_mode(False)
+        relay_info["trial_s"] = {"direct": round(t_off, 4), "relayed_batched_copies": round(t_b, 4), "relayed_single_copies": round(t_c, 4)}
+        t_on = min(t_b, t_c)
         relay_info["used"] = bool(t_on < 0.98 * t_off)
+        relay_info["mode"] = "batched" if t_b <= t_c else "single"
+        if relay is not None:
+            relay.batched = t_b <= t_c
         use_relay[0] = relay_info["used"] and relay is not None
     elif relay_info is not None:
         relay_info["used"] = False

@@ -37,6 +37,7 @@ class IngestRelay:
             e.record(self.dst_stream)
         self.k = 0
         self.last_relayed_bytes = 0
+        self.batched = True          # per-video staging copies in one cudaMemcpyBatchAsync submission (False: one cudaMemcpyAsync each)
 
     def describe(self):
         return {"relay_device": str(self.relay_device), "fraction": round(self.fraction, 3)}
@@ -98,8 +99,12 @@ class IngestRelay:
         idx = (torch.repeat_interleave(f_g * L - start_g, n_g) + torch.arange(nrows)).pin_memory()
         self.h2d_stream.wait_event(self.free[slot])                          # staging / landing of this slot have been consumed
         with torch.cuda.stream(self.h2d_stream):                             # (makes the relay device current for these copies)
-            check(_lib.lib().mesm_memcpy_batch_h2d(src_p.ctypes.data_as(ctypes.c_void_p), dst_p.ctypes.data_as(ctypes.c_void_p),
-                                                   size_p.ctypes.data_as(ctypes.c_void_p), len(gi), _stream()))
+            if self.batched:
+                check(_lib.lib().mesm_memcpy_batch_h2d(src_p.ctypes.data_as(ctypes.c_void_p), dst_p.ctypes.data_as(ctypes.c_void_p),
+                                                       size_p.ctypes.data_as(ctypes.c_void_p), len(gi), _stream()))
+            else:
+                for g, s0, n in zip(gi, start_g.tolist(), n_g.tolist()):
+                    stg2[s0:s0 + n].copy_(video_feat[first[g], :n], non_blocking=True)
             with torch.cuda.stream(self.dst_stream):
                 self.dst_stream.wait_event(zeroed)
                 idx_d = idx.to(self.device, non_blocking=True)

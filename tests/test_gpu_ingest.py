@@ -217,6 +217,7 @@ def test_relayed_upload_is_bit_identical_to_the_direct_one():
     relay = IngestRelay(dev, torch.device("cuda", 1), 0.5, 1 << 20, nbuf=2)
     first = torch.cumsum(torch.tensor([0] + nc[:-1]), 0)
     for rep in range(5):                                  # more calls than staging buffers
+        relay.batched = rep % 2 == 0                      # batched submission / one copy per video
         out_f = torch.full((B, L, Dv), 7.0, dtype=torch.float16, device=dev)
         out_m = torch.zeros(B, L, dtype=torch.bool, device=dev)
         with torch.cuda.device(dev):
