@@ -7,14 +7,17 @@
 // phases (stage operands -> MMA -> TMEM -> softmax -> P to shared memory -> MMA -> TMEM -> store) at 11 % tensor-pipe and 15 % DRAM
 // utilisation.  Here every warp owns 16 query rows end to end and never talks to another warp while it computes:
 //     S = Q K^T       mma.sync m16n8k16, bf16x3 split operands (Qhi Khi + Qlo Khi + Qhi Klo), fp32 scores in registers
-//     online softmax  64 keys per step, exp2 of the scores scaled by log2(e) / sqrt(32)
+//     online softmax  32 or 64 keys per step (register budget of the variant), exp2 of the scores scaled by log2(e) / sqrt(32)
 //     O += P V        the score fragments ARE the A fragments of the next MMA (no shared-memory round trip), bf16x3 again
 // K / V of one head sit in shared memory as bf16 hi / lo planes, [key][32 dims] = 64-byte rows with the 16-byte chunks XOR-swizzled
 // by (key >> 1) & 3 so that ldmatrix (K) and ldmatrix.trans (V) are conflict-free without padding.
 //
-// One CTA per (pair, head) converts K / V of the head from fp32 itself (feeding the kernel pre-split planes through cp.async
-// was measured SLOWER: 1549 vs 1307 us per 4096 x 147-row launch - 64-byte plane segments instead of 128-byte fp32 lines - and a
-// persistent double-buffered variant slower still, 2772 us: each (pair, head) item is too short to hide its own Q loads).
+//   attn_mma_kernel        encoder self-attention: one CTA per (pair, head) converts K / V of the head from fp32 itself (feeding the
+//                          kernel pre-split planes through cp.async was measured SLOWER: 1549 vs 1307 us per 4096 x 147-row launch -
+//                          64-byte plane segments instead of 128-byte fp32 lines - and a persistent double-buffered variant slower
+//                          still, 2772 us: each (pair, head) item is too short to hide its own Q loads)
+//   attn_mma_heads_kernel  T2V cross-attention (<= 64 keys): one CTA per pair, warp = head
+//   dec_cross_mma_kernel   decoder cross- / self-attention (<= 16 queries): B fragments straight from global memory
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <math_constants.h>
