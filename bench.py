@@ -746,6 +746,8 @@ def main():
                     "note": f"{nsub} sub-batches of {Bs} pairs per step, {e2e_steps} steps streamed back to back; pinned host -> device ingest up to {NB} sub-batches ahead ({NB} device buffers) on a copy stream through mesm_b200.prepare_batch_input ({'zero-padded tensor copied whole' if padded else 'valid clip rows only, pad rows zero-filled on the device' + ('; the video a group of queries shares (replicated by the collate step, dataset/base.py:307-309) crosses PCIe once' if shared else '')}), windows + keep sets back to host", "h2d_padded_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()) * nsub},
             "gpu_launches": int(launches), "roofline": roof, "topk_gathered": int(top.shape[0])}
     if relay_info is not None:
+        if relay is not None:
+            relay_info["this_rank"] = relay.describe()
         line["e2e"]["ingest_relay"] = relay_info
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

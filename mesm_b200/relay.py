@@ -37,12 +37,24 @@ class IngestRelay:
             e.record(self.dst_stream)
         self.k = 0
         self.last_relayed_bytes = 0
+        self.broken = None           # set to the error text when the relay path failed once (direct uploads from then on)
         self.batched = True          # per-video staging copies in one cudaMemcpyBatchAsync submission (False: one cudaMemcpyAsync each)
 
     def describe(self):
-        return {"relay_device": str(self.relay_device), "fraction": round(self.fraction, 3)}
+        return {"relay_device": str(self.relay_device), "fraction": round(self.fraction, 3), "broken": self.broken}
 
     def upload(self, video_feat, video_mask, out_feat, out_mask, num_clips, non_blocking=True):
+        """Relayed upload (see ``_upload``); any host-side failure of the relay path (allocation, peer access, a missing symbol)
+        disables the relay for the rest of the run and falls back to the direct upload of the whole batch."""
+        if not self.broken:
+            try:
+                return self._upload(video_feat, video_mask, out_feat, out_mask, num_clips, non_blocking)
+            except Exception as e:                              # noqa: BLE001 - the direct path always works
+                self.broken = f"{type(e).__name__}: {e}"
+        self.last_relayed_bytes = 0
+        return ingest.upload_clips(video_feat, video_mask, out_feat=out_feat, out_mask=out_mask, num_clips=num_clips, non_blocking=non_blocking)
+
+    def _upload(self, video_feat, video_mask, out_feat, out_mask, num_clips, non_blocking=True):
         """``ingest.upload_clips(video_feat, video_mask, out_feat=..., out_mask=..., num_clips=...)`` on the current stream of
         ``out_feat``'s device, with the videos of the LAST groups of the batch (about ``fraction`` of the valid clip rows)
         routed through the relay GPU.  Returns (out_feat, out_mask, bytes crossing PCIe)."""
