@@ -66,6 +66,24 @@ cudaError_t launch_transpose_pack(const float* W, int row0, int nrows, int K, fl
 }  // namespace mesm
 namespace {
 
+// SS-MESM reconstructor (model/model.py:467-488) evaluated on the unprojected clips needs, per head h, qk_h = Wk_h^T q_h (32 -> 256) and
+// out_h = Wv_h pooled_h (256 -> 32).  As dense block-structured matrices both are ordinary linears over all heads at once:
+//   Wqk[(h, c), k] = (k / 32 == h) ? Wk[k, c] : 0      [8 * 256, 256]      qk[b, h, :] = Wqk q_b
+//   Wvo[n, (h, c)] = (n / 32 == h) ? Wv[n, c] : 0      [256, 8 * 256]      out_b      = Wvo pooled_b + bv
+// (7/8 of the MACs multiply zeros - 4 GFLOP per launch, nothing - but the launches move from the fp32 SIMT kernel to tcgen05).
+__global__ void recon_block_weights_kernel(const float* __restrict__ in_w, float* __restrict__ Wqk, float* __restrict__ Wvo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;            // 0 .. 8 * 256 * 256
+    if (i >= NH * D * D) return;
+    {   // Wqk row r = h * 256 + c, column k
+        const int r = i / D, k = i - r * D, h = r / D, c = r - h * D;
+        Wqk[i] = (k / HD == h) ? in_w[(long long)(D + k) * D + c] : 0.f;
+    }
+    {   // Wvo row n, column q = h * 256 + c
+        const int n = i / (NH * D), q = i - n * (NH * D), h = q / D, c = q - h * D;
+        Wvo[i] = (n / HD == h) ? in_w[(long long)(2 * D + n) * D + c] : 0.f;
+    }
+}
+
 struct Packer {
     mesm_ctx* ctx;
     cudaStream_t s;
@@ -127,6 +145,23 @@ struct Packer {
         return r;
     }
     PL lin(const std::string& p, int64_t N, int64_t K) { return pack(p + ".weight", p + ".bias", N, K, 0, (int)N); }
+    // a weight matrix built on the device (W [N, K] fp32 row-major, bias [N] or null): fp32 transposed copy + tcgen05 image
+    PL pack_dev(const float* W, const float* bias, int N, int K) {
+        PL r;
+        const int Kp = (K + 15) / 16 * 16, ldw = (N + 3) / 4 * 4;
+        float* Wt = alloc((size_t)Kp * ldw);
+        if (!Wt) return r;
+        const long long tot = (long long)Kp * ldw;
+        transpose_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(W, 0, N, K, nullptr, Wt, ldw, Kp);
+        r.Wt = Wt; r.ldw = ldw; r.K = K; r.N = N; r.bias = bias;
+        void* wp = nullptr;
+        cudaError_t e = cudaMalloc(&wp, tc_packed_bytes(N, K));
+        if (e != cudaSuccess) { ok = false; cerr = e; return r; }
+        ctx->owned.push_back(wp);
+        launch_pack_tc(W, 0, N, K, nullptr, wp, s);
+        r.Wp = wp;
+        return r;
+    }
     const float* bias_sum(const float* a, const float* b, int n) {
         if (!a || !b) return nullptr;
         float* o = alloc(n);
@@ -149,6 +184,15 @@ struct Packer {
         const Tensor* b = get(ib, {3 * D});
         L.in_w = W ? W->p : nullptr; L.in_b = b ? b->p : nullptr;
         if (recon) L.vT = L.v.Wt;
+        if (recon && W && b && D == 256) {
+            float* Wqk = alloc((size_t)NH * D * D);
+            float* Wvo = alloc((size_t)NH * D * D);
+            if (Wqk && Wvo) {
+                recon_block_weights_kernel<<<(NH * D * D + 255) / 256, 256, 0, s>>>(W->p, Wqk, Wvo);
+                L.blk_qk = pack_dev(Wqk, nullptr, NH * D, D);
+                L.blk_v = pack_dev(Wvo, b->p + 2 * D, D, NH * D);
+            }
+        }
         if (!recon && D == 256 && FF == 1024) {             // fused FFN kernel: weight slots in consumption order
             const Tensor* W1 = get(p + "linear1.weight", {FF, D});
             const Tensor* W2 = get(p + "linear2.weight", {D, FF});
@@ -462,6 +506,11 @@ ProfScope::~ProfScope() {
     if (!on) return;
     ProfRec r; r.a = a; cudaEventCreate(&r.b); cudaEventRecord(r.b, s); r.flops = flops; r.M = M; r.name = name;
     g_prof.push_back(r);
+}
+static int recon_blk() {               // MESM_RECON_BLOCK=0: per-head batched back-projections on the fp32 SIMT kernel
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MESM_RECON_BLOCK"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
 }
 static int force_simt() {
     static int v = -1;
@@ -987,7 +1036,9 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
         for (size_t l = 0; l < ctx->rec.size(); ++l) {
             const AttnFfn& L = ctx->rec[l];
             CK(Lin(B, L.q, S, D, p.rq, D).scale(kScale32).run(s));
-            {   // qk[b,h,:] = Wk_h^T q_h : per head [B,32] x [32,256]
+            if (L.blk_qk.Wp && recon_blk()) {   // qk[b,h,:] = Wk_h^T q_h for all heads: one dense GEMM on the block-structured weights
+                CK(Lin(B, L.blk_qk, p.rq, D, p.rqk, NH * D).run(s));
+            } else {                            // per head [B,32] x [32,256], batched over blockIdx.z (fp32 SIMT kernel)
                 PL w; w.Wt = L.in_w + (size_t)D * D; w.ldw = D; w.K = HD; w.N = D; w.bias = nullptr;
                 CK(Lin(B, w, p.rq, D, p.rqk, NH * D).batch(NH, HD, (long long)HD * D, 0, D).run(s));
             }
@@ -997,7 +1048,9 @@ extern "C" int mesm_forward(mesm_ctx* ctx, const mesm_inputs* in, const mesm_out
             ra.B = B; ra.Lv = Lv; ra.qvh = cf.qvh_grouping; ra.max_keys = recon_max_keys; ra.b0 = 0; ra.Btot = B;
             ra.x_start = d_cu;
             CK(launch_recon_pool(ra, s));
-            {   // attn_out[:, h*32:+32] = Wv_h pooled_h + bv_h
+            if (L.blk_v.Wp && recon_blk()) {    // attn_out = Wvo pooled + bv (all heads at once)
+                CK(Lin(B, L.blk_v, p.rpool, NH * D, p.rao, D).run(s));
+            } else {                            // attn_out[:, h*32:+32] = Wv_h pooled_h + bv_h
                 PL w; w.Wt = L.vT; w.ldw = L.v.ldw; w.K = D; w.N = HD; w.bias = L.v.bias;
                 CK(Lin(B, w, p.rpool, NH * D, p.rao, D).batch(NH, D, HD, HD, HD).run(s));
             }

@@ -34,6 +34,7 @@ struct AttnFfn {         // T2V / recon / encoder layer
     const float* in_w = nullptr;           // raw in_proj_weight [768,256] (recon back-projection uses row slices)
     const float* in_b = nullptr;
     const float* vT = nullptr;             // Wv^T packed [256,256] (recon)
+    PL blk_qk, blk_v;                      // recon back-projections as ONE dense GEMM each: block-structured weights [8*256, 256] / [256, 8*256]
     Norm n1, n2;
     const float* prelu = nullptr;
     const void* ffn_w1 = nullptr;          // fused-FFN weight images (ffn_tc.cu); null when the shape is not 256 / 1024
