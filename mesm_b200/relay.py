@@ -170,10 +170,20 @@ def plan_ingest_relay(local_rank, dist, staging_bytes, nbuf=3, min_ratio=1.15, m
     dist.all_reduce(t)
     bws, locs = t[:, 0].tolist(), [int(x) for x in t[:, 1].tolist()]
     info = {"h2d_gbs": [round(x, 1) for x in bws], "pairs": pair_links(bws, min_ratio, max_fraction, force_fraction)}
-    relay = None
-    for pr in info["pairs"]:
-        if rank == pr["rank"] and pr["fraction"] > 0:
-            relay = IngestRelay(dev, torch.device("cuda", locs[pr["via_rank"]]), pr["fraction"], staging_bytes, nbuf)
+    relay, err = None, None
+    try:
+        for pr in info["pairs"]:
+            if rank == pr["rank"] and pr["fraction"] > 0:
+                relay = IngestRelay(dev, torch.device("cuda", locs[pr["via_rank"]]), pr["fraction"], staging_bytes, nbuf)
+    except Exception as e:                                      # noqa: BLE001 - e.g. no memory for the staging buffers on the peer
+        relay, err = None, f"{type(e).__name__}: {e}"
+    # the decision has to be the same on every rank (the caller's trial runs collectives): one failure disables the relay for all
+    ok = torch.tensor([0.0 if err else 1.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) < 1.0:
+        info["disabled"] = err or "the relay could not be set up on another rank"
+        info["pairs"] = []
+        relay = None
     return relay, info
 
 
